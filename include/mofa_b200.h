@@ -1,0 +1,172 @@
+/*
+ * mofa_b200.h -- C ABI of libmofa_b200.so, the sm_100a kernel library behind the MOFA-Video hot path
+ * (SVD denoise loop + MOFA-Adapter/FlowControlNet + flow warp).
+ *
+ * The reference has no FFI layer of its own: its one native boundary is the CuPy launch of the
+ * softsplat CUDA string with raw data_ptr()s on torch's current stream
+ * (/root/reference/MOFA-Video-Traj/models/softsplat.py:219-226, 340-345).  Every entry point here
+ * follows the same contract: raw device pointers owned by the caller (PyTorch's allocator), plain
+ * sizes, a caller-supplied cudaStream_t, no device allocation, no synchronisation, int return
+ * (0 = ok, negative = error, text via mofa_last_error()).  Each op cites the reference code whose
+ * arithmetic it replaces.  All activations are fp16, channels-last ("NHWC": [frames, h*w, C]).
+ */
+#ifndef MOFA_B200_H
+#define MOFA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mofa_stream_t; /* cudaStream_t */
+
+#define MOFA_OK 0
+#define MOFA_ERR_ARG (-1)
+#define MOFA_ERR_CUDA (-2)
+#define MOFA_ERR_UNSUPPORTED (-3)
+
+const char* mofa_last_error(void);
+int mofa_version(void);
+/* number of kernels launched by this library since load / since the last reset (bench "gpu_launches") */
+int64_t mofa_launch_count(void);
+void mofa_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tensor-core GEMM family (tcgen05.mma, TMA-fed, TMEM accumulators, persistent tiles).
+ *   out[row, n] = epilogue( sum_k A[row, k] * Wt[n, k] )
+ * A-operand modes (how the 128-row A tile of each k-block is fetched by TMA):
+ *   LINEAR    A is [M, K] row-major (lda); optionally split K = K1 (from a) + K-K1 (from a2):
+ *             torch Linear / 1x1 conv / channel-concat (diffusers up-block torch.cat + conv_shortcut).
+ *   CONV3X3   A is NHWC [n_img, H, W, C]; implicit GEMM of a 3x3 / stride 1 / pad 1 convolution,
+ *             K = 9*C ordered (ky, kx, c); each k-block is a shifted 4-D TMA box, halo zero-filled
+ *             by TMA out-of-bounds handling (replaces cuDNN Conv2d inside ResnetBlock2D etc.).
+ *   TEMPORAL3 A is [B, T, HW, C]; implicit GEMM of Conv3d kernel (3,1,1) pad (1,0,0) along T,
+ *             K = 3*C ordered (kt, c) (TemporalResnetBlock of SpatioTemporalResBlock).
+ * Epilogue (fp32):  v = acc + bias[n] + rowbias[row / rows_per_group, n]
+ *                   v = act(v)           act: 0 none, 1 SiLU, 2 GEGLU (see below)
+ *                   v = alpha * v + beta1 * res1[row, n] + beta2 * res2[row, n]      -> fp16
+ * GEGLU (act=2): weight rows are packed per N tile as [bn/2 value rows | bn/2 gate rows]; the
+ *   tile writes bn/2 columns  value * gelu_erf(gate)  (diffusers GEGLU); out has N/2 columns.
+ * ---------------------------------------------------------------------------------------------- */
+#define MOFA_A_LINEAR 0
+#define MOFA_A_CONV3X3 1
+#define MOFA_A_TEMPORAL3 2
+
+typedef struct mofa_gemm_args {
+  int32_t mode;
+  int32_t act;            /* 0 none, 1 silu, 2 geglu */
+  const void* a;          /* fp16 */
+  const void* a2;         /* fp16, LINEAR split-K second source or NULL */
+  const void* w;          /* fp16 [N, Ktot] row-major */
+  void* out;              /* fp16 [rows, ldc] */
+  int64_t ldc;
+  /* LINEAR */
+  int64_t M, K, K1, lda, lda2;
+  /* CONV3X3: NHWC input */
+  int32_t n_img, H, W, C;
+  /* TEMPORAL3: [B, T, HW, C] (C shared with conv) */
+  int32_t B, T, HW;
+  int32_t N;              /* weight rows */
+  int32_t bn;             /* N tile (multiple of 16, <= 256) */
+  const void* bias;       /* fp16 [N] or NULL */
+  const void* rowbias;    /* fp16 [groups, ld_rowbias] or NULL */
+  int64_t ld_rowbias;
+  int64_t rows_per_group;
+  const void* res1;       /* fp16 [rows, ldr1] or NULL */
+  int64_t ldr1;
+  const void* res2;
+  int64_t ldr2;
+  float alpha, beta1, beta2;
+  int32_t max_ctas;       /* 0 = one per SM */
+} mofa_gemm_args;
+
+int mofa_gemm(const mofa_gemm_args* args, mofa_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Spatial self-attention (diffusers Attention + AttnProcessor2_0 / F.scaled_dot_product_attention,
+ * no mask): qkv is [frames*L, 3*C] fp16 (q | k | v thirds, heads of 64 inside each third);
+ * out[frames*L, C].  FlashAttention-style: S=QK^T and PV on tcgen05, online softmax in fp32.
+ * ---------------------------------------------------------------------------------------------- */
+int mofa_attn_spatial(const void* qkv, void* out, int32_t frames, int32_t L, int32_t heads, float scale,
+                      mofa_stream_t stream);
+
+/* Temporal self-attention over T (<=32) tokens per (batch, pixel, head) (TemporalBasicTransformerBlock
+ * attn1): qkv [B*T*HW, 3*C] rows ordered (b, t, p); out same row order [B*T*HW, C]. */
+int mofa_attn_temporal(const void* qkv, void* out, int32_t B, int32_t T, int32_t HW, int32_t heads, float scale,
+                       mofa_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Normalisation / elementwise (HBM-bound)
+ * ---------------------------------------------------------------------------------------------- */
+/* GroupNorm(32 groups)+optional SiLU over channels-last input, optionally over the channel concat of
+ * two sources (x1[rows,C1] | x2[rows,C2]) (torch.cat([h, skip],1) + GroupNorm in up blocks).
+ * Statistics span `rows_per_stat` consecutive rows (h*w for 2-D GroupNorm, T*h*w for the 5-D temporal
+ * one).  stats is a caller workspace of (rows/rows_per_stat)*groups*2 floats. */
+int mofa_groupnorm(const void* x1, int32_t C1, const void* x2, int32_t C2, const void* gamma, const void* beta,
+                   void* out, int64_t rows, int64_t rows_per_stat, int32_t groups, float eps, int32_t silu,
+                   float* stats, mofa_stream_t stream);
+
+/* LayerNorm over C per row; optional pre-add of a per-row-group vector:  x' = x + add[(row / rows_per_group) %
+ * add_period]; out = LN(x'); if sum_out != NULL also writes x' (frame position embedding add,
+ * TransformerSpatioTemporalModel). */
+int mofa_layernorm(const void* x, const void* gamma, const void* beta, void* out, int64_t rows, int32_t C, float eps,
+                   const void* add, int64_t rows_per_group, int64_t add_period, void* sum_out, mofa_stream_t stream);
+
+/* out[i] = x[i] + scale * y[i % period]   (period = n for plain axpy; broadcast add otherwise), fp16 */
+int mofa_axpy_bcast(const void* x, const void* y, void* out, int64_t n, int64_t period, float scale,
+                    mofa_stream_t stream);
+
+/* im2col for 3x3 pad-1 convs with stride s on NHWC fp16: out[n*Ho*Wo, Kpad], K order (ky,kx,c), zero padded */
+int mofa_im2col3x3(const void* x, void* out, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t stride,
+                   int32_t Kpad, mofa_stream_t stream);
+
+/* nearest 2x upsample NHWC fp16 (Upsample2D before its conv) */
+int mofa_upsample2x(const void* x, void* out, int32_t n_img, int32_t H, int32_t W, int32_t C, mofa_stream_t stream);
+
+/* NCHW <-> NHWC fp16 layout changes at the API boundary; nchw_to_nhwc can write into a channel slice */
+int mofa_nchw_to_nhwc(const void* x, void* out, int32_t n_img, int32_t C, int32_t HW, int32_t ldo, int32_t c_off,
+                      mofa_stream_t stream);
+int mofa_nhwc_to_nchw(const void* x, void* out, int32_t n_img, int32_t C, int32_t HW, int32_t ldi, int32_t c_off,
+                      mofa_stream_t stream);
+
+/* small-M linear (M <= 8): out[m,n] = act_out( sum_k act_in(a[m,k]) * w[n,k] + bias[n] ), fp16 io, fp32 acc.
+ * act: 0 none, 1 SiLU.  (TimestepEmbedding MLPs, time_emb_proj, collapsed cross-attention vectors.) */
+int mofa_linear_small(const void* a, const void* w, const void* bias, void* out, int32_t M, int32_t N, int32_t K,
+                      int32_t act_in, int32_t act_out, mofa_stream_t stream);
+
+/* sinusoidal Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): out[m, dim] fp16 = [cos | sin] */
+int mofa_timestep_embedding(const float* t, void* out, int32_t M, int32_t dim, mofa_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Flow warp: softmax-splatting forward, 'avg' mode
+ * (/root/reference/MOFA-Video-Traj/models/softsplat.py:232-274, kernel :285-335), for all flows of a
+ * clip in one launch, with the adapter's nearest flow pyramid fused
+ * (/root/reference/MOFA-Video-Traj/models/svdxt_featureflow_forward_controlnet_s2d_fixcmp_norefine.py:302-319).
+ *   feat  fp16 NHWC [hs, ws, C]          first-frame feature at this scale
+ *   flow  fp16 NCHW [F, 2, Hf, Wf]       full-resolution flows (the pipeline hands the adapter fp16,
+ *                                        pipeline.py:396-397); scale = Hf / hs
+ *   acc   fp32 workspace [F, hs, ws, C]  and wsum fp32 [F, hs, ws]  (zeroed by the call)
+ *   out   fp16 NHWC [F, hs, ws, C]  =  acc / (wsum + 1e-7)
+ * ---------------------------------------------------------------------------------------------- */
+int mofa_softsplat_avg(const void* feat, const void* flow, float* acc, float* wsum, void* out, int32_t F, int32_t hs,
+                       int32_t ws, int32_t C, int32_t Hf, int32_t Wf, mofa_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused CFG combine + Euler (v-prediction) step + next model input
+ * (pipeline.py:449-454, 495-500; scheduling_euler_discrete_karras_fix.py:264-288, 481-520).
+ *   noise  fp16 NHWC [2*T, HW, 4] (uncond frames then cond frames)
+ *   latents fp32 NCHW [T, 4, HW] in/out (kept in fp32 between steps is NOT what the reference does:
+ *           the reference rounds prev_sample to fp16 each step, so `latents_h` fp16 is the state)
+ *   latents_h fp16 NCHW [T,4,HW] in/out;  image_latents fp16 NCHW [2, 4, HW] (uncond zeros, cond)
+ *   next_in fp16 NHWC [2*T, HW, 8] = cat(latents'/sqrt(sigma_next^2+1), image_latents)
+ * If noise == NULL only next_in is produced from the current latents (loop prologue) with sigma.
+ * ---------------------------------------------------------------------------------------------- */
+int mofa_cfg_euler_step(const void* noise, void* latents_h, const void* image_latents, void* next_in, int32_t T,
+                        int32_t HW, float g_min, float g_max, float sigma, float sigma_next, mofa_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOFA_B200_H */

@@ -1,0 +1,189 @@
+// Shared device helpers for the sm_100a kernels: mbarrier / TMA / tcgen05 / TMEM PTX wrappers.
+// Everything here is inline PTX; no CUTLASS/CuTe dependency.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MOFA_DEVICE __device__ __forceinline__
+
+namespace mofa {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing shared by every C-ABI entry point
+// ---------------------------------------------------------------------------------------------
+void set_last_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+// ---------------------------------------------------------------------------------------------
+// basic
+// ---------------------------------------------------------------------------------------------
+MOFA_DEVICE uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+MOFA_DEVICE uint32_t lane_id() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(r));
+    return r;
+}
+MOFA_DEVICE bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier
+// ---------------------------------------------------------------------------------------------
+MOFA_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+MOFA_DEVICE void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+MOFA_DEVICE void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+MOFA_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(addr),
+        "r"(parity)
+        : "memory");
+}
+MOFA_DEVICE void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+MOFA_DEVICE void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA (cp.async.bulk.tensor) loads, tile mode, completion on an mbarrier
+// ---------------------------------------------------------------------------------------------
+MOFA_DEVICE void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+MOFA_DEVICE void tma_load_2d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+MOFA_DEVICE void tma_load_3d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+MOFA_DEVICE void tma_load_4d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+        "[%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 / TMEM
+// ---------------------------------------------------------------------------------------------
+MOFA_DEVICE void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+MOFA_DEVICE void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// whole-warp: allocate `cols` (power of two >= 32) TMEM columns, base address written to *dst (smem)
+MOFA_DEVICE void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+MOFA_DEVICE void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], fp16 inputs, fp32 accumulate; issued by ONE thread
+MOFA_DEVICE void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+MOFA_DEVICE void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread t holds row lane_base+t)
+MOFA_DEVICE void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+MOFA_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor for a K-major tile stored as 128-byte rows with SWIZZLE_128B
+// (the layout a TMA box with inner extent 64 fp16 and CU_TENSOR_MAP_SWIZZLE_128B produces):
+// 8-row x 128 B swizzle atoms stacked along M/N with a 1024 B stride (SBO); LBO unused.
+MOFA_DEVICE uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);  // start address, 16 B units
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;            // stride byte offset between 8-row groups
+    d |= 1ull << 46;                                        // descriptor version (sm_100)
+    d |= 2ull << 61;                                        // SWIZZLE_128B
+    return d;
+}
+// MN-major operand (the contiguous dimension is M/N, e.g. V[kv][d] used as B with N=d, K=kv):
+// atoms are 8 K-rows x 128 B (64 fp16 along N); consecutive K-groups 1024 B apart (SBO);
+// LBO = byte distance between 64-wide N atoms (unused when the tile is exactly 64 wide).
+MOFA_DEVICE uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= 1ull << 46;
+    d |= 2ull << 61;
+    return d;
+}
+// instruction descriptor: fp16 x fp16 -> fp32, M = 128
+MOFA_DEVICE uint32_t umma_idesc_f16(uint32_t n, bool b_mn_major) {
+    uint32_t d = 0;
+    d |= 1u << 4;                     // D format: F32
+    d |= 0u << 7;                     // A format: F16
+    d |= 0u << 10;                    // B format: F16
+    d |= (b_mn_major ? 1u : 0u) << 16;  // B major
+    d |= (n >> 3) << 17;              // N / 8
+    d |= (128u >> 4) << 24;           // M / 16
+    return d;
+}
+
+MOFA_DEVICE float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+MOFA_DEVICE float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+MOFA_DEVICE float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+}  // namespace mofa

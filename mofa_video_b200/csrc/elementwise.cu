@@ -1,0 +1,601 @@
+// HBM-bound kernels of the hot path: GroupNorm(+SiLU), LayerNorm, broadcast axpy, im2col, nearest
+// upsample, NCHW<->NHWC, small-M linear, sinusoidal timestep embedding, fused CFG + Euler step.
+// All activations are fp16 channels-last; statistics and arithmetic are fp32; 16-byte vector accesses.
+#include "../../include/mofa_b200.h"
+#include "common.cuh"
+
+namespace mofa {
+
+union V8 {
+    uint4 u;
+    __half h[8];
+    __half2 h2[4];
+};
+
+// =============================================================================================
+// GroupNorm (torch.nn.GroupNorm(32, C, eps) [+ SiLU]) on channels-last data, optional concat input
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+groupnorm_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2,
+                       long long rows_per_stat, int rows_per_block, int groups, float* __restrict__ stats) {
+    const int C = C1 + C2;
+    const int vecs = C >> 3;
+    const int cpg = C / groups;
+    const int VX = blockDim.x, VY = blockDim.y;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const long long s = blockIdx.y;
+    const long long r_begin = static_cast<long long>(blockIdx.x) * rows_per_block;
+    long long r_end = r_begin + rows_per_block;
+    if (r_end > rows_per_stat) r_end = rows_per_stat;
+    const long long row0 = s * rows_per_stat;
+
+    __shared__ float s_sum[64], s_sq[64];
+    const int tid = ty * VX + tx;
+    if (tid < 64) {
+        s_sum[tid] = 0.f;
+        s_sq[tid] = 0.f;
+    }
+    __syncthreads();
+
+    for (int vec = tx; vec < vecs; vec += VX) {
+        const int c = vec << 3;
+        const __half* base;
+        long long ld;
+        int cc;
+        if (c < C1) {
+            base = x1;
+            ld = C1;
+            cc = c;
+        } else {
+            base = x2;
+            ld = C2;
+            cc = c - C1;
+        }
+        float sum[8], sq[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
+        for (long long r = r_begin + ty; r < r_end; r += VY) {
+            V8 v;
+            v.u = __ldg(reinterpret_cast<const uint4*>(base + (row0 + r) * ld + cc));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float f = __half2float(v.h[j]);
+                sum[j] += f;
+                sq[j] += f * f;
+            }
+        }
+        // flush: channels c..c+7 touch at most two groups when cpg >= 8, more when cpg < 8
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int g = (c + j) / cpg;
+            atomicAdd(&s_sum[g], sum[j]);
+            atomicAdd(&s_sq[g], sq[j]);
+        }
+    }
+    __syncthreads();
+    if (tid < groups) {
+        atomicAdd(&stats[(s * groups + tid) * 2 + 0], s_sum[tid]);
+        atomicAdd(&stats[(s * groups + tid) * 2 + 1], s_sq[tid]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+groupnorm_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2,
+                       const __half* __restrict__ gamma, const __half* __restrict__ beta, __half* __restrict__ out,
+                       long long rows, long long rows_per_stat, int groups, float eps, int silu,
+                       const float* __restrict__ stats) {
+    const int C = C1 + C2;
+    const int vecs = C >> 3;
+    const int cpg = C / groups;
+    const float inv_cnt = 1.0f / (static_cast<float>(cpg) * static_cast<float>(rows_per_stat));
+    const long long total = rows * vecs;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long row = idx / vecs;
+        const int c = static_cast<int>(idx - row * vecs) << 3;
+        const long long s = row / rows_per_stat;
+        V8 v;
+        if (c < C1)
+            v.u = __ldg(reinterpret_cast<const uint4*>(x1 + row * C1 + c));
+        else
+            v.u = __ldg(reinterpret_cast<const uint4*>(x2 + row * C2 + (c - C1)));
+        V8 g, b, o;
+        g.u = __ldg(reinterpret_cast<const uint4*>(gamma + c));
+        b.u = __ldg(reinterpret_cast<const uint4*>(beta + c));
+        int gi_prev = -1;
+        float mean = 0.f, rstd = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int gi = (c + j) / cpg;
+            if (gi != gi_prev) {
+                const float sm = stats[(s * groups + gi) * 2 + 0];
+                const float sq = stats[(s * groups + gi) * 2 + 1];
+                mean = sm * inv_cnt;
+                float var = sq * inv_cnt - mean * mean;
+                var = var < 0.f ? 0.f : var;
+                rstd = rsqrtf(var + eps);
+                gi_prev = gi;
+            }
+            float y = (__half2float(v.h[j]) - mean) * rstd * __half2float(g.h[j]) + __half2float(b.h[j]);
+            if (silu) y = silu_f(y);
+            o.h[j] = __float2half_rn(y);
+        }
+        *reinterpret_cast<uint4*>(out + row * C + c) = o.u;
+    }
+}
+
+// =============================================================================================
+// LayerNorm over C (<= 2048) per row, one warp per row, optional per-row-group pre-add
+// =============================================================================================
+template <int kMaxVec>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma, const __half* __restrict__ beta,
+                 __half* __restrict__ out, long long rows, int C, float eps, const __half* __restrict__ add,
+                 long long rows_per_group, long long add_period, __half* __restrict__ sum_out) {
+    const int lane = threadIdx.x & 31;
+    const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int vecs = C >> 3;
+    float v[kMaxVec][8];
+    const __half* addrow = add ? add + ((row / rows_per_group) % add_period) * C : nullptr;
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+        const int vec = lane + i * 32;
+        if (vec < vecs) {
+            V8 t;
+            t.u = __ldg(reinterpret_cast<const uint4*>(x + row * C + vec * 8));
+            if (addrow) {
+                V8 a;
+                a.u = __ldg(reinterpret_cast<const uint4*>(addrow + vec * 8));
+                V8 so;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    // the reference adds in fp16 (hidden_states + emb), so round the sum to fp16
+                    so.h[j] = __float2half_rn(__half2float(t.h[j]) + __half2float(a.h[j]));
+                    v[i][j] = __half2float(so.h[j]);
+                }
+                if (sum_out) *reinterpret_cast<uint4*>(sum_out + row * C + vec * 8) = so.u;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[i][j] = __half2float(t.h[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sum += v[i][j];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / static_cast<float>(C);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+        const int vec = lane + i * 32;
+        if (vec < vecs) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float d = v[i][j] - mean;
+                sq += d * d;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / static_cast<float>(C) + eps);
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+        const int vec = lane + i * 32;
+        if (vec < vecs) {
+            V8 g, b, o;
+            g.u = __ldg(reinterpret_cast<const uint4*>(gamma + vec * 8));
+            b.u = __ldg(reinterpret_cast<const uint4*>(beta + vec * 8));
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                o.h[j] = __float2half_rn((v[i][j] - mean) * rstd * __half2float(g.h[j]) + __half2float(b.h[j]));
+            *reinterpret_cast<uint4*>(out + row * C + vec * 8) = o.u;
+        }
+    }
+}
+
+// =============================================================================================
+// out = x + scale * y[i % period]
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+axpy_bcast_kernel(const __half* __restrict__ x, const __half* __restrict__ y, __half* __restrict__ out,
+                  long long nvec, long long period_vec, float scale) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        V8 a, b, o;
+        a.u = __ldg(reinterpret_cast<const uint4*>(x) + i);
+        b.u = __ldg(reinterpret_cast<const uint4*>(y) + (i % period_vec));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.h[j] = __float2half_rn(__half2float(a.h[j]) + scale * __half2float(b.h[j]));
+        reinterpret_cast<uint4*>(out)[i] = o.u;
+    }
+}
+
+// =============================================================================================
+// im2col 3x3, pad 1, stride s (for stride-2 convs and convs whose C is not a multiple of 64)
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+im2col3x3_kernel(const __half* __restrict__ x, __half* __restrict__ out, int n_img, int H, int W, int C, int stride,
+                 int Ho, int Wo, int Kpad) {
+    const long long total = static_cast<long long>(n_img) * Ho * Wo * Kpad;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long row = idx / Kpad;
+        const int k = static_cast<int>(idx - row * Kpad);
+        __half v = __float2half(0.f);
+        if (k < 9 * C) {
+            const int tap = k / C;
+            const int c = k - tap * C;
+            const int ky = tap / 3, kx = tap - ky * 3;
+            const int ox = static_cast<int>(row % Wo);
+            const long long t = row / Wo;
+            const int oy = static_cast<int>(t % Ho);
+            const int n = static_cast<int>(t / Ho);
+            const int iy = oy * stride + ky - 1;
+            const int ix = ox * stride + kx - 1;
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[((static_cast<long long>(n) * H + iy) * W + ix) * C + c];
+        }
+        out[idx] = v;
+    }
+}
+// vectorised variant for C % 8 == 0 and Kpad == 9*C
+__global__ void __launch_bounds__(256)
+im2col3x3_vec_kernel(const __half* __restrict__ x, __half* __restrict__ out, int n_img, int H, int W, int C,
+                     int stride, int Ho, int Wo) {
+    const int cv = C >> 3;
+    const long long total = static_cast<long long>(n_img) * Ho * Wo * 9 * cv;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c8 = static_cast<int>(idx % cv);
+        long long t = idx / cv;
+        const int tap = static_cast<int>(t % 9);
+        const long long row = t / 9;
+        const int ky = tap / 3, kx = tap - ky * 3;
+        const int ox = static_cast<int>(row % Wo);
+        t = row / Wo;
+        const int oy = static_cast<int>(t % Ho);
+        const int n = static_cast<int>(t / Ho);
+        const int iy = oy * stride + ky - 1;
+        const int ix = ox * stride + kx - 1;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+            v = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<long long>(n) * H + iy) * W + ix) * C) + c8);
+        reinterpret_cast<uint4*>(out)[idx] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const __half* __restrict__ x, __half* __restrict__ out, int n_img, int H, int W, int C) {
+    const int cv = C >> 3;
+    const int Ho = 2 * H, Wo = 2 * W;
+    const long long total = static_cast<long long>(n_img) * Ho * Wo * cv;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c8 = static_cast<int>(idx % cv);
+        long long t = idx / cv;
+        const int ox = static_cast<int>(t % Wo);
+        t /= Wo;
+        const int oy = static_cast<int>(t % Ho);
+        const int n = static_cast<int>(t / Ho);
+        reinterpret_cast<uint4*>(out)[idx] = __ldg(
+            reinterpret_cast<const uint4*>(x + ((static_cast<long long>(n) * H + (oy >> 1)) * W + (ox >> 1)) * C) + c8);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ out, int n_img, int C, int HW, int ldo,
+                    int c_off) {
+    const long long total = static_cast<long long>(n_img) * HW * C;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(idx % C);
+        const long long t = idx / C;
+        const int p = static_cast<int>(t % HW);
+        const long long n = t / HW;
+        out[(n * HW + p) * ldo + c_off + c] = x[(n * C + c) * HW + p];
+    }
+}
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const __half* __restrict__ x, __half* __restrict__ out, int n_img, int C, int HW, int ldi,
+                    int c_off) {
+    const long long total = static_cast<long long>(n_img) * HW * C;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int p = static_cast<int>(idx % HW);
+        const long long t = idx / HW;
+        const int c = static_cast<int>(t % C);
+        const long long n = t / C;
+        out[idx] = x[(n * HW + p) * ldi + c_off + c];
+    }
+}
+
+// =============================================================================================
+// small-M linear: one warp per output column
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+linear_small_kernel(const __half* __restrict__ a, const __half* __restrict__ w, const __half* __restrict__ bias,
+                    __half* __restrict__ out, int M, int N, int K, int act_in, int act_out) {
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (n >= N) return;
+    float acc[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) acc[m] = 0.f;
+    for (int k = lane * 8; k < K; k += 256) {
+        V8 wv;
+        wv.u = __ldg(reinterpret_cast<const uint4*>(w + static_cast<long long>(n) * K + k));
+        float wf[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wf[j] = __half2float(wv.h[j]);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            if (m < M) {
+                V8 av;
+                av.u = __ldg(reinterpret_cast<const uint4*>(a + static_cast<long long>(m) * K + k));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float f = __half2float(av.h[j]);
+                    if (act_in == 1) f = __half2float(__float2half_rn(silu_f(f)));
+                    acc[m] += f * wf[j];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], o);
+    }
+    if (lane == 0) {
+        const float b = bias ? __half2float(bias[n]) : 0.f;
+        for (int m = 0; m < M; ++m) {
+            float v = acc[m] + b;
+            if (act_out == 1) v = silu_f(v);
+            out[static_cast<long long>(m) * N + n] = __float2half_rn(v);
+        }
+    }
+}
+
+// diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0) -> [cos | sin], fp32 math
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, __half* __restrict__ out, int M, int dim) {
+    const int half_dim = dim >> 1;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * half_dim) return;
+    const int m = idx / half_dim, j = idx - m * half_dim;
+    const float freq = expf(-9.210340371976184f * static_cast<float>(j) / static_cast<float>(half_dim));
+    const float arg = t[m] * freq;
+    out[m * dim + j] = __float2half_rn(cosf(arg));
+    out[m * dim + half_dim + j] = __float2half_rn(sinf(arg));
+}
+
+// =============================================================================================
+// CFG combine + Euler v-prediction step + next model input
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+cfg_euler_kernel(const __half* __restrict__ noise, __half* __restrict__ latents, const __half* __restrict__ img_lat,
+                 __half* __restrict__ next_in, int T, int HW, float g_min, float g_max, float sigma,
+                 float sigma_next) {
+    const long long total = static_cast<long long>(T) * HW;
+    const float in_scale = rsqrtf(sigma_next * sigma_next + 1.0f);
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int t = static_cast<int>(idx / HW);
+        const int p = static_cast<int>(idx - static_cast<long long>(t) * HW);
+        float x[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) x[c] = __half2float(latents[(static_cast<long long>(t) * 4 + c) * HW + p]);
+        if (noise) {
+            float g = (T > 1) ? g_min + (g_max - g_min) * static_cast<float>(t) / static_cast<float>(T - 1) : g_min;
+            g = __half2float(__float2half_rn(g));  // guidance_scale.to(latents.dtype), pipeline.py:424
+            const __half2* nu = reinterpret_cast<const __half2*>(noise + (static_cast<long long>(t) * HW + p) * 4);
+            const __half2* nc = reinterpret_cast<const __half2*>(noise + (static_cast<long long>(T + t) * HW + p) * 4);
+            const float2 u01 = __half22float2(nu[0]), u23 = __half22float2(nu[1]);
+            const float2 c01 = __half22float2(nc[0]), c23 = __half22float2(nc[1]);
+            const float u[4] = {u01.x, u01.y, u23.x, u23.y};
+            const float cd[4] = {c01.x, c01.y, c23.x, c23.y};
+            const float s2 = sigma * sigma + 1.0f;
+            const float c_out = -sigma * rsqrtf(s2);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float v = u[c] + g * (cd[c] - u[c]);
+                const float x0 = v * c_out + x[c] / s2;
+                const float d = (x[c] - x0) / sigma;
+                const float xn = x[c] + d * (sigma_next - sigma);
+                const __half xh = __float2half_rn(xn);
+                latents[(static_cast<long long>(t) * 4 + c) * HW + p] = xh;
+                x[c] = __half2float(xh);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            V8 o;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                o.h[c] = __float2half_rn(x[c] * in_scale);
+                o.h[4 + c] = img_lat[(static_cast<long long>(b) * 4 + c) * HW + p];
+            }
+            *reinterpret_cast<uint4*>(next_in + ((static_cast<long long>(b) * T + t) * HW + p) * 8) = o.u;
+        }
+    }
+}
+
+static int grid_for(long long work_items, int block = 256) {
+    long long g = (work_items + block - 1) / block;
+    const long long cap = 148LL * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return static_cast<int>(g);
+}
+
+}  // namespace mofa
+
+using namespace mofa;
+
+extern "C" int mofa_groupnorm(const void* x1, int32_t C1, const void* x2, int32_t C2, const void* gamma,
+                              const void* beta, void* out, int64_t rows, int64_t rows_per_stat, int32_t groups,
+                              float eps, int32_t silu, float* stats, mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int C = C1 + (x2 ? C2 : 0);
+    if (!x2) C2 = 0;
+    if (!x1 || !out || !stats || rows <= 0 || rows_per_stat <= 0 || (rows % rows_per_stat) != 0 || groups <= 0 ||
+        groups > 64 || (C % groups) != 0 || (C1 % 8) != 0 || (C2 % 8) != 0) {
+        set_last_error("mofa_groupnorm: bad arguments (C1=%d C2=%d rows=%lld rows_per_stat=%lld groups=%d)", C1, C2,
+                       (long long)rows, (long long)rows_per_stat, groups);
+        return MOFA_ERR_ARG;
+    }
+    const long long nstat = rows / rows_per_stat;
+    cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * nstat, stream);
+    const int vecs = C / 8;
+    int VX = vecs < 256 ? vecs : 256;
+    int VY = 256 / VX;
+    if (VY < 1) VY = 1;
+    int rows_per_block = 256;
+    if (rows_per_stat < rows_per_block) rows_per_block = static_cast<int>(rows_per_stat);
+    dim3 block(VX, VY);
+    dim3 grid(static_cast<unsigned>((rows_per_stat + rows_per_block - 1) / rows_per_block),
+              static_cast<unsigned>(nstat));
+    groupnorm_stats_kernel<<<grid, block, 0, stream>>>(static_cast<const __half*>(x1), C1,
+                                                       static_cast<const __half*>(x2), C2, rows_per_stat,
+                                                       rows_per_block, groups, stats);
+    int rc = check_launch("mofa_groupnorm(stats)");
+    if (rc) return rc;
+    groupnorm_apply_kernel<<<grid_for(rows * vecs), 256, 0, stream>>>(
+        static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2, static_cast<const __half*>(gamma),
+        static_cast<const __half*>(beta), static_cast<__half*>(out), rows, rows_per_stat, groups, eps, silu, stats);
+    return check_launch("mofa_groupnorm(apply)");
+}
+
+extern "C" int mofa_layernorm(const void* x, const void* gamma, const void* beta, void* out, int64_t rows, int32_t C,
+                              float eps, const void* add, int64_t rows_per_group, int64_t add_period, void* sum_out,
+                              mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!x || !out || rows <= 0 || C <= 0 || (C % 8) != 0 || C > 2048) {
+        set_last_error("mofa_layernorm: bad arguments (C=%d rows=%lld)", C, (long long)rows);
+        return MOFA_ERR_ARG;
+    }
+    if (rows_per_group <= 0) rows_per_group = 1;
+    if (add_period <= 0) add_period = 1;
+    const int warps = 8;
+    const unsigned grid = static_cast<unsigned>((rows + warps - 1) / warps);
+    const int vecs = C / 8;
+#define LN_LAUNCH(MV)                                                                                              \
+    layernorm_kernel<MV><<<grid, warps * 32, 0, stream>>>(                                                         \
+        static_cast<const __half*>(x), static_cast<const __half*>(gamma), static_cast<const __half*>(beta),        \
+        static_cast<__half*>(out), rows, C, eps, static_cast<const __half*>(add), rows_per_group, add_period,      \
+        static_cast<__half*>(sum_out))
+    if (vecs <= 64)
+        LN_LAUNCH(2);
+    else if (vecs <= 160)
+        LN_LAUNCH(5);
+    else
+        LN_LAUNCH(8);
+#undef LN_LAUNCH
+    return check_launch("mofa_layernorm");
+}
+
+extern "C" int mofa_axpy_bcast(const void* x, const void* y, void* out, int64_t n, int64_t period, float scale,
+                               mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!x || !y || !out || n <= 0 || (n % 8) != 0 || period <= 0 || (period % 8) != 0) {
+        set_last_error("mofa_axpy_bcast: n and period must be positive multiples of 8");
+        return MOFA_ERR_ARG;
+    }
+    axpy_bcast_kernel<<<grid_for(n / 8), 256, 0, stream>>>(static_cast<const __half*>(x),
+                                                          static_cast<const __half*>(y), static_cast<__half*>(out),
+                                                          n / 8, period / 8, scale);
+    return check_launch("mofa_axpy_bcast");
+}
+
+extern "C" int mofa_im2col3x3(const void* x, void* out, int32_t n_img, int32_t H, int32_t W, int32_t C,
+                              int32_t stride, int32_t Kpad, mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!x || !out || n_img <= 0 || H <= 0 || W <= 0 || C <= 0 || (stride != 1 && stride != 2) || Kpad < 9 * C) {
+        set_last_error("mofa_im2col3x3: bad arguments");
+        return MOFA_ERR_ARG;
+    }
+    const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+    if ((C % 8) == 0 && Kpad == 9 * C) {
+        const long long total = static_cast<long long>(n_img) * Ho * Wo * 9 * (C / 8);
+        im2col3x3_vec_kernel<<<grid_for(total), 256, 0, stream>>>(static_cast<const __half*>(x),
+                                                                 static_cast<__half*>(out), n_img, H, W, C, stride, Ho,
+                                                                 Wo);
+    } else {
+        const long long total = static_cast<long long>(n_img) * Ho * Wo * Kpad;
+        im2col3x3_kernel<<<grid_for(total), 256, 0, stream>>>(static_cast<const __half*>(x),
+                                                             static_cast<__half*>(out), n_img, H, W, C, stride, Ho, Wo,
+                                                             Kpad);
+    }
+    return check_launch("mofa_im2col3x3");
+}
+
+extern "C" int mofa_upsample2x(const void* x, void* out, int32_t n_img, int32_t H, int32_t W, int32_t C,
+                               mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!x || !out || (C % 8) != 0) {
+        set_last_error("mofa_upsample2x: C must be a multiple of 8");
+        return MOFA_ERR_ARG;
+    }
+    const long long total = static_cast<long long>(n_img) * 4 * H * W * (C / 8);
+    upsample2x_kernel<<<grid_for(total), 256, 0, stream>>>(static_cast<const __half*>(x), static_cast<__half*>(out),
+                                                          n_img, H, W, C);
+    return check_launch("mofa_upsample2x");
+}
+
+extern "C" int mofa_nchw_to_nhwc(const void* x, void* out, int32_t n_img, int32_t C, int32_t HW, int32_t ldo,
+                                 int32_t c_off, mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const long long total = static_cast<long long>(n_img) * C * HW;
+    nchw_to_nhwc_kernel<<<grid_for(total), 256, 0, stream>>>(static_cast<const __half*>(x), static_cast<__half*>(out),
+                                                            n_img, C, HW, ldo, c_off);
+    return check_launch("mofa_nchw_to_nhwc");
+}
+extern "C" int mofa_nhwc_to_nchw(const void* x, void* out, int32_t n_img, int32_t C, int32_t HW, int32_t ldi,
+                                 int32_t c_off, mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const long long total = static_cast<long long>(n_img) * C * HW;
+    nhwc_to_nchw_kernel<<<grid_for(total), 256, 0, stream>>>(static_cast<const __half*>(x), static_cast<__half*>(out),
+                                                            n_img, C, HW, ldi, c_off);
+    return check_launch("mofa_nhwc_to_nchw");
+}
+
+extern "C" int mofa_linear_small(const void* a, const void* w, const void* bias, void* out, int32_t M, int32_t N,
+                                 int32_t K, int32_t act_in, int32_t act_out, mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!a || !w || !out || M <= 0 || M > 8 || N <= 0 || K <= 0 || (K % 8) != 0) {
+        set_last_error("mofa_linear_small: needs 1<=M<=8 and K %% 8 == 0 (M=%d K=%d)", M, K);
+        return MOFA_ERR_ARG;
+    }
+    const int warps = 8;
+    linear_small_kernel<<<(N + warps - 1) / warps, warps * 32, 0, stream>>>(
+        static_cast<const __half*>(a), static_cast<const __half*>(w), static_cast<const __half*>(bias),
+        static_cast<__half*>(out), M, N, K, act_in, act_out);
+    return check_launch("mofa_linear_small");
+}
+
+extern "C" int mofa_timestep_embedding(const float* t, void* out, int32_t M, int32_t dim, mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!t || !out || M <= 0 || dim <= 0 || (dim & 1)) {
+        set_last_error("mofa_timestep_embedding: bad arguments");
+        return MOFA_ERR_ARG;
+    }
+    const int total = M * (dim / 2);
+    timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, stream>>>(t, static_cast<__half*>(out), M, dim);
+    return check_launch("mofa_timestep_embedding");
+}
+
+extern "C" int mofa_cfg_euler_step(const void* noise, void* latents_h, const void* image_latents, void* next_in,
+                                   int32_t T, int32_t HW, float g_min, float g_max, float sigma, float sigma_next,
+                                   mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!latents_h || !image_latents || !next_in || T <= 0 || HW <= 0) {
+        set_last_error("mofa_cfg_euler_step: bad arguments");
+        return MOFA_ERR_ARG;
+    }
+    cfg_euler_kernel<<<grid_for(static_cast<long long>(T) * HW), 256, 0, stream>>>(
+        static_cast<const __half*>(noise), static_cast<__half*>(latents_h), static_cast<const __half*>(image_latents),
+        static_cast<__half*>(next_in), T, HW, g_min, g_max, sigma, sigma_next);
+    return check_launch("mofa_cfg_euler_step");
+}

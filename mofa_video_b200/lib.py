@@ -1,0 +1,250 @@
+"""ctypes binding of libmofa_b200.so (C ABI declared in include/mofa_b200.h).
+
+Every wrapper takes torch CUDA tensors, passes raw data_ptr()s and the current torch stream -- the
+same calling convention the reference uses for its one native kernel
+(/root/reference/MOFA-Video-Traj/models/softsplat.py:340-345).  There is NO fallback: if the shared
+library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmofa_b200.so")
+
+A_LINEAR, A_CONV3X3, A_TEMPORAL3 = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+
+EXPORTS = [
+    "mofa_last_error", "mofa_version", "mofa_launch_count", "mofa_launch_count_reset", "mofa_gemm",
+    "mofa_attn_spatial", "mofa_attn_temporal", "mofa_groupnorm", "mofa_layernorm", "mofa_axpy_bcast",
+    "mofa_im2col3x3", "mofa_upsample2x", "mofa_nchw_to_nhwc", "mofa_nhwc_to_nchw", "mofa_linear_small",
+    "mofa_timestep_embedding", "mofa_softsplat_avg", "mofa_cfg_euler_step",
+]
+
+
+class GemmArgs(ctypes.Structure):
+    _fields_ = [
+        ("mode", ctypes.c_int32), ("act", ctypes.c_int32),
+        ("a", ctypes.c_void_p), ("a2", ctypes.c_void_p), ("w", ctypes.c_void_p), ("out", ctypes.c_void_p),
+        ("ldc", ctypes.c_int64),
+        ("M", ctypes.c_int64), ("K", ctypes.c_int64), ("K1", ctypes.c_int64), ("lda", ctypes.c_int64),
+        ("lda2", ctypes.c_int64),
+        ("n_img", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32), ("C", ctypes.c_int32),
+        ("B", ctypes.c_int32), ("T", ctypes.c_int32), ("HW", ctypes.c_int32),
+        ("N", ctypes.c_int32), ("bn", ctypes.c_int32),
+        ("bias", ctypes.c_void_p), ("rowbias", ctypes.c_void_p), ("ld_rowbias", ctypes.c_int64),
+        ("rows_per_group", ctypes.c_int64),
+        ("res1", ctypes.c_void_p), ("ldr1", ctypes.c_int64), ("res2", ctypes.c_void_p), ("ldr2", ctypes.c_int64),
+        ("alpha", ctypes.c_float), ("beta1", ctypes.c_float), ("beta2", ctypes.c_float),
+        ("max_ctas", ctypes.c_int32),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library; fail loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the CUDA extension is not built (run `python -c 'import __graft_entry__ as g; "
+            "g.build()'`). mofa_video_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.mofa_last_error.restype = ctypes.c_char_p
+    lib.mofa_launch_count.restype = ctypes.c_int64
+    vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+    lib.mofa_gemm.argtypes = [ctypes.POINTER(GemmArgs), vp]
+    lib.mofa_attn_spatial.argtypes = [vp, vp, i32, i32, i32, f32, vp]
+    lib.mofa_attn_temporal.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp]
+    lib.mofa_groupnorm.argtypes = [vp, i32, vp, i32, vp, vp, vp, i64, i64, i32, f32, i32, vp, vp]
+    lib.mofa_layernorm.argtypes = [vp, vp, vp, vp, i64, i32, f32, vp, i64, i64, vp, vp]
+    lib.mofa_axpy_bcast.argtypes = [vp, vp, vp, i64, i64, f32, vp]
+    lib.mofa_im2col3x3.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    lib.mofa_upsample2x.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    lib.mofa_nchw_to_nhwc.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.mofa_nhwc_to_nchw.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.mofa_linear_small.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.mofa_timestep_embedding.argtypes = [vp, vp, i32, i32, vp]
+    lib.mofa_softsplat_avg.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    lib.mofa_cfg_euler_step.argtypes = [vp, vp, vp, vp, i32, i32, f32, f32, f32, f32, vp]
+    _lib = lib
+    return lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (rc={rc}): {load().mofa_last_error().decode()}")
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _chk_h(*ts):
+    for t in ts:
+        if t is not None:
+            assert t.is_cuda and t.dtype == torch.float16 and t.is_contiguous(), (t.dtype, t.shape, t.is_contiguous())
+
+
+def launch_count():
+    return int(load().mofa_launch_count())
+
+
+def launch_count_reset():
+    load().mofa_launch_count_reset()
+
+
+def pick_bn(n, geglu=False):
+    """N tile for mofa_gemm: the widest tile (<=256) that wastes the least of N."""
+    if geglu:
+        for bn in (256, 192, 128, 64):
+            if n % bn == 0:
+                return bn
+        raise ValueError(f"GEGLU N={n} has no valid tile")
+    if n <= 256:
+        return max(16, (n + 15) // 16 * 16)
+    best, best_cost = None, None
+    for bn in range(256, 111, -16):
+        tiles = (n + bn - 1) // bn
+        cost = tiles * bn  # padded columns computed
+        # prefer less padding; tie -> larger tile
+        if best is None or cost < best_cost:
+            best, best_cost = bn, cost
+    return best
+
+
+def gemm(mode, a, w, out, *, N, bn=None, act=ACT_NONE, a2=None, M=0, K=0, K1=0, lda=0, lda2=0, n_img=0, H=0, W=0,
+         C=0, B=0, T=0, HW=0, ldc=None, bias=None, rowbias=None, rows_per_group=1, res1=None, res2=None, alpha=1.0,
+         beta1=1.0, beta2=1.0, max_ctas=0):
+    lib = load()
+    _chk_h(a, a2, w, out, bias, rowbias, res1, res2)
+    g = GemmArgs()
+    g.mode, g.act = mode, act
+    g.a, g.a2, g.w, g.out = a.data_ptr(), (a2.data_ptr() if a2 is not None else None), w.data_ptr(), out.data_ptr()
+    n_out = N // 2 if act == ACT_GEGLU else N
+    g.ldc = ldc if ldc is not None else n_out
+    g.M, g.K, g.K1, g.lda, g.lda2 = M, K, K1, lda, lda2
+    g.n_img, g.H, g.W, g.C, g.B, g.T, g.HW = n_img, H, W, C, B, T, HW
+    g.N = N
+    g.bn = bn if bn is not None else pick_bn(N, act == ACT_GEGLU)
+    g.bias = bias.data_ptr() if bias is not None else None
+    if rowbias is not None:
+        g.rowbias, g.ld_rowbias, g.rows_per_group = rowbias.data_ptr(), rowbias.shape[-1], rows_per_group
+    else:
+        g.rowbias, g.ld_rowbias, g.rows_per_group = None, 0, 1
+    g.res1 = res1.data_ptr() if res1 is not None else None
+    g.ldr1 = res1.shape[-1] if res1 is not None else 0
+    g.res2 = res2.data_ptr() if res2 is not None else None
+    g.ldr2 = res2.shape[-1] if res2 is not None else 0
+    g.alpha, g.beta1, g.beta2 = alpha, beta1, beta2
+    g.max_ctas = max_ctas
+    _check(lib.mofa_gemm(ctypes.byref(g), _stream()), "mofa_gemm")
+    return out
+
+
+def linear(a, w, out, **kw):
+    """a [M, K] (row-major, last dim contiguous), w [N, K]."""
+    M, K = a.shape[0], a.shape[1]
+    return gemm(A_LINEAR, a, w, out, N=w.shape[0], M=M, K=K if "K" not in kw else kw.pop("K"), lda=a.stride(0), **kw)
+
+
+def attn_spatial(qkv, out, frames, L, heads, scale):
+    _chk_h(qkv, out)
+    _check(load().mofa_attn_spatial(_p(qkv), _p(out), frames, L, heads, scale, _stream()), "mofa_attn_spatial")
+    return out
+
+
+def attn_temporal(qkv, out, B, T, HW, heads, scale):
+    _chk_h(qkv, out)
+    _check(load().mofa_attn_temporal(_p(qkv), _p(out), B, T, HW, heads, scale, _stream()), "mofa_attn_temporal")
+    return out
+
+
+def groupnorm(x1, gamma, beta, out, rows_per_stat, eps, silu, stats, x2=None, groups=32):
+    _chk_h(x1, x2, gamma, beta, out)
+    rows = x1.shape[0]
+    C1 = x1.shape[1]
+    C2 = x2.shape[1] if x2 is not None else 0
+    assert stats.dtype == torch.float32 and stats.numel() >= (rows // rows_per_stat) * groups * 2
+    _check(load().mofa_groupnorm(_p(x1), C1, _p(x2), C2, _p(gamma), _p(beta), _p(out), rows, rows_per_stat, groups,
+                                 eps, 1 if silu else 0, _p(stats), _stream()), "mofa_groupnorm")
+    return out
+
+
+def layernorm(x, gamma, beta, out, eps=1e-5, add=None, rows_per_group=1, add_period=1, sum_out=None):
+    _chk_h(x, gamma, beta, out, add, sum_out)
+    _check(load().mofa_layernorm(_p(x), _p(gamma), _p(beta), _p(out), x.shape[0], x.shape[1], eps, _p(add),
+                                 rows_per_group, add_period, _p(sum_out), _stream()), "mofa_layernorm")
+    return out
+
+
+def axpy_bcast(x, y, out, scale=1.0):
+    _chk_h(x, y, out)
+    _check(load().mofa_axpy_bcast(_p(x), _p(y), _p(out), x.numel(), y.numel(), scale, _stream()), "mofa_axpy_bcast")
+    return out
+
+
+def im2col3x3(x, out, n_img, H, W, C, stride, Kpad):
+    _chk_h(x, out)
+    _check(load().mofa_im2col3x3(_p(x), _p(out), n_img, H, W, C, stride, Kpad, _stream()), "mofa_im2col3x3")
+    return out
+
+
+def upsample2x(x, out, n_img, H, W, C):
+    _chk_h(x, out)
+    _check(load().mofa_upsample2x(_p(x), _p(out), n_img, H, W, C, _stream()), "mofa_upsample2x")
+    return out
+
+
+def nchw_to_nhwc(x, out, n_img, C, HW, ldo=None, c_off=0):
+    _chk_h(x, out)
+    _check(load().mofa_nchw_to_nhwc(_p(x), _p(out), n_img, C, HW, ldo if ldo is not None else C, c_off, _stream()),
+           "mofa_nchw_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw(x, out, n_img, C, HW, ldi=None, c_off=0):
+    _chk_h(x, out)
+    _check(load().mofa_nhwc_to_nchw(_p(x), _p(out), n_img, C, HW, ldi if ldi is not None else C, c_off, _stream()),
+           "mofa_nhwc_to_nchw")
+    return out
+
+
+def linear_small(a, w, bias, out, act_in=0, act_out=0):
+    _chk_h(a, w, bias, out)
+    M, K = a.shape
+    N = w.shape[0]
+    _check(load().mofa_linear_small(_p(a), _p(w), _p(bias), _p(out), M, N, K, act_in, act_out, _stream()),
+           "mofa_linear_small")
+    return out
+
+
+def timestep_embedding(t, out, dim):
+    assert t.dtype == torch.float32 and t.is_cuda
+    _chk_h(out)
+    _check(load().mofa_timestep_embedding(_p(t), _p(out), t.numel(), dim, _stream()), "mofa_timestep_embedding")
+    return out
+
+
+def softsplat_avg(feat, flow, acc, wsum, out, F, hs, ws, C, Hf, Wf):
+    _chk_h(feat, flow, out)
+    assert acc.dtype == torch.float32 and wsum.dtype == torch.float32
+    _check(load().mofa_softsplat_avg(_p(feat), _p(flow), _p(acc), _p(wsum), _p(out), F, hs, ws, C, Hf, Wf, _stream()),
+           "mofa_softsplat_avg")
+    return out
+
+
+def cfg_euler_step(noise, latents_h, image_latents, next_in, T, HW, g_min, g_max, sigma, sigma_next):
+    _chk_h(noise, latents_h, image_latents, next_in)
+    _check(load().mofa_cfg_euler_step(_p(noise), _p(latents_h), _p(image_latents), _p(next_in), T, HW, g_min, g_max,
+                                      sigma, sigma_next, _stream()), "mofa_cfg_euler_step")
+    return next_in

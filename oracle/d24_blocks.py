@@ -1,0 +1,488 @@
+"""ORACLE (test infrastructure, never imported by the product): CPU/fp32 restatement of the
+diffusers==0.24.0 blocks the reference instantiates.
+
+PARITY UNPINNED for this file: diffusers 0.24.0 is pinned by
+/root/reference/MOFA-Video-Traj/requirements.txt:1 but its source is neither under /root/reference nor
+installed here, and the reference ships no tests or golden vectors.  The algorithm
+below restates the published 0.24.0 implementation of
+  get_down_block / get_up_block / UNetMidBlockSpatioTemporal          (unet_3d_blocks.py)
+  SpatioTemporalResBlock / ResnetBlock2D / TemporalResnetBlock / AlphaBlender   (resnet.py)
+  TransformerSpatioTemporalModel                                       (transformer_temporal.py)
+  BasicTransformerBlock / TemporalBasicTransformerBlock / FeedForward / GEGLU   (attention.py)
+  Attention + AttnProcessor2_0                                         (attention_processor.py)
+  Timesteps / TimestepEmbedding                                        (embeddings.py)
+anchored on the reference's call sites
+(/root/reference/MOFA-Video-Traj/models/unet_spatio_temporal_condition_controlnet.py:137-143, 169-233;
+ /root/reference/MOFA-Video-Traj/models/controlnet_sdv.py:227-309) and on the one known answer the
+topology must reproduce: the SVD-XT UNet has 1,524,623,082 parameters (tests/test_oracle.py).
+Module/parameter names follow diffusers so reference-layout state dicts load unchanged.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+# ------------------------------------------------------------------------------------------------
+# embeddings.py
+# ------------------------------------------------------------------------------------------------
+def get_timestep_embedding(timesteps, embedding_dim, flip_sin_to_cos=False, downscale_freq_shift=1.0, scale=1.0,
+                           max_period=10000):
+    half_dim = embedding_dim // 2
+    exponent = -math.log(max_period) * torch.arange(0, half_dim, dtype=torch.float32, device=timesteps.device)
+    exponent = exponent / (half_dim - downscale_freq_shift)
+    emb = torch.exp(exponent)
+    emb = timesteps[:, None].float() * emb[None, :]
+    emb = scale * emb
+    emb = torch.cat([torch.sin(emb), torch.cos(emb)], dim=-1)
+    if flip_sin_to_cos:
+        emb = torch.cat([emb[:, half_dim:], emb[:, :half_dim]], dim=-1)
+    if embedding_dim % 2 == 1:
+        emb = F.pad(emb, (0, 1, 0, 0))
+    return emb
+
+
+class Timesteps(nn.Module):
+    def __init__(self, num_channels, flip_sin_to_cos, downscale_freq_shift):
+        super().__init__()
+        self.num_channels, self.flip_sin_to_cos, self.downscale_freq_shift = num_channels, flip_sin_to_cos, downscale_freq_shift
+
+    def forward(self, timesteps):
+        return get_timestep_embedding(timesteps, self.num_channels, self.flip_sin_to_cos, self.downscale_freq_shift)
+
+
+class TimestepEmbedding(nn.Module):
+    def __init__(self, in_channels, time_embed_dim, out_dim=None):
+        super().__init__()
+        self.linear_1 = nn.Linear(in_channels, time_embed_dim)
+        self.act = nn.SiLU()
+        self.linear_2 = nn.Linear(time_embed_dim, out_dim if out_dim is not None else time_embed_dim)
+
+    def forward(self, sample):
+        return self.linear_2(self.act(self.linear_1(sample)))
+
+
+# ------------------------------------------------------------------------------------------------
+# resnet.py
+# ------------------------------------------------------------------------------------------------
+class ResnetBlock2D(nn.Module):
+    def __init__(self, in_channels, out_channels, temb_channels, eps, groups=32):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(groups, in_channels, eps=eps, affine=True)
+        self.conv1 = nn.Conv2d(in_channels, out_channels, 3, padding=1)
+        self.time_emb_proj = nn.Linear(temb_channels, out_channels) if temb_channels is not None else None
+        self.norm2 = nn.GroupNorm(groups, out_channels, eps=eps, affine=True)
+        self.conv2 = nn.Conv2d(out_channels, out_channels, 3, padding=1)
+        self.conv_shortcut = nn.Conv2d(in_channels, out_channels, 1) if in_channels != out_channels else None
+
+    def forward(self, x, temb):
+        h = self.conv1(F.silu(self.norm1(x)))
+        if self.time_emb_proj is not None:
+            h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
+        h = self.conv2(F.silu(self.norm2(h)))
+        if self.conv_shortcut is not None:
+            x = self.conv_shortcut(x)
+        return x + h  # output_scale_factor = 1
+
+
+class TemporalResnetBlock(nn.Module):
+    def __init__(self, in_channels, out_channels, temb_channels, eps):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(32, in_channels, eps=eps, affine=True)
+        self.conv1 = nn.Conv3d(in_channels, out_channels, (3, 1, 1), padding=(1, 0, 0))
+        self.time_emb_proj = nn.Linear(temb_channels, out_channels) if temb_channels is not None else None
+        self.norm2 = nn.GroupNorm(32, out_channels, eps=eps, affine=True)
+        self.conv2 = nn.Conv3d(out_channels, out_channels, (3, 1, 1), padding=(1, 0, 0))
+        self.conv_shortcut = nn.Conv3d(in_channels, out_channels, 1) if in_channels != out_channels else None
+
+    def forward(self, x, temb):  # x [B, C, T, H, W], temb [B, T, temb_channels]
+        h = self.conv1(F.silu(self.norm1(x)))
+        if self.time_emb_proj is not None:
+            t = self.time_emb_proj(F.silu(temb))[:, :, :, None, None].permute(0, 2, 1, 3, 4)
+            h = h + t
+        h = self.conv2(F.silu(self.norm2(h)))
+        if self.conv_shortcut is not None:
+            x = self.conv_shortcut(x)
+        return x + h
+
+
+class AlphaBlender(nn.Module):
+    def __init__(self, alpha, merge_strategy="learned_with_images", switch_spatial_to_temporal_mix=False):
+        super().__init__()
+        self.merge_strategy = merge_strategy
+        self.switch_spatial_to_temporal_mix = switch_spatial_to_temporal_mix
+        if merge_strategy == "fixed":
+            self.register_buffer("mix_factor", torch.Tensor([alpha]))
+        else:
+            self.register_parameter("mix_factor", nn.Parameter(torch.Tensor([alpha])))
+
+    def get_alpha(self, image_only_indicator, ndims):
+        if self.merge_strategy == "fixed":
+            alpha = self.mix_factor
+        elif self.merge_strategy == "learned":
+            alpha = torch.sigmoid(self.mix_factor)
+        else:  # learned_with_images
+            alpha = torch.where(image_only_indicator.bool(), torch.ones(1, 1, device=image_only_indicator.device),
+                                torch.sigmoid(self.mix_factor)[..., None])
+            if ndims == 5:
+                alpha = alpha[:, None, :, None, None]
+            else:
+                alpha = alpha.reshape(-1)[:, None, None]
+        return alpha
+
+    def forward(self, x_spatial, x_temporal, image_only_indicator=None):
+        alpha = self.get_alpha(image_only_indicator, x_spatial.ndim).to(x_spatial.dtype)
+        if self.switch_spatial_to_temporal_mix:
+            alpha = 1.0 - alpha
+        return alpha * x_spatial + (1.0 - alpha) * x_temporal
+
+
+class SpatioTemporalResBlock(nn.Module):
+    def __init__(self, in_channels, out_channels, temb_channels, eps=1e-6, temporal_eps=None, merge_factor=0.5,
+                 merge_strategy="learned_with_images", switch_spatial_to_temporal_mix=False):
+        super().__init__()
+        self.spatial_res_block = ResnetBlock2D(in_channels, out_channels, temb_channels, eps)
+        self.temporal_res_block = TemporalResnetBlock(out_channels, out_channels, temb_channels,
+                                                      temporal_eps if temporal_eps is not None else eps)
+        self.time_mixer = AlphaBlender(merge_factor, merge_strategy, switch_spatial_to_temporal_mix)
+
+    def forward(self, hidden_states, temb, image_only_indicator):
+        num_frames = image_only_indicator.shape[-1]
+        hidden_states = self.spatial_res_block(hidden_states, temb)
+        bf, c, h, w = hidden_states.shape
+        b = bf // num_frames
+        hs_mix = hidden_states[None, :].reshape(b, num_frames, c, h, w).permute(0, 2, 1, 3, 4)
+        hidden_states = hidden_states[None, :].reshape(b, num_frames, c, h, w).permute(0, 2, 1, 3, 4)
+        if temb is not None:
+            temb = temb.reshape(b, num_frames, -1)
+        hidden_states = self.temporal_res_block(hidden_states, temb)
+        hidden_states = self.time_mixer(x_spatial=hs_mix, x_temporal=hidden_states,
+                                        image_only_indicator=image_only_indicator)
+        return hidden_states.permute(0, 2, 1, 3, 4).reshape(bf, c, h, w)
+
+
+class Downsample2D(nn.Module):
+    def __init__(self, channels):
+        super().__init__()
+        self.conv = nn.Conv2d(channels, channels, 3, stride=2, padding=1)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class Upsample2D(nn.Module):
+    def __init__(self, channels):
+        super().__init__()
+        self.conv = nn.Conv2d(channels, channels, 3, padding=1)
+
+    def forward(self, x):
+        return self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
+
+
+# ------------------------------------------------------------------------------------------------
+# attention.py / attention_processor.py
+# ------------------------------------------------------------------------------------------------
+class Attention(nn.Module):
+    def __init__(self, query_dim, heads, dim_head, cross_attention_dim=None):
+        super().__init__()
+        inner = heads * dim_head
+        self.heads = heads
+        kv_dim = cross_attention_dim if cross_attention_dim is not None else query_dim
+        self.to_q = nn.Linear(query_dim, inner, bias=False)
+        self.to_k = nn.Linear(kv_dim, inner, bias=False)
+        self.to_v = nn.Linear(kv_dim, inner, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(inner, query_dim), nn.Dropout(0.0)])
+
+    def forward(self, hidden_states, encoder_hidden_states=None):
+        ctx = hidden_states if encoder_hidden_states is None else encoder_hidden_states
+        b, n, _ = hidden_states.shape
+        q, k, v = self.to_q(hidden_states), self.to_k(ctx), self.to_v(ctx)
+        hd = q.shape[-1] // self.heads
+        q = q.view(b, -1, self.heads, hd).transpose(1, 2)
+        k = k.view(b, -1, self.heads, hd).transpose(1, 2)
+        v = v.view(b, -1, self.heads, hd).transpose(1, 2)
+        o = F.scaled_dot_product_attention(q, k, v)  # scale = hd ** -0.5
+        o = o.transpose(1, 2).reshape(b, -1, self.heads * hd)
+        return self.to_out[0](o)
+
+
+class GEGLU(nn.Module):
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+    def forward(self, x):
+        h, gate = self.proj(x).chunk(2, dim=-1)
+        return h * F.gelu(gate)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim, dim_out=None, mult=4):
+        super().__init__()
+        inner = int(dim * mult)
+        dim_out = dim_out if dim_out is not None else dim
+        self.net = nn.ModuleList([GEGLU(dim, inner), nn.Dropout(0.0), nn.Linear(inner, dim_out)])
+
+    def forward(self, x):
+        for m in self.net:
+            x = m(x)
+        return x
+
+
+class BasicTransformerBlock(nn.Module):
+    def __init__(self, dim, heads, dim_head, cross_attention_dim):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn1 = Attention(dim, heads, dim_head)
+        self.norm2 = nn.LayerNorm(dim)
+        self.attn2 = Attention(dim, heads, dim_head, cross_attention_dim)
+        self.norm3 = nn.LayerNorm(dim)
+        self.ff = FeedForward(dim)
+
+    def forward(self, x, encoder_hidden_states):
+        x = self.attn1(self.norm1(x)) + x
+        x = self.attn2(self.norm2(x), encoder_hidden_states) + x
+        x = self.ff(self.norm3(x)) + x
+        return x
+
+
+class TemporalBasicTransformerBlock(nn.Module):
+    def __init__(self, dim, time_mix_inner_dim, heads, dim_head, cross_attention_dim):
+        super().__init__()
+        self.is_res = dim == time_mix_inner_dim
+        self.norm_in = nn.LayerNorm(dim)
+        self.ff_in = FeedForward(dim, dim_out=time_mix_inner_dim)
+        self.norm1 = nn.LayerNorm(time_mix_inner_dim)
+        self.attn1 = Attention(time_mix_inner_dim, heads, dim_head)
+        self.norm2 = nn.LayerNorm(time_mix_inner_dim)
+        self.attn2 = Attention(time_mix_inner_dim, heads, dim_head, cross_attention_dim)
+        self.norm3 = nn.LayerNorm(time_mix_inner_dim)
+        self.ff = FeedForward(time_mix_inner_dim)
+
+    def forward(self, hidden_states, num_frames, encoder_hidden_states):
+        bf, s, c = hidden_states.shape
+        b = bf // num_frames
+        h = hidden_states[None, :].reshape(b, num_frames, s, c).permute(0, 2, 1, 3).reshape(b * s, num_frames, c)
+        residual = h
+        h = self.ff_in(self.norm_in(h))
+        if self.is_res:
+            h = h + residual
+        h = self.attn1(self.norm1(h)) + h
+        h = self.attn2(self.norm2(h), encoder_hidden_states) + h
+        ff = self.ff(self.norm3(h))
+        h = ff + h if self.is_res else ff
+        h = h[None, :].reshape(b, s, num_frames, c).permute(0, 2, 1, 3).reshape(b * num_frames, s, c)
+        return h
+
+
+# ------------------------------------------------------------------------------------------------
+# transformer_temporal.py
+# ------------------------------------------------------------------------------------------------
+class TransformerSpatioTemporalModel(nn.Module):
+    def __init__(self, num_attention_heads, attention_head_dim, in_channels, num_layers=1, cross_attention_dim=None):
+        super().__init__()
+        inner = num_attention_heads * attention_head_dim
+        self.in_channels = in_channels
+        self.norm = nn.GroupNorm(32, in_channels, eps=1e-6)
+        self.proj_in = nn.Linear(in_channels, inner)
+        self.transformer_blocks = nn.ModuleList(
+            [BasicTransformerBlock(inner, num_attention_heads, attention_head_dim, cross_attention_dim)
+             for _ in range(num_layers)])
+        self.temporal_transformer_blocks = nn.ModuleList(
+            [TemporalBasicTransformerBlock(inner, inner, num_attention_heads, attention_head_dim, cross_attention_dim)
+             for _ in range(num_layers)])
+        self.time_pos_embed = TimestepEmbedding(in_channels, in_channels * 4, out_dim=in_channels)
+        self.time_proj = Timesteps(in_channels, True, 0)
+        self.time_mixer = AlphaBlender(0.5, "learned_with_images")
+        self.proj_out = nn.Linear(inner, in_channels)
+
+    def forward(self, hidden_states, encoder_hidden_states, image_only_indicator):
+        bf, _, height, width = hidden_states.shape
+        num_frames = image_only_indicator.shape[-1]
+        b = bf // num_frames
+        time_context = encoder_hidden_states
+        tc_first = time_context[None, :].reshape(b, num_frames, -1, time_context.shape[-1])[:, 0]
+        # QUIRK (diffusers 0.24.0; reordered in later releases): the per-batch context is broadcast
+        # PIXEL-major [hw, b, 1, D] and flattened, while the temporal block's rows are batch-major
+        # (b*hw + p).  Row i therefore attends to the context of batch item (i % b).
+        time_context = tc_first[None, :].broadcast_to(height * width, b, 1, time_context.shape[-1])
+        time_context = time_context.reshape(height * width * b, 1, time_context.shape[-1])
+
+        residual = hidden_states
+        hidden_states = self.norm(hidden_states)
+        inner = hidden_states.shape[1]
+        hidden_states = hidden_states.permute(0, 2, 3, 1).reshape(bf, height * width, inner)
+        hidden_states = self.proj_in(hidden_states)
+
+        num_frames_emb = torch.arange(num_frames, device=hidden_states.device).repeat(b, 1).reshape(-1)
+        t_emb = self.time_proj(num_frames_emb).to(hidden_states.dtype)
+        emb = self.time_pos_embed(t_emb)[:, None, :]
+
+        for block, temporal_block in zip(self.transformer_blocks, self.temporal_transformer_blocks):
+            hidden_states = block(hidden_states, encoder_hidden_states)
+            hs_mix = hidden_states + emb
+            hs_mix = temporal_block(hs_mix, num_frames, time_context)
+            hidden_states = self.time_mixer(x_spatial=hidden_states, x_temporal=hs_mix,
+                                            image_only_indicator=image_only_indicator)
+        hidden_states = self.proj_out(hidden_states)
+        hidden_states = hidden_states.reshape(bf, height, width, inner).permute(0, 3, 1, 2).contiguous()
+        return hidden_states + residual
+
+
+# ------------------------------------------------------------------------------------------------
+# unet_3d_blocks.py
+# ------------------------------------------------------------------------------------------------
+class DownBlockSpatioTemporal(nn.Module):
+    has_cross_attention = False
+
+    def __init__(self, in_channels, out_channels, temb_channels, num_layers=1, add_downsample=True):
+        super().__init__()
+        self.resnets = nn.ModuleList([
+            SpatioTemporalResBlock(in_channels if i == 0 else out_channels, out_channels, temb_channels, eps=1e-5)
+            for i in range(num_layers)])
+        self.downsamplers = nn.ModuleList([Downsample2D(out_channels)]) if add_downsample else None
+
+    def forward(self, hidden_states, temb, image_only_indicator, encoder_hidden_states=None):
+        outs = ()
+        for resnet in self.resnets:
+            hidden_states = resnet(hidden_states, temb, image_only_indicator)
+            outs += (hidden_states,)
+        if self.downsamplers is not None:
+            hidden_states = self.downsamplers[0](hidden_states)
+            outs += (hidden_states,)
+        return hidden_states, outs
+
+
+class CrossAttnDownBlockSpatioTemporal(nn.Module):
+    has_cross_attention = True
+
+    def __init__(self, in_channels, out_channels, temb_channels, num_layers=1, transformer_layers_per_block=1,
+                 num_attention_heads=1, cross_attention_dim=1280, add_downsample=True):
+        super().__init__()
+        self.resnets = nn.ModuleList([
+            SpatioTemporalResBlock(in_channels if i == 0 else out_channels, out_channels, temb_channels, eps=1e-6)
+            for i in range(num_layers)])
+        self.attentions = nn.ModuleList([
+            TransformerSpatioTemporalModel(num_attention_heads, out_channels // num_attention_heads,
+                                           in_channels=out_channels, num_layers=transformer_layers_per_block,
+                                           cross_attention_dim=cross_attention_dim)
+            for _ in range(num_layers)])
+        self.downsamplers = nn.ModuleList([Downsample2D(out_channels)]) if add_downsample else None
+
+    def forward(self, hidden_states, temb, encoder_hidden_states, image_only_indicator):
+        outs = ()
+        for resnet, attn in zip(self.resnets, self.attentions):
+            hidden_states = resnet(hidden_states, temb, image_only_indicator)
+            hidden_states = attn(hidden_states, encoder_hidden_states, image_only_indicator)
+            outs += (hidden_states,)
+        if self.downsamplers is not None:
+            hidden_states = self.downsamplers[0](hidden_states)
+            outs += (hidden_states,)
+        return hidden_states, outs
+
+
+class UNetMidBlockSpatioTemporal(nn.Module):
+    has_cross_attention = True
+
+    def __init__(self, in_channels, temb_channels, num_layers=1, transformer_layers_per_block=1,
+                 num_attention_heads=1, cross_attention_dim=1280):
+        super().__init__()
+        resnets = [SpatioTemporalResBlock(in_channels, in_channels, temb_channels, eps=1e-5)]
+        attentions = []
+        for _ in range(num_layers):
+            attentions.append(TransformerSpatioTemporalModel(num_attention_heads, in_channels // num_attention_heads,
+                                                             in_channels=in_channels,
+                                                             num_layers=transformer_layers_per_block,
+                                                             cross_attention_dim=cross_attention_dim))
+            resnets.append(SpatioTemporalResBlock(in_channels, in_channels, temb_channels, eps=1e-5))
+        self.attentions = nn.ModuleList(attentions)
+        self.resnets = nn.ModuleList(resnets)
+
+    def forward(self, hidden_states, temb, encoder_hidden_states, image_only_indicator):
+        hidden_states = self.resnets[0](hidden_states, temb, image_only_indicator)
+        for attn, resnet in zip(self.attentions, self.resnets[1:]):
+            hidden_states = attn(hidden_states, encoder_hidden_states, image_only_indicator)
+            hidden_states = resnet(hidden_states, temb, image_only_indicator)
+        return hidden_states
+
+
+class UpBlockSpatioTemporal(nn.Module):
+    has_cross_attention = False
+
+    def __init__(self, in_channels, prev_output_channel, out_channels, temb_channels, num_layers=1, resnet_eps=1e-6,
+                 add_upsample=True):
+        super().__init__()
+        resnets = []
+        for i in range(num_layers):
+            res_skip = in_channels if i == num_layers - 1 else out_channels
+            rin = prev_output_channel if i == 0 else out_channels
+            resnets.append(SpatioTemporalResBlock(rin + res_skip, out_channels, temb_channels, eps=resnet_eps))
+        self.resnets = nn.ModuleList(resnets)
+        self.upsamplers = nn.ModuleList([Upsample2D(out_channels)]) if add_upsample else None
+
+    def forward(self, hidden_states, res_hidden_states_tuple, temb, image_only_indicator, encoder_hidden_states=None):
+        for resnet in self.resnets:
+            res = res_hidden_states_tuple[-1]
+            res_hidden_states_tuple = res_hidden_states_tuple[:-1]
+            hidden_states = torch.cat([hidden_states, res], dim=1)
+            hidden_states = resnet(hidden_states, temb, image_only_indicator)
+        if self.upsamplers is not None:
+            hidden_states = self.upsamplers[0](hidden_states)
+        return hidden_states
+
+
+class CrossAttnUpBlockSpatioTemporal(nn.Module):
+    has_cross_attention = True
+
+    def __init__(self, in_channels, out_channels, prev_output_channel, temb_channels, num_layers=1,
+                 transformer_layers_per_block=1, resnet_eps=1e-6, num_attention_heads=1, cross_attention_dim=1280,
+                 add_upsample=True):
+        super().__init__()
+        resnets, attentions = [], []
+        for i in range(num_layers):
+            res_skip = in_channels if i == num_layers - 1 else out_channels
+            rin = prev_output_channel if i == 0 else out_channels
+            resnets.append(SpatioTemporalResBlock(rin + res_skip, out_channels, temb_channels, eps=resnet_eps))
+            attentions.append(TransformerSpatioTemporalModel(num_attention_heads, out_channels // num_attention_heads,
+                                                             in_channels=out_channels,
+                                                             num_layers=transformer_layers_per_block,
+                                                             cross_attention_dim=cross_attention_dim))
+        self.resnets = nn.ModuleList(resnets)
+        self.attentions = nn.ModuleList(attentions)
+        self.upsamplers = nn.ModuleList([Upsample2D(out_channels)]) if add_upsample else None
+
+    def forward(self, hidden_states, res_hidden_states_tuple, temb, encoder_hidden_states, image_only_indicator):
+        for resnet, attn in zip(self.resnets, self.attentions):
+            res = res_hidden_states_tuple[-1]
+            res_hidden_states_tuple = res_hidden_states_tuple[:-1]
+            hidden_states = torch.cat([hidden_states, res], dim=1)
+            hidden_states = resnet(hidden_states, temb, image_only_indicator)
+            hidden_states = attn(hidden_states, encoder_hidden_states, image_only_indicator)
+        if self.upsamplers is not None:
+            hidden_states = self.upsamplers[0](hidden_states)
+        return hidden_states
+
+
+def get_down_block(down_block_type, num_layers, in_channels, out_channels, temb_channels, add_downsample,
+                   num_attention_heads, cross_attention_dim, transformer_layers_per_block=1, **_unused):
+    if down_block_type == "DownBlockSpatioTemporal":
+        return DownBlockSpatioTemporal(in_channels, out_channels, temb_channels, num_layers, add_downsample)
+    if down_block_type == "CrossAttnDownBlockSpatioTemporal":
+        return CrossAttnDownBlockSpatioTemporal(in_channels, out_channels, temb_channels, num_layers,
+                                                transformer_layers_per_block, num_attention_heads,
+                                                cross_attention_dim, add_downsample)
+    raise ValueError(down_block_type)
+
+
+def get_up_block(up_block_type, num_layers, in_channels, out_channels, prev_output_channel, temb_channels,
+                 add_upsample, resnet_eps, num_attention_heads, cross_attention_dim, transformer_layers_per_block=1,
+                 **_unused):
+    if up_block_type == "UpBlockSpatioTemporal":
+        return UpBlockSpatioTemporal(in_channels, prev_output_channel, out_channels, temb_channels, num_layers,
+                                     resnet_eps, add_upsample)
+    if up_block_type == "CrossAttnUpBlockSpatioTemporal":
+        return CrossAttnUpBlockSpatioTemporal(in_channels, out_channels, prev_output_channel, temb_channels,
+                                              num_layers, transformer_layers_per_block, resnet_eps,
+                                              num_attention_heads, cross_attention_dim, add_upsample)
+    raise ValueError(up_block_type)
