@@ -1,0 +1,333 @@
+"""bench.py -- headline benchmark of the MOFA-Video hot path on B200 (contract: see the task prompt).
+
+    python bench.py --gpus N --steps K --warmup W            # engine arm (this repo's sm_100a path)
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the oracle restatement of the reference
+
+Metric (BASELINE.json): frames/sec @ 576x1024x25f, 25 Euler steps.  One "step" of this benchmark is ONE CLIP
+through FlowControlNetPipeline.__call__ (CLIP embed + VAE encode + adapter cond branch + 25 x (adapter + UNet +
+CFG + Euler) + VAE decode) = configs[1] of BASELINE.json.  Synthetic image / flow, random-init weights in the
+reference checkpoint layout (no network here).
+  value : device-resident inputs (image, flow, initial noise already in HBM), frames left on the device.
+  e2e   : the reference-facing call with HOST inputs (PIL image, host flow tensor) and uint8 frames copied back
+          to the host; for N>1 the frames of all ranks are gathered to rank 0 with NCCL inside the timed region.
+  roofline : dominant kernel family (tcgen05 GEMM / implicit-GEMM conv), CUDA-event timed per launch on the
+          launching stream during the last timed clip; algorithmic FLOPs = 2*M*N*K of each launch.
+  cpu_baseline : the fp32 oracle on the host cores, bounded sample (see _cpu_sample).
+Multi-GPU: independent clips per rank (weak scaling), no collective on the data path except the final gather.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, T, STEPS = 576, 1024, 25, 25
+METRIC = "frames/sec @ 576x1024x25f, 25 steps"
+
+
+def _peaks():
+    fn = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(fn):
+        with open(fn) as f:
+            p = json.load(f)
+        return {"tflops_burst": p["bf16_tflops"], "tflops_sustained": p["bf16_tflops_sustained"],
+                "hbm_gbs": p["hbm_gbs"], "src": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_burst": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = max([int(float(r[2])) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (oracle): bounded sample of the same workload
+# ------------------------------------------------------------------------------------------------
+def _cpu_sample(steps, warmup, frames_per_half=2, budget_s=240.0):
+    """One denoise step (adapter trunk + cond branch + UNet, fp32) at 576x1024 on 2*frames_per_half of the 50
+    CFG-batched frames, on all host cores; clip time is extrapolated x(50/frames) x25 steps (VAE/CLIP excluded).
+    If `steps` such samples would not fit `budget_s` (judged from the first evaluation) the spatial size is halved
+    (and the extrapolation multiplied by the FLOP ratio of the two shapes) -- said in `sample`.
+    Returns (frames_per_sec, seconds_per_sample, cores, description)."""
+    from oracle import fixtures
+    from oracle.models import FlowControlNet, UNetSpatioTemporalConditionControlNetModel
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = dict(num_frames=frames_per_half)
+    with torch.device("meta"):
+        unet = UNetSpatioTemporalConditionControlNetModel(**cfg)
+        adapter = FlowControlNet(**cfg)
+    for m in (unet, adapter):
+        m.to_empty(device="cpu")
+        with torch.no_grad():
+            for n_, p in m.named_parameters():
+                if p.ndim > 1:
+                    p.normal_(0.0, 0.02)
+                elif n_.endswith("weight"):
+                    p.fill_(1.0)
+                else:
+                    p.zero_()
+        m.eval()
+    g = torch.Generator().manual_seed(0)
+    Tm = frames_per_half
+    emb = torch.randn(2, 1, 1024, generator=g)
+    ids = torch.tensor([[6.0, 128.0, 0.02]] * 2)
+    t = torch.tensor(1.6377)
+    # (height, width, per-frame step FLOPs relative to 576x1024): from SURVEY.md App. B, conv+linear 173.8 TF
+    # scale with the token count, attention 43.4 TF with its square: (173.8/4 + 43.4/16)/217.2 = 0.212, etc.
+    shapes = [(H, W, 1.0), (H // 2, W // 2, 0.212), (H // 4, W // 4, 0.0505)]
+
+    def make(hh, ww):
+        sample = torch.randn(2, Tm, 8, hh // 8, ww // 8, generator=g)
+        cond = torch.rand(2, 3, hh, ww, generator=g) * 2 - 1
+        flow = torch.randn(2, Tm - 1, 2, hh, ww, generator=g)
+
+        def one():
+            with torch.no_grad():
+                dres, mid, _, _ = adapter(sample, t, emb, ids, controlnet_cond=cond, controlnet_flow=flow)
+                return unet(sample, t, emb, dres, mid, added_time_ids=ids)[0]
+        return one
+
+    for (hh, ww, rel) in shapes:
+        one = make(hh, ww)
+        t0 = time.perf_counter()
+        one()  # first evaluation doubles as warm-up and as the budget probe
+        probe = time.perf_counter() - t0
+        if probe * (steps + max(warmup - 1, 0)) <= budget_s or (hh, ww) == shapes[-1][:2]:
+            break
+    for _ in range(max(warmup - 1, 0)):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / steps
+    clip_s = dt / rel * (2 * T / (2 * Tm)) * STEPS
+    desc = (f"1 denoise step (oracle adapter+UNet, fp32, {cores} threads) at {hh}x{ww} on {2 * Tm} of {2 * T} frames; "
+            f"clip time = sample x{1 / rel:.2f} (FLOP ratio to 576x1024) x{T / Tm:.1f} (frames) x{STEPS} steps; "
+            "VAE/CLIP excluded")
+    return T / clip_s, dt, cores, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    fps, dt, cores, desc = _cpu_sample(max(args.steps, 1), min(args.warmup, 1))
+    out = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+           "config": {"workload": "configs[1]: Traj adapter 576x1024, 25 frames, 25 steps", "sample": desc},
+           "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc},
+           "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# engine arm
+# ------------------------------------------------------------------------------------------------
+def run_engine(args):
+    import torch.distributed as dist
+    from mofa_video_b200 import lib
+    from mofa_video_b200.factory import build_synthetic_pipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib.load()
+
+    # per-rank clip (independent clips, seeds 1234+rank / 1235+rank -- SURVEY.md §8d config 5)
+    import numpy as np
+    import PIL.Image
+    g = torch.Generator().manual_seed(1234 + rank)
+    img = torch.nn.functional.avg_pool2d(torch.rand(1, 3, H + 8, W + 8, generator=g), 9, stride=1)[0]
+    img = (img - img.min()) / (img.max() - img.min())
+    img_u8 = (img * 255).round().to(torch.uint8).permute(1, 2, 0).contiguous().numpy()
+    pil = PIL.Image.fromarray(img_u8)
+    g2 = torch.Generator().manual_seed(1235 + rank)
+    ys = torch.arange(H, dtype=torch.float32)[:, None] / H
+    xs = torch.arange(W, dtype=torch.float32)[None, :] / W
+    base = torch.stack([(torch.sin(6.2832 * ys) * torch.cos(6.2832 * xs)).expand(H, W),
+                        (torch.cos(6.2832 * ys) * torch.sin(6.2832 * xs)).expand(H, W)], 0) * (0.06 * H)
+    flow_host = torch.stack([(i + 1) / (T - 1) * base + torch.randn(2, H, W, generator=g2) for i in range(T - 1)])[None]
+    flow_host = flow_host.half().pin_memory()
+
+    pipe = build_synthetic_pipeline(device=dev, seed=0)
+    img_dev = (torch.from_numpy(img_u8).permute(2, 0, 1).float() / 255.0).to(dev)  # [3,H,W] in [0,1]
+    flow_dev = flow_host.to(dev)
+    lat_gen = torch.Generator(device=dev).manual_seed(42 + rank)
+
+    def clip_device():
+        return pipe(img_dev, img_dev, flow_dev, height=H, width=W, num_frames=T, num_inference_steps=STEPS,
+                    decode_chunk_size=8, generator=lat_gen, output_type="pt")
+
+    gather_buf = None
+    if world > 1 and rank == 0:
+        gather_buf = [torch.empty(T, H, W, 3, dtype=torch.uint8, device=dev) for _ in range(world)]
+    host_out = torch.empty(world if rank == 0 else 1, T, H, W, 3, dtype=torch.uint8).pin_memory()
+
+    def clip_e2e():
+        out = pipe(pil, pil, flow_host, height=H, width=W, num_frames=T, num_inference_steps=STEPS,
+                   decode_chunk_size=8, generator=lat_gen, output_type="pt")
+        vid = out.frames[0]  # [T, 3, H, W] in [0,1] on the device
+        u8 = (vid * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+        if world > 1:
+            dist.gather(u8, gather_buf if rank == 0 else None, dst=0)
+            if rank == 0:
+                for r in range(world):
+                    host_out[r].copy_(gather_buf[r], non_blocking=True)
+        else:
+            host_out[0].copy_(u8, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        sync_all()
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 0)):
+        clip_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.launch_count_reset()
+    K = max(args.steps, 1)
+    if K > 1:
+        ms_dev = timed(clip_device, K - 1)
+    else:
+        ms_dev = 0.0
+    # last timed clip: per-launch CUDA events for the roofline line
+    lib.profile_start()
+    ms_last = timed(clip_device, 1)
+    prof = lib.profile_stop()
+    tim = pipe.last_timings_ms()
+    ms_dev += ms_last
+    launches = lib.launch_count()
+    ms_e2e = timed(clip_e2e, K)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        peaks = _peaks()
+        fps = world * K * T / (ms_dev / 1e3)
+        fps_e2e = world * K * T / (ms_e2e / 1e3)
+        gem = {k: v for k, v in prof.items() if k.startswith("gemm_")}
+        g_ms = sum(v["ms"] for v in gem.values())
+        g_fl = sum(v["work"] for v in gem.values())
+        g_n = sum(v["launches"] for v in gem.values())
+        ach = g_fl / (g_ms * 1e-3) / 1e12 if g_ms else 0.0
+        traffic = None
+        tf = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+        if os.path.exists(tf):
+            with open(tf) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        att = prof.get("attn_spatial", {"ms": 0.0, "work": 0.0, "launches": 0})
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (linear / conv3x3 / temporal3 implicit GEMM)",
+                "achieved": round(ach, 1), "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                "frac": round(ach / peaks["tflops_sustained"], 4), "traffic": traffic,
+                "peak_source": peaks["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+                "launches_timed": g_n, "avg_launch_ms": round(g_ms / max(g_n, 1), 4),
+                "flops_per_launch_avg": g_fl / max(g_n, 1),
+                "share_of_clip": round(g_ms / ms_last, 4),
+                "by_kind": {k: {"ms": round(v["ms"], 2), "tflops": round(v["work"] / (v["ms"] * 1e-3) / 1e12, 1),
+                                "launches": v["launches"]} for k, v in prof.items()},
+                "attention": {"achieved": round(att["work"] / max(att["ms"], 1e-9) / 1e9, 1), "unit": "TFLOP/s",
+                              "share_of_clip": round(att["ms"] / ms_last, 4)}}
+        cpu = None
+        if not args.no_cpu_baseline:
+            cfps, cdt, cores, desc = _cpu_sample(1, 1)
+            cpu = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc,
+                   "seconds_per_sample": round(cdt, 2)}
+        h2d = img_u8.nbytes * 2 + flow_host.numel() * 2
+        d2h = world * T * H * W * 3
+        out = {"metric": METRIC, "value": round(fps, 4), "unit": "frames/s", "n_gpus": world, "steps": K,
+               "warmup": args.warmup, "ms_per_step": round(ms_dev / K, 2), "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
+               "config": {"workload": "configs[1]: Traj adapter 576x1024, 25 frames, 25 steps, fp16, CFG 1->3",
+                          "step": "one clip through FlowControlNetPipeline.__call__", "clips_per_gpu_per_step": 1,
+                          "parallelism": f"clip-parallel x{world}", "l2": "working set >> L2 (each level-0 "
+                          "activation is 295 MB; weights 4.4 GB)",
+                          "vae_clip": "interim PyTorch eager modules (SURVEY 8f row 1); hot loop is native",
+                          "phase_ms_last_clip": {k: round(v, 1) for k, v in tim.items()}},
+               "roofline": roof, "cpu_baseline": cpu,
+               "e2e": {"value": round(fps_e2e, 4), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
+                       "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e / K, 2)},
+               "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -44,7 +44,7 @@ void mofa_launch_count_reset(void);
  *             by TMA out-of-bounds handling (replaces cuDNN Conv2d inside ResnetBlock2D etc.).
  *   TEMPORAL3 A is [B, T, HW, C]; implicit GEMM of Conv3d kernel (3,1,1) pad (1,0,0) along T,
  *             K = 3*C ordered (kt, c) (TemporalResnetBlock of SpatioTemporalResBlock).
- * Epilogue (fp32):  v = acc + bias[n] + rowbias[row / rows_per_group, n]
+ * Epilogue (fp32):  v = acc + bias[n] + rowbias[row / rows_per_group  (or row % rowbias_mod), n]
  *                   v = act(v)           act: 0 none, 1 SiLU, 2 GEGLU (see below)
  *                   v = alpha * v + beta1 * res1[row, n] + beta2 * res2[row, n]      -> fp16
  * GEGLU (act=2): weight rows are packed per N tile as [bn/2 value rows | bn/2 gate rows]; the
@@ -74,6 +74,8 @@ typedef struct mofa_gemm_args {
   const void* rowbias;    /* fp16 [groups, ld_rowbias] or NULL */
   int64_t ld_rowbias;
   int64_t rows_per_group;
+  int64_t rowbias_mod;    /* > 0: rowbias row = row % rowbias_mod (diffusers 0.24 temporal cross-attention
+                             context ordering quirk); 0: rowbias row = row / rows_per_group */
   const void* res1;       /* fp16 [rows, ldr1] or NULL */
   int64_t ldr1;
   const void* res2;

@@ -43,6 +43,8 @@ struct GemmKernelParams {
     const __half* rowbias;
     long long ld_rowbias;
     long long rows_per_group;
+    long long rowbias_mod;  // > 0: group = row % rowbias_mod instead of row / rows_per_group
+    int vec_ok;             // all leading dimensions are multiples of 8 -> 16-byte epilogue accesses
     const __half* res1;
     long long ldr1;
     const __half* res2;
@@ -85,7 +87,7 @@ union H8 {
 // one group of 8 consecutive output columns of one row: bias / rowbias / activation / residuals / store
 MOFA_DEVICE void epilogue_store8(const GemmKernelParams& p, float (&v)[8], long long row, long long group, int n_bias,
                                  int n_out, bool act_silu, bool add_bias) {
-    const bool full = (n_out + 8 <= p.N_out);
+    const bool full = p.vec_ok && (n_out + 8 <= p.N_out);
     const bool use_bias = add_bias && p.bias != nullptr;
     const bool use_rowbias = add_bias && p.rowbias != nullptr;
     if (full) {
@@ -276,7 +278,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 valid = pp < p.HW;
                 row = static_cast<long long>(tc.frame) * p.HW + pp;
             }
-            const long long group = p.rowbias ? row / p.rows_per_group : 0;
+            const long long group =
+                p.rowbias ? (p.rowbias_mod > 0 ? row % p.rowbias_mod : row / p.rows_per_group) : 0;
 
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
@@ -452,9 +455,10 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
         set_last_error("mofa_gemm: bad N=%d for bn=%d", a->N, bn);
         return MOFA_ERR_ARG;
     }
-    if ((a->ldc % 8) != 0 || (a->res1 && (a->ldr1 % 8)) || (a->res2 && (a->ldr2 % 8)) ||
-        (a->rowbias && (a->ld_rowbias % 8))) {
-        set_last_error("mofa_gemm: ldc / ldr / ld_rowbias must be multiples of 8 elements");
+    const bool vec_ok = (a->ldc % 8) == 0 && !(a->res1 && (a->ldr1 % 8)) && !(a->res2 && (a->ldr2 % 8)) &&
+                        !(a->rowbias && (a->ld_rowbias % 8));
+    if (geglu && !vec_ok) {
+        set_last_error("mofa_gemm: GEGLU needs ldc / ldr multiples of 8 elements");
         return MOFA_ERR_ARG;
     }
 
@@ -471,6 +475,8 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
     p.rowbias = static_cast<const __half*>(a->rowbias);
     p.ld_rowbias = a->ld_rowbias;
     p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
+    p.rowbias_mod = a->rowbias_mod;
+    p.vec_ok = vec_ok ? 1 : 0;
     p.res1 = static_cast<const __half*>(a->res1);
     p.ldr1 = a->ldr1;
     p.res2 = static_cast<const __half*>(a->res2);

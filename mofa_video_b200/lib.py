@@ -35,7 +35,7 @@ class GemmArgs(ctypes.Structure):
         ("B", ctypes.c_int32), ("T", ctypes.c_int32), ("HW", ctypes.c_int32),
         ("N", ctypes.c_int32), ("bn", ctypes.c_int32),
         ("bias", ctypes.c_void_p), ("rowbias", ctypes.c_void_p), ("ld_rowbias", ctypes.c_int64),
-        ("rows_per_group", ctypes.c_int64),
+        ("rows_per_group", ctypes.c_int64), ("rowbias_mod", ctypes.c_int64),
         ("res1", ctypes.c_void_p), ("ldr1", ctypes.c_int64), ("res2", ctypes.c_void_p), ("ldr2", ctypes.c_int64),
         ("alpha", ctypes.c_float), ("beta1", ctypes.c_float), ("beta2", ctypes.c_float),
         ("max_ctas", ctypes.c_int32),
@@ -99,6 +99,46 @@ def launch_count():
     return int(load().mofa_launch_count())
 
 
+# optional per-launch device timing (CUDA events on the launching stream) used by bench.py's roofline line
+_prof = None
+
+
+def profile_start():
+    global _prof
+    _prof = []
+
+
+def profile_stop():
+    """-> {kind: {"ms": device time, "work": algorithmic FLOPs (or bytes), "launches": n}}"""
+    global _prof
+    rec, _prof = _prof, None
+    torch.cuda.synchronize()
+    out = {}
+    for kind, work, e0, e1 in rec or []:
+        d = out.setdefault(kind, {"ms": 0.0, "work": 0.0, "launches": 0})
+        d["ms"] += e0.elapsed_time(e1)
+        d["work"] += work
+        d["launches"] += 1
+    return out
+
+
+class _Timed:
+    def __init__(self, kind, work):
+        self.kind, self.work = kind, work
+
+    def __enter__(self):
+        if _prof is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if _prof is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _prof.append((self.kind, self.work, self.e0, e1))
+        return False
+
+
 def launch_count_reset():
     load().mofa_launch_count_reset()
 
@@ -123,10 +163,12 @@ def pick_bn(n, geglu=False):
 
 
 def gemm(mode, a, w, out, *, N, bn=None, act=ACT_NONE, a2=None, M=0, K=0, K1=0, lda=0, lda2=0, n_img=0, H=0, W=0,
-         C=0, B=0, T=0, HW=0, ldc=None, bias=None, rowbias=None, rows_per_group=1, res1=None, res2=None, alpha=1.0,
-         beta1=1.0, beta2=1.0, max_ctas=0):
+         C=0, B=0, T=0, HW=0, ldc=None, bias=None, rowbias=None, rows_per_group=1, rowbias_mod=0, res1=None, res2=None,
+         alpha=1.0, beta1=1.0, beta2=1.0, max_ctas=0):
     lib = load()
-    _chk_h(a, a2, w, out, bias, rowbias, res1, res2)
+    _chk_h(a, a2, w, out, bias, res1, res2)
+    if rowbias is not None:  # may be a column slice of a wider [groups, total] matrix
+        assert rowbias.is_cuda and rowbias.dtype == torch.float16 and rowbias.stride(-1) == 1
     g = GemmArgs()
     g.mode, g.act = mode, act
     g.a, g.a2, g.w, g.out = a.data_ptr(), (a2.data_ptr() if a2 is not None else None), w.data_ptr(), out.data_ptr()
@@ -138,7 +180,8 @@ def gemm(mode, a, w, out, *, N, bn=None, act=ACT_NONE, a2=None, M=0, K=0, K1=0, 
     g.bn = bn if bn is not None else pick_bn(N, act == ACT_GEGLU)
     g.bias = bias.data_ptr() if bias is not None else None
     if rowbias is not None:
-        g.rowbias, g.ld_rowbias, g.rows_per_group = rowbias.data_ptr(), rowbias.shape[-1], rows_per_group
+        g.rowbias, g.ld_rowbias, g.rows_per_group = rowbias.data_ptr(), rowbias.stride(0), rows_per_group
+        g.rowbias_mod = rowbias_mod
     else:
         g.rowbias, g.ld_rowbias, g.rows_per_group = None, 0, 1
     g.res1 = res1.data_ptr() if res1 is not None else None
@@ -147,6 +190,16 @@ def gemm(mode, a, w, out, *, N, bn=None, act=ACT_NONE, a2=None, M=0, K=0, K1=0, 
     g.ldr2 = res2.shape[-1] if res2 is not None else 0
     g.alpha, g.beta1, g.beta2 = alpha, beta1, beta2
     g.max_ctas = max_ctas
+    if _prof is not None:
+        if mode == A_LINEAR:
+            kind, work = "gemm_linear", 2.0 * M * N * K
+        elif mode == A_CONV3X3:
+            kind, work = "gemm_conv3x3", 2.0 * n_img * H * W * N * 9 * C
+        else:
+            kind, work = "gemm_temporal3", 2.0 * B * T * HW * N * 3 * C
+        with _Timed(kind, work):
+            _check(lib.mofa_gemm(ctypes.byref(g), _stream()), "mofa_gemm")
+        return out
     _check(lib.mofa_gemm(ctypes.byref(g), _stream()), "mofa_gemm")
     return out
 
@@ -159,7 +212,8 @@ def linear(a, w, out, **kw):
 
 def attn_spatial(qkv, out, frames, L, heads, scale):
     _chk_h(qkv, out)
-    _check(load().mofa_attn_spatial(_p(qkv), _p(out), frames, L, heads, scale, _stream()), "mofa_attn_spatial")
+    with _Timed("attn_spatial", 4.0 * frames * heads * L * L * 64):
+        _check(load().mofa_attn_spatial(_p(qkv), _p(out), frames, L, heads, scale, _stream()), "mofa_attn_spatial")
     return out
 
 

@@ -1,0 +1,130 @@
+"""Shared plumbing of the engine-backed model classes: config bag, checkpoint reading (config.json +
+diffusion_pytorch_model[.fp16].safetensors, the layout in /root/reference/MOFA-Video-Traj/README.md:20-38
+and /root/reference/MOFA-Video-Hybrid/ckpt_tree.md:60-84), the few nn.Module-like methods the reference's
+callers touch (/root/reference/MOFA-Video-Traj/run_gradio.py:119-128), and NCHW<->channels-last
+conversion at the API boundary."""
+import json
+import os
+from types import SimpleNamespace
+
+import torch
+
+from mofa_video_b200 import engine
+from mofa_video_b200 import lib as _lib
+
+DEFAULT_CONFIG = dict(
+    sample_size=None, in_channels=8, out_channels=4,
+    down_block_types=("CrossAttnDownBlockSpatioTemporal", "CrossAttnDownBlockSpatioTemporal",
+                      "CrossAttnDownBlockSpatioTemporal", "DownBlockSpatioTemporal"),
+    up_block_types=("UpBlockSpatioTemporal", "CrossAttnUpBlockSpatioTemporal", "CrossAttnUpBlockSpatioTemporal",
+                    "CrossAttnUpBlockSpatioTemporal"),
+    block_out_channels=(320, 640, 1280, 1280), addition_time_embed_dim=256,
+    projection_class_embeddings_input_dim=768, layers_per_block=2, cross_attention_dim=1024,
+    transformer_layers_per_block=1, num_attention_heads=(5, 10, 10, 20), num_frames=25,
+    conditioning_channels=3, conditioning_embedding_out_channels=(16, 32, 96, 256),
+)
+
+
+def read_checkpoint(path, subfolder=None, variant=None):
+    d = os.path.join(path, subfolder) if subfolder else path
+    with open(os.path.join(d, "config.json")) as f:
+        cfg = {k: v for k, v in json.load(f).items() if not k.startswith("_")}
+    names = []
+    if variant:
+        names.append(f"diffusion_pytorch_model.{variant}.safetensors")
+    names += ["diffusion_pytorch_model.safetensors", "diffusion_pytorch_model.fp16.safetensors"]
+    for n in names:
+        fn = os.path.join(d, n)
+        if os.path.exists(fn):
+            from safetensors.torch import load_file
+            return cfg, load_file(fn)
+    raise FileNotFoundError(f"no diffusion_pytorch_model*.safetensors under {d}")
+
+
+class EngineModel:
+    """Base of UNetSpatioTemporalConditionControlNetModel / FlowControlNet."""
+
+    kind = None
+
+    def __init__(self, state_dict, config=None, device="cuda", ops=None):
+        cfg = dict(DEFAULT_CONFIG)
+        cfg.update(config or {})
+        self.config = SimpleNamespace(**cfg)
+        self._cfg = cfg
+        self._device = torch.device(device)
+        self._ops = ops if ops is not None else _lib
+        if ops is None:
+            _lib.load()  # fail loudly right here when the CUDA library is missing
+        self.net = engine.Net(self.kind, state_dict, cfg, self._ops, self._device)
+        self.add_embedding = SimpleNamespace(linear_1=SimpleNamespace(
+            in_features=int(state_dict["add_embedding.linear_1.weight"].shape[1])))
+        self._clip_key = None
+
+    # -- construction --------------------------------------------------------------------------
+    @classmethod
+    def from_pretrained(cls, path, subfolder=None, variant=None, low_cpu_mem_usage=True, torch_dtype=None,
+                        device="cuda", **_ignored):
+        cfg, sd = read_checkpoint(path, subfolder, variant)
+        return cls(sd, cfg, device=device)
+
+    @classmethod
+    def from_state_dict(cls, state_dict, config=None, device="cuda", ops=None):
+        return cls(state_dict, config, device=device, ops=ops)
+
+    # -- nn.Module look-alikes the reference scripts call ---------------------------------------
+    @property
+    def dtype(self):
+        return torch.float16
+
+    @property
+    def device(self):
+        return self._device
+
+    def to(self, *args, **kwargs):
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.dtype) and a != torch.float16:
+                raise ValueError("the sm_100a engine computes in fp16 only")
+        return self
+
+    def requires_grad_(self, flag=False):
+        if flag:
+            raise ValueError("inference engine: no gradients")
+        return self
+
+    def eval(self):
+        return self
+
+    def parameters(self):
+        return iter(())
+
+    def enable_xformers_memory_efficient_attention(self, *a, **k):
+        return self  # attention is already the fused tcgen05 kernel
+
+    def enable_gradient_checkpointing(self):
+        raise ValueError("inference engine: no gradients")
+
+    # -- helpers --------------------------------------------------------------------------------
+    def _prepare(self, encoder_hidden_states, added_time_ids):
+        key = (encoder_hidden_states.data_ptr(), encoder_hidden_states._version, added_time_ids.data_ptr(),
+               added_time_ids._version, tuple(encoder_hidden_states.shape))
+        if key != self._clip_key:
+            self.net.prepare_clip(encoder_hidden_states.to(self._device), added_time_ids.to(self._device))
+            self._clip_key = key
+
+    def _to_cl(self, x5):
+        """[B, T, C, h, w] (any float dtype) -> channels-last fp16 [B*T*h*w, C]."""
+        b, t, c, h, w = x5.shape
+        src = x5.to(device=self._device, dtype=torch.float16).contiguous()
+        out = torch.empty(b * t * h * w, c, dtype=torch.float16, device=self._device)
+        self._ops.nchw_to_nhwc(src, out, b * t, c, h * w)
+        return out
+
+    def _from_cl(self, x, n_img, h, w):
+        c = x.shape[1]
+        out = torch.empty(n_img, c, h, w, dtype=torch.float16, device=self._device)
+        self._ops.nhwc_to_nchw(x, out, n_img, c, h * w)
+        return out
+
+    @staticmethod
+    def _t_value(timestep):
+        return float(timestep)

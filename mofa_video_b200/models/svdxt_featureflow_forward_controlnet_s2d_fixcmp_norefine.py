@@ -1,0 +1,80 @@
+"""FlowControlNet (MOFA-Adapter, trajectory variant) with the reference's entry point
+(/root/reference/MOFA-Video-Traj/models/svdxt_featureflow_forward_controlnet_s2d_fixcmp_norefine.py:180-383),
+executed by the sm_100a engine.  forward keeps the reference signature (:236-248) and return convention
+(:378-383); the loop-invariant conditioning branch (:297-319) is cached per (cond image, flow) pair and
+evaluated for one CFG half (both halves are identical, pipeline.py:393-397)."""
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from mofa_video_b200.models._base import EngineModel
+
+
+@dataclass
+class FlowControlNetOutput:
+    down_block_res_samples: Tuple[torch.Tensor] = None
+    mid_block_res_sample: torch.Tensor = None
+    controlnet_flow: torch.Tensor = None
+    cmp_output: Optional[torch.Tensor] = None
+
+
+class FlowControlNet(EngineModel):
+    kind = "adapter"
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._cond_key = None
+
+    def prepare_condition(self, controlnet_cond, controlnet_flow):
+        """controlnet_cond [B, 3, H, W] in [-1, 1], controlnet_flow [B, T-1, 2, H, W] (B = CFG copies)."""
+        key = (controlnet_cond.data_ptr(), controlnet_cond._version, controlnet_flow.data_ptr(),
+               controlnet_flow._version, tuple(controlnet_flow.shape))
+        if key == self._cond_key:
+            return
+        if controlnet_cond.shape[0] > 1 and not torch.equal(controlnet_cond[0], controlnet_cond[-1]):
+            raise ValueError("the engine hoists the conditioning branch assuming identical CFG halves "
+                             "(pipeline.py:393-397); got different condition images per batch item")
+        _, _, H, W = controlnet_cond.shape
+        if H % 64 or W % 64:
+            raise ValueError("height and width must be multiples of 64 (flow pyramid down to 1/64, FCN.py:302-315)")
+        cond = controlnet_cond[:1].to(device=self._device, dtype=torch.float16).contiguous()
+        cl = torch.empty(H * W, 3, dtype=torch.float16, device=self._device)
+        self._ops.nchw_to_nhwc(cond, cl, 1, 3, H * W)
+        flow = controlnet_flow[0].to(device=self._device, dtype=torch.float16).contiguous()
+        self.net.adapter_cond_branch(cl, flow, H, W)
+        self._cond_key = key
+
+    def forward(self, sample, timestep, encoder_hidden_states, added_time_ids, controlnet_cond=None,
+                controlnet_flow=None, image_only_indicator=None, return_dict=True, guess_mode=False,
+                conditioning_scale=1.0, channels_last_output=False):
+        b, t, c, h, w = sample.shape
+        if t != self.config.num_frames:
+            raise ValueError(f"num_frames mismatch: sample has {t}, model packed for {self.config.num_frames}")
+        self._prepare(encoder_hidden_states, added_time_ids)
+        self.prepare_condition(controlnet_cond, controlnet_flow)
+        x = self._to_cl(sample)
+        res, mid = self.net.adapter_forward(x, self._t_value(timestep), h, w, conditioning_scale)
+        if channels_last_output:
+            for r in res + [mid]:
+                r._mofa_channels_last = True
+            down, midr = res, mid
+        else:
+            sizes = []
+            hh, ww = h, w
+            nlev = len(self.config.block_out_channels)
+            lpb = self.config.layers_per_block
+            sizes.append((hh, ww))
+            for i in range(nlev):
+                sizes += [(hh, ww)] * (lpb if isinstance(lpb, int) else lpb[i])
+                if i != nlev - 1:
+                    hh, ww = (hh - 1) // 2 + 1, (ww - 1) // 2 + 1
+                    sizes.append((hh, ww))
+            down = [self._from_cl(r, b * t, *sizes[k]) for k, r in enumerate(res)]
+            midr = self._from_cl(mid, b * t, hh, ww)
+        if not return_dict:
+            return (down, midr, controlnet_flow, None)
+        return FlowControlNetOutput(down_block_res_samples=down, mid_block_res_sample=midr,
+                                    controlnet_flow=controlnet_flow, cmp_output=None)
+
+    __call__ = forward

@@ -1,0 +1,335 @@
+"""FlowControlNetPipeline with the reference's entry point
+(/root/reference/MOFA-Video-Traj/pipeline/pipeline.py:87-527), driving the sm_100a engine.
+
+Same constructor kwargs (:90-108), same __call__ signature and defaults (:283-311), same output object
+(:72-84), same errors (check_inputs :222-234, add-time-id check :34-40).  What changes is the execution:
+the 25-step loop (:447-511) keeps the latents, the model input and every activation on the device in
+channels-last fp16, runs adapter + UNet through the C-ABI kernels, and replaces the Python-side
+torch.cat / scale_model_input / CFG / scheduler.step (:449-454, 495-500) by one fused kernel per step.
+Quirks kept on purpose: Q3 un-normalised CLIP input, Q4 hard-coded added_time_ids,
+Q5 CFG is mandatory, Q6 per-frame guidance, Q7 RNG placement, Q8 VAE chunking, Q16, Q21, Q22.
+"""
+import json
+import os
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Union
+
+import numpy as np
+import PIL.Image
+import torch
+import torch.nn.functional as F
+
+from mofa_video_b200 import lib as _lib
+
+
+@dataclass
+class FlowControlNetPipelineOutput:
+    frames: Union[List[PIL.Image.Image], np.ndarray, torch.Tensor] = None
+    controlnet_flow: Union[List[PIL.Image.Image], np.ndarray, torch.Tensor] = None
+
+
+def _get_add_time_ids(noise_aug_strength, dtype, batch_size, fps=4, motion_bucket_id=128, unet=None):
+    """pipeline.py:24-46."""
+    add_time_ids = [fps, motion_bucket_id, noise_aug_strength]
+    passed = unet.config.addition_time_embed_dim * len(add_time_ids)
+    expected = unet.add_embedding.linear_1.in_features
+    if expected != passed:
+        raise ValueError(
+            f"Model expects an added time embedding vector of length {expected}, but a vector of {passed} was "
+            "created. The model has an incorrect config. Please check `unet.config.time_embedding_type` and "
+            "`text_encoder_2.config.projection_dim`.")
+    return torch.tensor([add_time_ids], dtype=dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# image pre/post-processing (diffusers VaeImageProcessor behaviour used by the reference, Q21)
+# ------------------------------------------------------------------------------------------------
+def _to_unit_tensor(image, height=None, width=None):
+    """PIL / ndarray / tensor -> float32 [N, 3, H, W] in [0, 1] (PIL is resized like VaeImageProcessor)."""
+    if isinstance(image, PIL.Image.Image):
+        image = [image]
+    if isinstance(image, (list, tuple)) and isinstance(image[0], PIL.Image.Image):
+        arrs = []
+        for im in image:
+            if height is not None and im.size != (width, height):
+                im = im.resize((width, height), resample=PIL.Image.LANCZOS)
+            arrs.append(np.asarray(im.convert("RGB"), dtype=np.float32) / 255.0)
+        return torch.from_numpy(np.stack(arrs, 0)).permute(0, 3, 1, 2).contiguous()
+    if isinstance(image, np.ndarray):
+        a = image.astype(np.float32) / (255.0 if image.dtype == np.uint8 else 1.0)
+        if a.ndim == 3:
+            a = a[None]
+        return torch.from_numpy(a).permute(0, 3, 1, 2).contiguous()
+    if isinstance(image, torch.Tensor):
+        t = image.float()
+        return t[None] if t.ndim == 3 else t
+    raise ValueError(f"unsupported image type {type(image)}")
+
+
+def _gauss_kernel(size, sigma):
+    x = torch.arange(size, dtype=torch.float32) - size // 2
+    if size % 2 == 0:
+        x = x + 0.5
+    k = torch.exp(-x.pow(2) / (2 * sigma * sigma))
+    return k / k.sum()
+
+
+def _resize_with_antialiasing(img, size):
+    """Gaussian pre-blur (sigma = (factor-1)/2, two-sigma odd kernel, reflect padding) then bicubic with
+    align_corners=True -- the CLIP-side resize of pipeline.py:532-562."""
+    if img.ndim == 3:
+        img = img[None]
+    h, w = img.shape[-2:]
+    sig = (max((h / size[0] - 1.0) / 2.0, 0.001), max((w / size[1] - 1.0) / 2.0, 0.001))
+    ks = [int(max(4.0 * s, 3)) for s in sig]
+    ks = [k + 1 if k % 2 == 0 else k for k in ks]
+    c = img.shape[1]
+    kx = _gauss_kernel(ks[1], sig[1]).to(img).view(1, 1, 1, -1).expand(c, 1, 1, -1)
+    ky = _gauss_kernel(ks[0], sig[0]).to(img).view(1, 1, -1, 1).expand(c, 1, -1, 1)
+    px, py = (ks[1] - 1) // 2, (ks[0] - 1) // 2
+    out = F.conv2d(F.pad(img, (px, ks[1] - 1 - px, 0, 0), mode="reflect"), kx, groups=c)
+    out = F.conv2d(F.pad(out, (0, 0, py, ks[0] - 1 - py), mode="reflect"), ky, groups=c)
+    return F.interpolate(out, size=size, mode="bicubic", align_corners=True)
+
+
+class FlowControlNetPipeline:
+    model_cpu_offload_seq = "image_encoder->unet->vae"
+    _callback_tensor_inputs = ["latents"]
+
+    def __init__(self, vae, image_encoder, unet, controlnet, scheduler, feature_extractor=None):
+        self.vae, self.image_encoder, self.unet, self.controlnet = vae, image_encoder, unet, controlnet
+        self.scheduler, self.feature_extractor = scheduler, feature_extractor
+        self.vae_scale_factor = 2 ** (len(self.vae.config.block_out_channels) - 1)
+        self._device = torch.device("cuda")
+        self.timings = {}
+        _lib.load()  # no fallback: fail here if the CUDA library is missing
+
+    @classmethod
+    def from_pretrained(cls, path, unet=None, controlnet=None, image_encoder=None, vae=None, scheduler=None,
+                        feature_extractor=None, torch_dtype=None, **_ignored):
+        """T/run_gradio.py:147-154: the four models are passed in; the scheduler comes from the SVD folder."""
+        if scheduler is None:
+            from mofa_video_b200.utils.scheduling_euler_discrete_karras_fix import EulerDiscreteScheduler
+            fn = os.path.join(path, "scheduler", "scheduler_config.json")
+            if os.path.exists(fn):
+                with open(fn) as f:
+                    scheduler = EulerDiscreteScheduler.from_config(
+                        {k: v for k, v in json.load(f).items() if not k.startswith("_")})
+            else:
+                scheduler = EulerDiscreteScheduler()
+        if None in (unet, controlnet, image_encoder, vae):
+            raise ValueError("pass unet=, controlnet=, image_encoder= and vae= (as T/run_gradio.py:147-154 does)")
+        return cls(vae=vae, image_encoder=image_encoder, unet=unet, controlnet=controlnet, scheduler=scheduler,
+                   feature_extractor=feature_extractor)
+
+    def to(self, device=None, *a, **k):
+        if device is not None:
+            self._device = torch.device(device)
+        return self
+
+    @property
+    def guidance_scale(self):
+        return self._guidance_scale
+
+    @property
+    def num_timesteps(self):
+        return self._num_timesteps
+
+    def maybe_free_model_hooks(self):
+        pass
+
+    # ------------------------------------------------------------------ pieces of __call__
+    def check_inputs(self, image, height, width):
+        if not isinstance(image, (torch.Tensor, PIL.Image.Image, list)):
+            raise ValueError("`image` has to be of type `torch.FloatTensor` or `PIL.Image.Image` or "
+                             f"`List[PIL.Image.Image]` but is {type(image)}")
+        if height % 8 != 0 or width % 8 != 0:
+            raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+
+    def _encode_image(self, image, device, num_videos_per_prompt, do_classifier_free_guidance):
+        """pipeline.py:114-141 (Q3: [0,1] image, antialiased bicubic to 224, no CLIP mean/std)."""
+        dtype = next(self.image_encoder.parameters()).dtype
+        img = _to_unit_tensor(image)
+        img = _resize_with_antialiasing(img, (224, 224)).to(device=device, dtype=dtype)
+        emb = self.image_encoder(img).image_embeds.unsqueeze(1)
+        emb = emb.repeat(1, num_videos_per_prompt, 1)
+        if do_classifier_free_guidance:
+            emb = torch.cat([torch.zeros_like(emb), emb])
+        return emb
+
+    def _encode_vae_image(self, image, device, num_videos_per_prompt, do_classifier_free_guidance):
+        """pipeline.py:143-164: .mode() of the posterior, NOT multiplied by scaling_factor (Q8)."""
+        lat = self.vae.encode(image.to(device=device)).latent_dist.mode()
+        if do_classifier_free_guidance:
+            lat = torch.cat([torch.zeros_like(lat), lat])
+        return lat.repeat(num_videos_per_prompt, 1, 1, 1)
+
+    def prepare_latents(self, batch_size, num_frames, num_channels_latents, height, width, dtype, device, generator,
+                        latents=None):
+        shape = (batch_size, num_frames, num_channels_latents // 2, height // self.vae_scale_factor,
+                 width // self.vae_scale_factor)
+        if isinstance(generator, list) and len(generator) != batch_size:
+            raise ValueError(f"You have passed a list of generators of length {len(generator)}, but requested an "
+                             f"effective batch size of {batch_size}.")
+        if latents is None:
+            gdev = generator.device if isinstance(generator, torch.Generator) else device
+            latents = torch.randn(shape, generator=generator if isinstance(generator, torch.Generator) else None,
+                                  device=gdev, dtype=dtype).to(device)
+        else:
+            latents = latents.to(device)
+        return latents * self.scheduler.init_noise_sigma
+
+    def decode_latents(self, latents, num_frames, decode_chunk_size=14):
+        """pipeline.py:194-220 (Q8: chunks see zero temporal padding at their borders)."""
+        latents = latents.flatten(0, 1)
+        latents = 1 / self.vae.config.scaling_factor * latents
+        frames = []
+        for i in range(0, latents.shape[0], decode_chunk_size):
+            chunk = latents[i:i + decode_chunk_size]
+            frames.append(self.vae.decode(chunk, num_frames=chunk.shape[0]).sample)
+        frames = torch.cat(frames, dim=0)
+        frames = frames.reshape(-1, num_frames, *frames.shape[1:]).permute(0, 2, 1, 3, 4)
+        return frames.float()
+
+    @staticmethod
+    def _postprocess(frames, output_type):
+        """tensor2vid + VaeImageProcessor.postprocess (pipeline.py:57-69, Q21). frames [B, C, T, H, W]."""
+        outs = []
+        for b in range(frames.shape[0]):
+            vid = (frames[b].permute(1, 0, 2, 3) / 2 + 0.5).clamp(0, 1)  # [T, C, H, W]
+            if output_type == "pt":
+                outs.append(vid)
+                continue
+            if output_type == "np":
+                outs.append(vid.permute(0, 2, 3, 1).cpu().float().numpy())
+                continue
+            u8 = (vid * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous().cpu().numpy()
+            if output_type == "uint8":
+                outs.append(u8)
+            elif output_type == "pil":
+                outs.append([PIL.Image.fromarray(f) for f in u8])
+            else:
+                raise ValueError(f"unknown output_type {output_type}")
+        return outs
+
+    # ------------------------------------------------------------------ the call
+    @torch.no_grad()
+    def __call__(self, image, controlnet_condition=None, controlnet_flow=None, height: int = 576, width: int = 1024,
+                 num_frames: Optional[int] = None, num_inference_steps: int = 25, min_guidance_scale: float = 1.0,
+                 max_guidance_scale: float = 3.0, fps: int = 7, motion_bucket_id: int = 127,
+                 noise_aug_strength: float = 0.02, decode_chunk_size: Optional[int] = None,
+                 num_videos_per_prompt: Optional[int] = 1, generator=None, latents: Optional[torch.Tensor] = None,
+                 output_type: Optional[str] = "pil",
+                 callback_on_step_end: Optional[Callable[[int, int, Dict], None]] = None,
+                 callback_on_step_end_tensor_inputs: List[str] = ["latents"], return_dict: bool = True,
+                 controlnet_cond_scale=1.0, batch_size=1):
+        ops = _lib
+        height = height or self.unet.config.sample_size * self.vae_scale_factor
+        width = width or self.unet.config.sample_size * self.vae_scale_factor
+        num_frames = num_frames if num_frames is not None else self.unet.config.num_frames
+        decode_chunk_size = decode_chunk_size if decode_chunk_size is not None else num_frames
+        self.check_inputs(image, height, width)
+        if batch_size != 1 or num_videos_per_prompt != 1:
+            raise NotImplementedError("one clip per call (the reference's batch>1 path is unusable with one image, "
+                                      "pipeline.py:378-388,454); shard clips across processes/GPUs instead")
+        device = self._device
+        do_cfg = max_guidance_scale > 1.0
+        if not do_cfg:
+            raise ValueError("max_guidance_scale must be > 1: without CFG the reference substitutes the latents for "
+                             "the condition image and flow (pipeline.py:393,396), which is not a usable mode")
+        ev = {k: torch.cuda.Event(enable_timing=True) for k in ("t0", "enc", "loop", "dec")}
+        ev["t0"].record()
+
+        # 3. CLIP image embedding
+        image_embeddings = self._encode_image(image, device, num_videos_per_prompt, do_cfg)
+        emb_dtype = image_embeddings.dtype
+        fps = fps - 1
+
+        # 4. VAE-encode the (noise-augmented) conditioning frame; CPU RNG like the reference (Q7)
+        img = _to_unit_tensor(image, height, width) * 2.0 - 1.0
+        gen_cpu = generator if isinstance(generator, torch.Generator) and generator.device.type == "cpu" else None
+        noise = torch.randn(img.shape, generator=gen_cpu, dtype=img.dtype)
+        img = img + noise_aug_strength * noise.to(img.device)
+        vae_dtype = self.vae.dtype
+        needs_upcasting = vae_dtype == torch.float16 and self.vae.config.force_upcast
+        if needs_upcasting:
+            self.vae.to(dtype=torch.float32)
+        image_latents = self._encode_vae_image(img.to(self.vae.dtype), device, num_videos_per_prompt, do_cfg)
+        image_latents = image_latents.to(emb_dtype)
+        if needs_upcasting:
+            self.vae.to(dtype=torch.float16)
+
+        # 5. added time ids: computed from the arguments, then overwritten by constants (Q4, pipeline.py:430-440)
+        _get_add_time_ids(noise_aug_strength, emb_dtype, batch_size, fps, motion_bucket_id, unet=self.unet)
+        added_time_ids = torch.cat([_get_add_time_ids(0.02, emb_dtype, batch_size, 6, 128, unet=self.unet)] * 2)
+        added_time_ids = added_time_ids.to(device)
+
+        self.scheduler.set_timesteps(num_inference_steps, device=device)
+        timesteps = self.scheduler.timesteps
+        num_channels_latents = self.unet.config.in_channels
+        latents = self.prepare_latents(batch_size, num_frames, num_channels_latents, height, width, emb_dtype, device,
+                                       generator, latents)
+
+        cond = (_to_unit_tensor(controlnet_condition, height, width) * 2.0 - 1.0)
+        cond = torch.cat([cond] * 2).to(device, latents.dtype)
+        if controlnet_flow is None or controlnet_flow.shape[1] != num_frames - 1:
+            raise ValueError(f"controlnet_flow must be [1, {num_frames - 1}, 2, H, W]")
+        controlnet_flow = torch.cat([controlnet_flow] * 2).to(device, latents.dtype)
+
+        g = torch.linspace(min_guidance_scale, max_guidance_scale, num_frames).unsqueeze(0).to(device, latents.dtype)
+        self._guidance_scale = g[(...,) + (None,) * 3]
+        self._num_timesteps = len(timesteps)
+
+        # ---- engine state for this clip
+        h, w = height // self.vae_scale_factor, width // self.vae_scale_factor
+        hw, T = h * w, num_frames
+        unet_net, ad_net = self.unet.net, self.controlnet.net
+        unet_net.prepare_clip(image_embeddings, added_time_ids)
+        ad_net.prepare_clip(image_embeddings, added_time_ids)
+        self.controlnet.prepare_condition(cond, controlnet_flow)
+        lat_h = latents[0].to(torch.float16).reshape(T, 4, hw).contiguous()
+        img_lat = image_latents.to(torch.float16).reshape(2, 4, hw).contiguous()
+        next_in = torch.empty(2 * T * hw, 8, dtype=torch.float16, device=device)
+        sig = self.scheduler._sigmas_host
+        ts = self.scheduler._timesteps_host
+        self.scheduler._step_index = 0
+        ops.cfg_euler_step(None, lat_h, img_lat, next_in, T, hw, min_guidance_scale, max_guidance_scale, 0.0, sig[0])
+        ev["enc"].record()
+
+        # 8. denoising loop (pipeline.py:447-511)
+        for i in range(len(ts)):
+            res, mid = ad_net.adapter_forward(next_in, ts[i], h, w, controlnet_cond_scale)
+            noise_pred = unet_net.unet_forward(next_in, ts[i], h, w, res, mid)
+            ops.cfg_euler_step(noise_pred, lat_h, img_lat, next_in, T, hw, min_guidance_scale, max_guidance_scale,
+                               sig[i], sig[i + 1])
+            self.scheduler._step_index = i + 1
+            if callback_on_step_end is not None:
+                cur = lat_h.reshape(1, T, 4, h, w)
+                kw = {k: cur for k in callback_on_step_end_tensor_inputs if k == "latents"}
+                outs = callback_on_step_end(self, i, timesteps[i], kw) or {}
+                new = outs.pop("latents", None)
+                if new is not None and new is not cur:
+                    lat_h.copy_(new.reshape(T, 4, hw))
+                    ops.cfg_euler_step(None, lat_h, img_lat, next_in, T, hw, min_guidance_scale,
+                                       max_guidance_scale, 0.0, sig[i + 1])
+        latents = lat_h.reshape(1, T, 4, h, w)
+        ev["loop"].record()
+
+        if output_type != "latent":
+            frames = self.decode_latents(latents.to(self.vae.dtype), num_frames, decode_chunk_size)
+            frames = self._postprocess(frames, output_type)
+        else:
+            frames = latents
+        ev["dec"].record()
+        self._events = ev
+        controlnet_flow_out = controlnet_flow
+        if not return_dict:
+            return frames, controlnet_flow_out
+        return FlowControlNetPipelineOutput(frames=frames, controlnet_flow=controlnet_flow_out)
+
+    def last_timings_ms(self):
+        """Device times of the last call (after a synchronize): encode (CLIP+VAE enc+cond branch), loop, decode."""
+        e = self._events
+        torch.cuda.synchronize()
+        return {"encode_ms": e["t0"].elapsed_time(e["enc"]), "loop_ms": e["enc"].elapsed_time(e["loop"]),
+                "decode_ms": e["loop"].elapsed_time(e["dec"])}

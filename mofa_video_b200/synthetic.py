@@ -1,0 +1,193 @@
+"""Random-init weights in the reference's state-dict layout, for benchmarks and smoke
+tests: there are no checkpoints and no network here.  This enumerates every parameter name/shape of the SVD
+UNet and the trajectory MOFA-Adapter; `tests/test_synthetic.py` checks the enumeration against the oracle
+modules' own state_dict() key/shape sets (and thereby against the published 1,524,623,082 UNet parameters).
+
+Init (seeded): N(0, 1/fan_in) weights, zero biases, unit norms, mix_factor 0.5,
+out-projections x0.1, zero-convs N(0, 0.02^2) so the adapter contributes.
+"""
+import math
+
+import torch
+
+SVD_XT_CONFIG = dict(
+    sample_size=96, in_channels=8, out_channels=4,
+    down_block_types=("CrossAttnDownBlockSpatioTemporal", "CrossAttnDownBlockSpatioTemporal",
+                      "CrossAttnDownBlockSpatioTemporal", "DownBlockSpatioTemporal"),
+    up_block_types=("UpBlockSpatioTemporal", "CrossAttnUpBlockSpatioTemporal", "CrossAttnUpBlockSpatioTemporal",
+                    "CrossAttnUpBlockSpatioTemporal"),
+    block_out_channels=(320, 640, 1280, 1280), addition_time_embed_dim=256,
+    projection_class_embeddings_input_dim=768, layers_per_block=2, cross_attention_dim=1024,
+    transformer_layers_per_block=1, num_attention_heads=(5, 10, 20, 20), num_frames=25,
+    conditioning_channels=3, conditioning_embedding_out_channels=(16, 32, 96, 256),
+)
+
+
+class _Gen:
+    def __init__(self, seed, dtype):
+        self.g = torch.Generator().manual_seed(seed)
+        self.sd = {}
+        self.dtype = dtype
+
+    def w(self, name, shape, fan_in=None, gain=1.0, std=None):
+        if std is None:
+            fan_in = fan_in if fan_in is not None else int(torch.tensor(shape[1:]).prod())
+            std = gain / math.sqrt(fan_in)
+        self.sd[name] = (torch.randn(shape, generator=self.g) * std).to(self.dtype)
+
+    def const(self, name, shape, v):
+        self.sd[name] = torch.full(shape, v).to(self.dtype)
+
+    def conv(self, name, cout, cin, k=3, gain=1.0, std=None):
+        self.w(name + ".weight", (cout, cin, k, k), gain=gain, std=std)
+        if std is None:
+            self.const(name + ".bias", (cout,), 0.0)
+        else:
+            self.w(name + ".bias", (cout,), std=std)
+
+    def tconv(self, name, cout, cin, gain=1.0):
+        self.w(name + ".weight", (cout, cin, 3, 1, 1), gain=gain)
+        self.const(name + ".bias", (cout,), 0.0)
+
+    def lin(self, name, cout, cin, bias=True, gain=1.0):
+        self.w(name + ".weight", (cout, cin), gain=gain)
+        if bias:
+            self.const(name + ".bias", (cout,), 0.0)
+
+    def norm(self, name, c):
+        self.const(name + ".weight", (c,), 1.0)
+        self.const(name + ".bias", (c,), 0.0)
+
+    # composite blocks --------------------------------------------------------------------------
+    def resblock(self, pre, cin, cout, temb):
+        sp, tp = pre + ".spatial_res_block", pre + ".temporal_res_block"
+        self.norm(sp + ".norm1", cin)
+        self.conv(sp + ".conv1", cout, cin)
+        self.lin(sp + ".time_emb_proj", cout, temb)
+        self.norm(sp + ".norm2", cout)
+        self.conv(sp + ".conv2", cout, cout, gain=0.1)
+        if cin != cout:
+            self.conv(sp + ".conv_shortcut", cout, cin, k=1)
+        self.norm(tp + ".norm1", cout)
+        self.tconv(tp + ".conv1", cout, cout)
+        self.lin(tp + ".time_emb_proj", cout, temb)
+        self.norm(tp + ".norm2", cout)
+        self.tconv(tp + ".conv2", cout, cout, gain=0.1)
+        self.const(pre + ".time_mixer.mix_factor", (1,), 0.5)
+
+    def attn(self, pre, dim, kv_dim):
+        self.lin(pre + ".to_q", dim, dim, bias=False)
+        self.lin(pre + ".to_k", dim, kv_dim, bias=False)
+        self.lin(pre + ".to_v", dim, kv_dim, bias=False)
+        self.lin(pre + ".to_out.0", dim, dim, gain=0.1)
+
+    def ff(self, pre, dim):
+        self.lin(pre + ".net.0.proj", 8 * dim, dim)
+        self.lin(pre + ".net.2", dim, 4 * dim, gain=0.1)
+
+    def transformer(self, pre, C, ctx):
+        self.norm(pre + ".norm", C)
+        self.lin(pre + ".proj_in", C, C)
+        sb, tb = pre + ".transformer_blocks.0", pre + ".temporal_transformer_blocks.0"
+        self.norm(sb + ".norm1", C)
+        self.attn(sb + ".attn1", C, C)
+        self.norm(sb + ".norm2", C)
+        self.attn(sb + ".attn2", C, ctx)
+        self.norm(sb + ".norm3", C)
+        self.ff(sb + ".ff", C)
+        self.norm(tb + ".norm_in", C)
+        self.ff(tb + ".ff_in", C)
+        self.norm(tb + ".norm1", C)
+        self.attn(tb + ".attn1", C, C)
+        self.norm(tb + ".norm2", C)
+        self.attn(tb + ".attn2", C, ctx)
+        self.norm(tb + ".norm3", C)
+        self.ff(tb + ".ff", C)
+        self.lin(pre + ".time_pos_embed.linear_1", 4 * C, C)
+        self.lin(pre + ".time_pos_embed.linear_2", C, 4 * C)
+        self.const(pre + ".time_mixer.mix_factor", (1,), 0.5)
+        self.lin(pre + ".proj_out", C, C, gain=0.1)
+
+
+def _tup(v, n):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v,) * n
+
+
+def _trunk(g, cfg):
+    boc = tuple(cfg["block_out_channels"])
+    n = len(boc)
+    lpb, ctx = _tup(cfg["layers_per_block"], n), _tup(cfg["cross_attention_dim"], n)
+    temb = boc[0] * 4
+    g.conv("conv_in", boc[0], cfg["in_channels"])
+    g.lin("time_embedding.linear_1", temb, boc[0])
+    g.lin("time_embedding.linear_2", temb, temb)
+    g.lin("add_embedding.linear_1", temb, cfg["projection_class_embeddings_input_dim"])
+    g.lin("add_embedding.linear_2", temb, temb)
+    out = boc[0]
+    for i, t in enumerate(cfg["down_block_types"]):
+        cin, out = out, boc[i]
+        for j in range(lpb[i]):
+            g.resblock(f"down_blocks.{i}.resnets.{j}", cin if j == 0 else out, out, temb)
+            if "CrossAttn" in t:
+                g.transformer(f"down_blocks.{i}.attentions.{j}", out, ctx[i])
+        if i != n - 1:
+            g.conv(f"down_blocks.{i}.downsamplers.0.conv", out, out)
+    C = boc[-1]
+    g.resblock("mid_block.resnets.0", C, C, temb)
+    g.transformer("mid_block.attentions.0", C, ctx[-1])
+    g.resblock("mid_block.resnets.1", C, C, temb)
+    return boc, n, lpb, ctx, temb
+
+
+def unet_state_dict(config=None, seed=0, dtype=torch.float16):
+    cfg = dict(SVD_XT_CONFIG)
+    cfg.update(config or {})
+    g = _Gen(seed, dtype)
+    boc, n, lpb, ctx, temb = _trunk(g, cfg)
+    rboc, rlpb, rctx = list(reversed(boc)), list(reversed(lpb)), list(reversed(ctx))
+    out = rboc[0]
+    for i, t in enumerate(cfg["up_block_types"]):
+        prev, out = out, rboc[i]
+        cin = rboc[min(i + 1, n - 1)]
+        nl = rlpb[i] + 1
+        for j in range(nl):
+            skip = cin if j == nl - 1 else out
+            rin = prev if j == 0 else out
+            g.resblock(f"up_blocks.{i}.resnets.{j}", rin + skip, out, temb)
+            if "CrossAttn" in t:
+                g.transformer(f"up_blocks.{i}.attentions.{j}", out, rctx[i])
+        if i != n - 1:
+            g.conv(f"up_blocks.{i}.upsamplers.0.conv", out, out)
+    g.norm("conv_norm_out", boc[0])
+    g.conv("conv_out", cfg["out_channels"], boc[0])
+    return cfg, g.sd
+
+
+def adapter_state_dict(config=None, seed=1, dtype=torch.float16, zero_std=0.02):
+    cfg = dict(SVD_XT_CONFIG)
+    cfg.update(config or {})
+    g = _Gen(seed, dtype)
+    boc, n, lpb, ctx, temb = _trunk(g, cfg)
+    k = 0
+    g.conv(f"controlnet_down_blocks.{k}", boc[0], boc[0], k=1, std=zero_std)
+    for i in range(n):
+        for _ in range(lpb[i]):
+            k += 1
+            g.conv(f"controlnet_down_blocks.{k}", boc[i], boc[i], k=1, std=zero_std)
+        if i != n - 1:
+            k += 1
+            g.conv(f"controlnet_down_blocks.{k}", boc[i], boc[i], k=1, std=zero_std)
+    g.conv("controlnet_mid_block", boc[-1], boc[-1], k=1, std=zero_std)
+    ce = "controlnet_cond_embedding"
+    ceo = tuple(cfg["conditioning_embedding_out_channels"])
+    g.conv(ce + ".conv_in", ceo[0], cfg["conditioning_channels"])
+    for b in range(len(ceo) - 1):
+        g.conv(f"{ce}.blocks.{2 * b}", ceo[b], ceo[b])
+        g.conv(f"{ce}.blocks.{2 * b + 1}", ceo[b + 1], ceo[b])
+    g.conv(ce + ".conv_out", boc[0], ceo[-1], std=zero_std)
+    cin = boc[0]
+    for b in range(3):
+        g.conv(f"flow_encoder.encoders.{b}.conv_in", boc[b], cin)
+        g.conv(f"flow_encoder.zeroconvs.{b}", boc[b], boc[b], k=1, std=zero_std)
+        cin = boc[b]
+    return cfg, g.sd

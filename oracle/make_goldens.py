@@ -1,0 +1,178 @@
+"""ORACLE tooling: generate tests/golden/*.pt by EXECUTING THE REFERENCE'S OWN CODE from /root/reference.
+
+Runs only in the builder container (the GPU box has no /root/reference); the produced fixtures are committed.
+The reference modules import diffusers 0.24 / cupy, which are absent, so minimal import stubs are installed
+for the *base classes and helpers only* (ConfigMixin, register_to_config, SchedulerMixin, BaseOutput,
+randn_tensor, logging, ModelMixin ...).  The arithmetic executed is the reference's:
+  * utils/scheduling_euler_discrete_karras_fix.py : EulerDiscreteScheduler (whole class)
+  * models/svdxt_featureflow_forward_controlnet_s2d_fixcmp_norefine.py :
+        FlowControlNetConditioningEmbeddingSVD, FlowControlNetFirstFrameEncoder
+  * models/cmp/models/modules/* + backbone/resnet.py + utils/visualize_utils.py (CMP forward, see make_cmp)
+
+    python -m oracle.make_goldens
+"""
+import functools
+import inspect
+import os
+import sys
+import types
+from collections import OrderedDict
+
+import torch
+
+REF = "/root/reference/MOFA-Video-Traj"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _mod(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def install_stubs():
+    class ConfigMixin:
+        # diffusers' ConfigMixin.__getattr__ falls back to the registered config (the reference's scheduler
+        # reads self.use_karras_sigmas before assigning it, SCHED.py:225 vs :246)
+        def __getattr__(self, name):
+            cfg = self.__dict__.get("config")
+            if cfg is not None and name in cfg.__dict__:
+                return cfg.__dict__[name]
+            raise AttributeError(name)
+
+    def register_to_config(init):
+        @functools.wraps(init)
+        def wrapper(self, *args, **kwargs):
+            sig = inspect.signature(init)
+            bound = sig.bind(self, *args, **kwargs)
+            bound.apply_defaults()
+            cfg = {k: v for k, v in bound.arguments.items() if k != "self"}
+            self.config = types.SimpleNamespace(**cfg)
+            self.config.__dict__["get"] = cfg.get
+            init(self, *args, **kwargs)
+        return wrapper
+
+    class BaseOutput(OrderedDict):
+        def __post_init__(self):
+            pass
+
+    class _Logger:
+        def warning(self, *a, **k):
+            pass
+
+        info = debug = warning
+
+    logging = types.SimpleNamespace(get_logger=lambda name=None: _Logger())
+
+    def randn_tensor(shape, generator=None, device=None, dtype=None, layout=None):
+        return torch.randn(shape, generator=generator, device=device, dtype=dtype)
+
+    class SchedulerMixin:
+        pass
+
+    class _Dummy(torch.nn.Module):
+        def __init__(self, *a, **k):
+            super().__init__()
+
+    _mod("diffusers")
+    _mod("diffusers.configuration_utils", ConfigMixin=ConfigMixin, register_to_config=register_to_config)
+    _mod("diffusers.utils", BaseOutput=BaseOutput, logging=logging)
+    _mod("diffusers.utils.torch_utils", randn_tensor=randn_tensor)
+    _mod("diffusers.schedulers")
+    _mod("diffusers.schedulers.scheduling_utils", KarrasDiffusionSchedulers=[], SchedulerMixin=SchedulerMixin)
+    _mod("diffusers.loaders", FromOriginalControlnetMixin=type("FromOriginalControlnetMixin", (), {}))
+    names = ["ADDED_KV_ATTENTION_PROCESSORS", "CROSS_ATTENTION_PROCESSORS", "AttentionProcessor",
+             "AttnAddedKVProcessor", "AttnProcessor"]
+    _mod("diffusers.models", UNetSpatioTemporalConditionModel=_Dummy)
+    _mod("diffusers.models.attention_processor", **{n: _Dummy for n in names})
+    _mod("diffusers.models.embeddings", TextImageProjection=_Dummy, TextImageTimeEmbedding=_Dummy,
+         TextTimeEmbedding=_Dummy, TimestepEmbedding=_Dummy, Timesteps=_Dummy)
+    _mod("diffusers.models.modeling_utils", ModelMixin=torch.nn.Module)
+    _mod("diffusers.models.unet_3d_blocks", get_down_block=None, get_up_block=None,
+         UNetMidBlockSpatioTemporal=_Dummy)
+    # cupy-backed kernel module: not executable here
+    _mod("cupy")
+
+
+def load_reference_scheduler():
+    install_stubs()
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_sched", os.path.join(REF, "utils",
+                                                                              "scheduling_euler_discrete_karras_fix.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def make_scheduler():
+    m = load_reference_scheduler()
+    from oracle.scheduler import SVD_XT_SCHEDULER_CONFIG
+    s = m.EulerDiscreteScheduler(**SVD_XT_SCHEDULER_CONFIG)
+    g = {"init_noise_sigma_initial": float(s.init_noise_sigma)}
+    for n in (25, 2):
+        s.set_timesteps(n)
+        g[f"sigmas_{n}"] = s.sigmas.clone()
+        g[f"timesteps_{n}"] = s.timesteps.clone()
+        g[f"init_noise_sigma_{n}"] = float(s.init_noise_sigma)
+    s.set_timesteps(25)
+    gen = torch.Generator().manual_seed(123)
+    x = torch.randn(1, 3, 4, 6, 5, generator=gen) * float(s.init_noise_sigma)
+    g["x0"] = x.clone()
+    g["model_out"], g["scaled"], g["traj"] = [], [], []
+    for t in s.timesteps:
+        mo = torch.randn(1, 3, 4, 6, 5, generator=gen)
+        g["model_out"].append(mo)
+        g["scaled"].append(s.scale_model_input(x, t).clone())
+        x = s.step(mo, t, x).prev_sample
+        g["traj"].append(x.clone())
+    torch.save(g, os.path.join(OUT, "scheduler_svdxt.pt"))
+    print("scheduler golden written;", "sigma[0..2] =", g["sigmas_25"][:3].tolist())
+
+
+def make_adapter_encoders():
+    install_stubs()
+    sys.path.insert(0, REF)
+    # neighbours of FCN.py that cannot be imported here (diffusers blocks / cupy): give it what it names
+    import torch.nn as nn
+
+    def zero_module(module):  # same contract as controlnet_sdv.py:779-782
+        for p in module.parameters():
+            nn.init.zeros_(p)
+        return module
+
+    _mod("models.controlnet_sdv", ControlNetSDVModel=torch.nn.Module, zero_module=zero_module)
+    _mod("models.softsplat", softsplat=None)
+    _mod("models.cmp")
+    _mod("models.cmp.models")
+    _mod("models.cmp.utils")
+    _mod("torchvision")
+    _mod("torchvision.transforms")
+    import importlib.util
+    fn = os.path.join(REF, "models", "svdxt_featureflow_forward_controlnet_s2d_fixcmp_norefine.py")
+    spec = importlib.util.spec_from_file_location("ref_fcn", fn)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    torch.manual_seed(0)
+    ce = m.FlowControlNetConditioningEmbeddingSVD(conditioning_embedding_channels=32)   # small: keeps the fixture < 1 MB
+    fe = m.FlowControlNetFirstFrameEncoder(c_in=32, channels=[32, 64, 128])
+    gen = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for mod in (ce, fe):  # un-zero the zero-convs so the fixture exercises them
+            for p in mod.parameters():
+                if p.abs().max() == 0:
+                    p.copy_(torch.randn(p.shape, generator=gen) * 0.02)
+        cond_in = torch.randn(1, 3, 64, 64, generator=gen)
+        cond_out = ce(cond_in)
+        flow_out = fe(cond_out)
+    g = {"cond_embedding_sd": ce.state_dict(), "flow_encoder_sd": fe.state_dict(), "cond_in": cond_in,
+         "cond_out": cond_out, "flow_out": flow_out}
+    torch.save(g, os.path.join(OUT, "adapter_encoders.pt"))
+    print("adapter encoder golden written:", [tuple(t.shape) for t in flow_out])
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    make_scheduler()
+    if "--all" in sys.argv:
+        make_adapter_encoders()

@@ -20,14 +20,15 @@ def pick_bn(n, geglu=False):
     return real.pick_bn(n, geglu)
 
 
-def _epilogue(acc, *, N, bn, act, bias, rowbias, rows_per_group, res1, res2, alpha, beta1, beta2):
+def _epilogue(acc, *, N, bn, act, bias, rowbias, rows_per_group, rowbias_mod, res1, res2, alpha, beta1, beta2):
     """acc: fp32 [rows, N] pre-bias accumulator."""
     rows = acc.shape[0]
     v = acc
     if bias is not None:
         v = v + bias.float()[None, :]
     if rowbias is not None:
-        grp = torch.arange(rows, device=acc.device) // rows_per_group
+        ar = torch.arange(rows, device=acc.device)
+        grp = ar % rowbias_mod if rowbias_mod > 0 else ar // rows_per_group
         v = v + rowbias.float()[grp]
     if act == ACT_SILU:
         v = F.silu(v)
@@ -44,8 +45,8 @@ def _epilogue(acc, *, N, bn, act, bias, rowbias, rows_per_group, res1, res2, alp
 
 
 def gemm(mode, a, w, out, *, N, bn=None, act=ACT_NONE, a2=None, M=0, K=0, K1=0, lda=0, lda2=0, n_img=0, H=0, W=0,
-         C=0, B=0, T=0, HW=0, ldc=None, bias=None, rowbias=None, rows_per_group=1, res1=None, res2=None, alpha=1.0,
-         beta1=1.0, beta2=1.0, max_ctas=0):
+         C=0, B=0, T=0, HW=0, ldc=None, bias=None, rowbias=None, rows_per_group=1, rowbias_mod=0, res1=None, res2=None,
+         alpha=1.0, beta1=1.0, beta2=1.0, max_ctas=0):
     if bn is None:
         bn = pick_bn(N, act == ACT_GEGLU)
     wf = w.float()
@@ -63,8 +64,8 @@ def gemm(mode, a, w, out, *, N, bn=None, act=ACT_NONE, a2=None, M=0, K=0, K1=0, 
         xp = F.pad(x, (0, 0, 0, 0, 1, 1))
         cols = torch.cat([xp[:, 0:T], xp[:, 1:T + 1], xp[:, 2:T + 2]], dim=-1)  # (kt, c)
         acc = cols.reshape(B * T * HW, 3 * C) @ wf.t()
-    res = _epilogue(acc, N=N, bn=bn, act=act, bias=bias, rowbias=rowbias, rows_per_group=rows_per_group, res1=res1,
-                    res2=res2, alpha=alpha, beta1=beta1, beta2=beta2)
+    res = _epilogue(acc, N=N, bn=bn, act=act, bias=bias, rowbias=rowbias, rows_per_group=rows_per_group, rowbias_mod=rowbias_mod,
+                    res1=res1, res2=res2, alpha=alpha, beta1=beta1, beta2=beta2)
     n_out = res.shape[1]
     ld = ldc if ldc is not None else n_out
     out.view(-1, ld)[: res.shape[0], :n_out] = res

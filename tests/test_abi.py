@@ -1,0 +1,51 @@
+"""-m "not gpu": the C-ABI library builds, loads, and exports every symbol include/mofa_b200.h declares."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "mofa_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mofa_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mofa_video_b200 import build, lib
+    path = build.build(force=False)
+    so = ctypes.CDLL(path)
+    declared = _declared()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(so, name), f"{name} declared in mofa_b200.h but not exported"
+    assert sorted(lib.EXPORTS) == declared
+    assert so.mofa_version() >= 100
+
+
+def test_gemm_args_struct_matches_header_field_order():
+    from mofa_video_b200 import lib
+    hdr = open(os.path.join(ROOT, "include", "mofa_b200.h")).read()
+    body = hdr[hdr.index("typedef struct mofa_gemm_args {"):hdr.index("} mofa_gemm_args;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.replace("typedef struct mofa_gemm_args {", "").strip()
+        if not decl:
+            continue
+        parts = decl.replace("*", " ").split(",")
+        first = parts[0].split()
+        if not first:
+            continue
+        names.append(first[-1])
+        names += [p.strip() for p in parts[1:]]
+    assert names == [f[0] for f in lib.GemmArgs._fields_]
+
+
+def test_bad_arguments_are_rejected_without_a_gpu():
+    from mofa_video_b200 import lib
+    so = lib.load()
+    g = lib.GemmArgs()
+    assert so.mofa_gemm(ctypes.byref(g), None) == -1
+    assert b"null" in so.mofa_last_error()

@@ -1,0 +1,135 @@
+"""-m gpu: the engine-backed reference entry points (FlowControlNet.forward, UNet.forward,
+FlowControlNetPipeline.__call__, softsplat) on the B200 against the fp32 CPU oracle.
+
+Tolerances (fp16 storage / fp32 accumulate against an fp32 oracle, random-init weights):
+  single adapter+UNet evaluation : max |err| <= 1e-2 * max |ref|   (measured ~1e-3)
+  3-step pipeline latents        : max |err| <= 2e-2 * max |ref|
+"""
+import pytest
+import torch
+
+from oracle import fixtures
+from oracle import pipeline as opipe
+from oracle import scheduler as osched
+from oracle.softsplat import softsplat as oracle_softsplat
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    return ((a.float().cpu() - b.float().cpu()).abs().max() / (b.abs().max() + 1e-12)).item()
+
+
+def build_pair(cfg, adapter_gain=20.0):
+    from mofa_video_b200.models.svdxt_featureflow_forward_controlnet_s2d_fixcmp_norefine import FlowControlNet
+    from mofa_video_b200.models.unet_spatio_temporal_condition_controlnet import \
+        UNetSpatioTemporalConditionControlNetModel
+    unet, adapter = fixtures.make_models(cfg, seed=0, adapter_gain=adapter_gain)
+    e_unet = UNetSpatioTemporalConditionControlNetModel.from_state_dict(unet.state_dict(), unet.config.__dict__)
+    e_ad = FlowControlNet.from_state_dict(adapter.state_dict(), adapter.config.__dict__)
+    return unet, adapter, e_unet, e_ad
+
+
+def one_step(cfg, H, W, tol):
+    unet, adapter, e_unet, e_ad = build_pair(cfg)
+    inp = fixtures.make_step_inputs(cfg, H, W)
+    t = torch.tensor(1.6377)
+    with torch.no_grad():
+        dres, mid, _, _ = adapter(inp["sample"], t, inp["encoder_hidden_states"], inp["added_time_ids"],
+                                  controlnet_cond=inp["controlnet_cond"], controlnet_flow=inp["controlnet_flow"],
+                                  conditioning_scale=0.8)
+        ref = unet(inp["sample"], t, inp["encoder_hidden_states"], dres, mid, added_time_ids=inp["added_time_ids"])[0]
+    cu = {k: v.cuda() for k, v in inp.items()}
+    down, midr, flow_back, none = e_ad.forward(cu["sample"], 1.6377, cu["encoder_hidden_states"],
+                                               cu["added_time_ids"], controlnet_cond=cu["controlnet_cond"],
+                                               controlnet_flow=cu["controlnet_flow"], conditioning_scale=0.8,
+                                               return_dict=False)
+    assert none is None and flow_back is cu["controlnet_flow"] and len(down) == 12
+    for k, (a, b) in enumerate(zip(down, dres)):
+        assert a.shape == b.shape
+        assert rel_err(a, b) < tol, f"adapter residual {k}: {rel_err(a, b)}"
+    assert rel_err(midr, mid) < tol
+    out = e_unet.forward(cu["sample"], 1.6377, cu["encoder_hidden_states"], down, midr,
+                         added_time_ids=cu["added_time_ids"], return_dict=False)[0]
+    assert out.shape == ref.shape
+    e = rel_err(out, ref)
+    assert e < tol, f"unet output rel err {e}"
+    return e
+
+
+def test_step_tiny_config():
+    one_step(dict(fixtures.TINY_CONFIG), 16, 16, 1e-2)
+
+
+def test_step_tiny_rectangular_more_frames():
+    cfg = dict(fixtures.TINY_CONFIG)
+    cfg["num_frames"] = 5
+    one_step(cfg, 16, 24, 1e-2)
+
+
+def test_step_full_width_channels():
+    """Real SVD-XT channel widths / head counts (320,640,1280,1280; 5,10,20,20) at a small latent."""
+    cfg = dict(num_frames=2)
+    one_step(cfg, 16, 16, 1e-2)
+
+
+def test_softsplat_entry_point():
+    from mofa_video_b200.models.softsplat import softsplat
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 64, 12, 20, generator=g).half().float()
+    fl = (torch.randn(2, 2, 12, 20, generator=g) * 3).half().float()
+    ref = oracle_softsplat(x, fl, None, "avg")
+    out = softsplat(x.cuda(), fl.cuda(), None, "avg")
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    assert rel_err(out, ref) < 2e-3
+    with pytest.raises(AssertionError):
+        softsplat(x.cuda(), fl.cuda(), None, "bogus")
+
+
+class _TinyClip(torch.nn.Module):
+    """Stand-in for CLIPVisionModelWithProjection (a third-party constructor argument of the pipeline)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.proj = torch.nn.Linear(3 * 8 * 8, dim)
+
+    def forward(self, x):
+        from types import SimpleNamespace
+        f = torch.nn.functional.adaptive_avg_pool2d(x, 8).flatten(1)
+        return SimpleNamespace(image_embeds=self.proj(f))
+
+
+def test_pipeline_three_steps_matches_oracle():
+    from mofa_video_b200.models.autoencoder_kl_temporal_decoder import AutoencoderKLTemporalDecoder
+    from mofa_video_b200.pipeline.pipeline import FlowControlNetPipeline
+    from mofa_video_b200.utils.scheduling_euler_discrete_karras_fix import EulerDiscreteScheduler
+    cfg = dict(fixtures.TINY_CONFIG)
+    H, W = 128, 192
+    T = cfg["num_frames"]
+    unet, adapter, e_unet, e_ad = build_pair(cfg)
+    torch.manual_seed(5)
+    vae = AutoencoderKLTemporalDecoder(block_out_channels=(32, 32, 64, 64)).eval()
+    clip = _TinyClip(cfg["cross_attention_dim"]).eval()
+    image = fixtures.make_image(H, W)
+    flow = fixtures.make_flow(T, H, W)
+    lat0 = torch.randn(1, T, 4, H // 8, W // 8, generator=torch.Generator().manual_seed(9))
+    ref = opipe.run_pipeline(vae, clip, unet, adapter, osched.EulerDiscreteScheduler(), image, image, flow,
+                             height=H, width=W, num_inference_steps=3, latents=lat0.clone(),
+                             generator=torch.Generator().manual_seed(11), output_type="latent")
+    pipe = FlowControlNetPipeline(vae=vae.cuda().half(), image_encoder=clip.cuda().half(), unet=e_unet,
+                                  controlnet=e_ad, scheduler=EulerDiscreteScheduler())
+    out = pipe(image, image, flow, height=H, width=W, num_inference_steps=3, latents=lat0.clone().half(),
+               generator=torch.Generator().manual_seed(11), output_type="latent", decode_chunk_size=8)
+    lat = out.frames
+    assert lat.shape == ref.shape
+    assert torch.isfinite(lat).all()
+    e = rel_err(lat, ref)
+    assert e < 2e-2, f"3-step latents rel err {e}"
+    # full call with decode: shapes / dtypes / range of the reference's output contract
+    out = pipe(image, image, flow, height=H, width=W, num_inference_steps=2, latents=lat0.clone().half(),
+               output_type="pil", decode_chunk_size=2)
+    assert len(out.frames) == 1 and len(out.frames[0]) == T and out.frames[0][0].size == (W, H)
+    with pytest.raises(ValueError):
+        pipe(image, image, flow, height=H + 4, width=W)
+    with pytest.raises(ValueError):
+        pipe(image, image, flow, height=H, width=W, max_guidance_scale=1.0)

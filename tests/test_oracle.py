@@ -1,0 +1,104 @@
+"""-m "not gpu": the oracle against (i) fixtures generated from the reference's own code
+(tests/golden/*.pt, made by oracle/make_goldens.py) and (ii) algebraic identities."""
+import os
+
+import pytest
+import torch
+
+from oracle import scheduler as osched
+from oracle.softsplat import softsplat
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _gold(name):
+    fn = os.path.join(GOLD, name)
+    if not os.path.exists(fn):
+        pytest.skip(f"{name} not generated")
+    return torch.load(fn)
+
+
+def test_scheduler_matches_reference_fixture():
+    g = _gold("scheduler_svdxt.pt")
+    s = osched.EulerDiscreteScheduler()
+    assert abs(float(s.init_noise_sigma) - g["init_noise_sigma_initial"]) < 1e-4
+    for n in (25, 2):
+        s.set_timesteps(n)
+        assert torch.allclose(s.sigmas, g[f"sigmas_{n}"], rtol=1e-6, atol=0)
+        assert torch.allclose(s.timesteps, g[f"timesteps_{n}"], rtol=1e-6, atol=0)
+        assert abs(float(s.init_noise_sigma) - g[f"init_noise_sigma_{n}"]) < 1e-3
+    # one full trajectory of scale_model_input + step on seeded tensors
+    s.set_timesteps(25)
+    x = g["x0"].clone()
+    for i, t in enumerate(s.timesteps):
+        xin = s.scale_model_input(x, t)
+        assert torch.allclose(xin, g["scaled"][i], rtol=1e-5, atol=1e-6)
+        x = s.step(g["model_out"][i], t, x)
+        assert torch.allclose(x, g["traj"][i], rtol=1e-5, atol=1e-5)
+
+
+def test_product_scheduler_matches_reference_fixture():
+    from mofa_video_b200.utils.scheduling_euler_discrete_karras_fix import EulerDiscreteScheduler
+    g = _gold("scheduler_svdxt.pt")
+    s = EulerDiscreteScheduler()
+    for n in (25, 2):
+        s.set_timesteps(n)
+        assert torch.allclose(s.sigmas, g[f"sigmas_{n}"], rtol=1e-6, atol=0)
+        assert torch.allclose(s.timesteps, g[f"timesteps_{n}"], rtol=1e-6, atol=0)
+    s.set_timesteps(25)
+    x = g["x0"].clone()
+    for i, t in enumerate(s.timesteps):
+        assert torch.allclose(s.scale_model_input(x, t), g["scaled"][i], rtol=1e-5, atol=1e-6)
+        x = s.step(g["model_out"][i], t, x).prev_sample
+        assert torch.allclose(x, g["traj"][i], rtol=1e-5, atol=1e-5)
+
+
+def test_adapter_encoders_match_reference_fixture():
+    from oracle.models import FlowControlNetConditioningEmbeddingSVD, FlowControlNetFirstFrameEncoder
+    g = _gold("adapter_encoders.pt")
+    ce = FlowControlNetConditioningEmbeddingSVD(32)
+    ce.load_state_dict(g["cond_embedding_sd"])
+    fe = FlowControlNetFirstFrameEncoder(c_in=32, channels=(32, 64, 128))
+    fe.load_state_dict(g["flow_encoder_sd"])
+    with torch.no_grad():
+        c = ce(g["cond_in"])
+        assert torch.allclose(c, g["cond_out"], rtol=1e-5, atol=1e-6)
+        for a, b in zip(fe(g["cond_out"]), g["flow_out"]):
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+
+
+def test_softsplat_identities():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 5, 7, 9, generator=g)
+    zero = torch.zeros(2, 2, 7, 9)
+    assert torch.allclose(softsplat(x, zero, None, "avg"), x / (1 + 1e-7), rtol=1e-6, atol=1e-7)
+    # integer shift by (+2, +1): out[y+1, x+2] = in[y, x]; vacated pixels are empty -> 0
+    fl = torch.zeros(2, 2, 7, 9)
+    fl[:, 0], fl[:, 1] = 2.0, 1.0
+    o = softsplat(x, fl, None, "avg")
+    assert torch.allclose(o[:, :, 1:, 2:], x[:, :, :-1, :-2] / (1 + 1e-7), rtol=1e-6, atol=1e-7)
+    assert o[:, :, 0].abs().max() == 0 and o[:, :, :, :2].abs().max() == 0
+    # 'sum' mode conserves mass for flows that stay in bounds
+    fl = torch.rand(2, 2, 7, 9, generator=g) * 0.9
+    inner = torch.zeros_like(x)
+    inner[:, :, 1:-2, 1:-2] = x[:, :, 1:-2, 1:-2]
+    assert torch.allclose(softsplat(inner, fl, None, "sum").sum((2, 3)), inner.sum((2, 3)), rtol=1e-4, atol=1e-4)
+    # non-finite flow is skipped (softsplat.py:301-302)
+    fl = torch.zeros(1, 2, 4, 4)
+    fl[0, 0, 1, 1] = float("nan")
+    o = softsplat(torch.ones(1, 1, 4, 4), fl, None, "sum")
+    assert o[0, 0, 1, 1] == 0 and o.sum() == 15
+
+
+def test_zero_convs_make_adapter_a_noop():
+    """Q19: with the reference's zero-initialised output convs every residual is exactly zero."""
+    from oracle import fixtures
+    from oracle.models import FlowControlNet
+    cfg = dict(fixtures.TINY_CONFIG)
+    torch.manual_seed(0)
+    ad = FlowControlNet(**cfg).eval()
+    inp = fixtures.make_step_inputs(cfg, 16, 16)
+    with torch.no_grad():
+        dres, mid, _, _ = ad(inp["sample"], torch.tensor(1.0), inp["encoder_hidden_states"], inp["added_time_ids"],
+                             controlnet_cond=inp["controlnet_cond"], controlnet_flow=inp["controlnet_flow"])
+    assert all(d.abs().max() == 0 for d in dres) and mid.abs().max() == 0
