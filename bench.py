@@ -83,7 +83,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm (oracle): bounded sample of the same workload
 # ------------------------------------------------------------------------------------------------
-def _cpu_sample(steps, warmup, frames_per_half=2, budget_s=240.0):
+def _cpu_sample(steps, warmup, frames_per_half=2, budget_s=60.0):
     """One denoise step (adapter trunk + cond branch + UNet, fp32) at 576x1024 on 2*frames_per_half of the 50
     CFG-batched frames, on all host cores; clip time is extrapolated x(50/frames) x25 steps (VAE/CLIP excluded).
     If `steps` such samples would not fit `budget_s` (judged from the first evaluation) the spatial size is halved
@@ -128,13 +128,20 @@ def _cpu_sample(steps, warmup, frames_per_half=2, budget_s=240.0):
                 return unet(sample, t, emb, dres, mid, added_time_ids=ids)[0]
         return one
 
-    for (hh, ww, rel) in shapes:
-        one = make(hh, ww)
+    # probe the smallest shape first and move up while the estimated run (FLOP-scaled) still fits the budget
+    evals = steps + max(warmup - 1, 0)
+    pick = len(shapes) - 1
+    one = make(*shapes[pick][:2])
+    t0 = time.perf_counter()
+    one()  # doubles as warm-up
+    probe = time.perf_counter() - t0
+    while pick > 0 and probe * (shapes[pick - 1][2] / shapes[pick][2]) * (evals + 1) <= budget_s:
+        pick -= 1
+        one = make(*shapes[pick][:2])
         t0 = time.perf_counter()
-        one()  # first evaluation doubles as warm-up and as the budget probe
+        one()
         probe = time.perf_counter() - t0
-        if probe * (steps + max(warmup - 1, 0)) <= budget_s or (hh, ww) == shapes[-1][:2]:
-            break
+    hh, ww, rel = shapes[pick]
     for _ in range(max(warmup - 1, 0)):
         one()
     t0 = time.perf_counter()
@@ -152,7 +159,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    fps, dt, cores, desc = _cpu_sample(max(args.steps, 1), min(args.warmup, 1))
+    fps, dt, cores, desc = _cpu_sample(max(args.steps, 1), min(args.warmup, 1), budget_s=180.0)
     out = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",

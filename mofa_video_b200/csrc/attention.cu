@@ -382,7 +382,7 @@ attn_temporal_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
 
 using namespace mofa;
 
-extern "C" int mofa_attn_spatial(const void* qkv, void* out, int32_t frames, int32_t L, int32_t heads, float scale,
+int attn_spatial_v1(const void* qkv, void* out, int32_t frames, int32_t L, int32_t heads, float scale,
                                  mofa_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!qkv || !out || frames <= 0 || L <= 0 || heads <= 0) {

@@ -150,7 +150,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const uint32_t b_bytes = static_cast<uint32_t>(p.bn) * (BK * 2);
     const uint32_t stage_bytes = kABytes + b_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
+    uint8_t* staging = smem + static_cast<size_t>(p.stages) * stage_bytes;  // 4 epilogue warps x 4 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 4 * 4096);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + p.stages;
     uint64_t* tfull_bar = bars + 2 * p.stages;
@@ -279,66 +280,182 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 row = static_cast<long long>(tc.frame) * p.HW + pp;
             }
             const long long group =
-                p.rowbias ? (p.rowbias_mod > 0 ? row % p.rowbias_mod : row / p.rows_per_group) : 0;
+                (p.rowbias && valid) ? (p.rowbias_mod > 0 ? row % p.rowbias_mod : row / p.rows_per_group) : 0;
 
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * acc_stride;
 
-            if constexpr (!kGeglu) {
-                const int chunks = (p.bn + 31) / 32;
-                for (int c = 0; c < chunks; ++c) {
-                    uint32_t acc[32];
-                    tmem_ld_32x32(taddr + c * 32, acc);
-                    tmem_ld_wait();
-                    if (valid) {
+            if (p.vec_ok) {
+                // ---- staged epilogue: (1) row-owner layout: bias / row-group bias / activation / alpha, fp16 into a
+                //      swizzled per-warp staging tile; (2) coalesced layout (8 lanes x 16 B = one 128 B row segment):
+                //      residual loads and the global store.  Only __syncwarp() is needed: a warp re-reads its own rows.
+                uint8_t* stg = staging + (warp - 2) * 4096;
+                const int sub = lane >> 3, chk = lane & 7;
+                const int out_cols = kGeglu ? (p.bn >> 1) : p.bn;  // output columns of this N tile
+                const int n_chunks = (out_cols + 63) >> 6;
+                for (int c = 0; c < n_chunks; ++c) {
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const int ncol = c * 32 + g * 8;
-                            if (ncol < p.bn) {
-                                const int n = nt * p.bn + ncol;
-                                if (n < p.N_out) {
-                                    float v[8];
+                    for (int hlf = 0; hlf < 2; ++hlf) {
+                        const int col0 = c * 64 + hlf * 32;
+                        if (col0 < out_cols) {
+                            uint32_t acc[32];
+                            tmem_ld_32x32(taddr + col0, acc);
+                            if constexpr (kGeglu) {
+                                uint32_t ag[32];
+                                tmem_ld_32x32(taddr + (p.bn >> 1) + col0, ag);
+                                tmem_ld_wait();
 #pragma unroll
-                                    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
-                                    epilogue_store8(p, v, row, group, n, n, p.act == 1, true);
+                                for (int g = 0; g < 4; ++g) {
+                                    const int nb = nt * p.bn + col0 + g * 8;
+                                    H8 bv, bg;
+                                    bv.u = make_uint4(0, 0, 0, 0);
+                                    bg.u = make_uint4(0, 0, 0, 0);
+                                    if (p.bias) {
+                                        bv.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nb));
+                                        bg.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nb + (p.bn >> 1)));
+                                    }
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        const float val = __uint_as_float(acc[g * 8 + j]) + __half2float(bv.h[j]);
+                                        const float gate = __uint_as_float(ag[g * 8 + j]) + __half2float(bg.h[j]);
+                                        acc[g * 8 + j] = __float_as_uint(val * gelu_erf_f(gate) * p.alpha);
+                                    }
+                                }
+                            } else {
+                                tmem_ld_wait();
+                                const bool silu = p.act == 1;
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) {
+                                    const int nb = nt * p.bn + col0 + g * 8;
+                                    float add[8];
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) add[j] = 0.f;
+                                    if (nb < p.N_out) {  // N_out % 8 == 0 on this path
+                                        if (p.bias) {
+                                            H8 b;
+                                            b.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nb));
+#pragma unroll
+                                            for (int j = 0; j < 8; ++j) add[j] += __half2float(b.h[j]);
+                                        }
+                                        if (p.rowbias) {
+                                            H8 b;
+                                            b.u = __ldg(reinterpret_cast<const uint4*>(p.rowbias + group * p.ld_rowbias + nb));
+#pragma unroll
+                                            for (int j = 0; j < 8; ++j) add[j] += __half2float(b.h[j]);
+                                        }
+                                    }
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        float v = __uint_as_float(acc[g * 8 + j]) + add[j];
+                                        if (silu) v = silu_f(v);
+                                        acc[g * 8 + j] = __float_as_uint(v * p.alpha);
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                H8 o;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    o.h2[j] = __floats2half2_rn(__uint_as_float(acc[g * 8 + 2 * j]),
+                                                                __uint_as_float(acc[g * 8 + 2 * j + 1]));
+                                const int ci = hlf * 4 + g;
+                                *reinterpret_cast<uint4*>(stg + lane * 128 + ((ci ^ (lane & 7)) << 4)) = o.u;
+                            }
+                        }
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rl = i * 4 + sub;
+                        const long long rrow = __shfl_sync(0xffffffffu, row, rl);
+                        const int rvalid = __shfl_sync(0xffffffffu, valid ? 1 : 0, rl);
+                        const int ncol = c * 64 + chk * 8;
+                        const int n_out = nt * out_cols + ncol;
+                        if (rvalid && ncol < out_cols && n_out < p.N_out) {
+                            H8 v;
+                            v.u = *reinterpret_cast<const uint4*>(stg + rl * 128 + ((chk ^ (rl & 7)) << 4));
+                            if (p.res1 || p.res2) {
+                                float f[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) f[j] = __half2float(v.h[j]);
+                                if (p.res1) {
+                                    H8 rr;
+                                    rr.u = __ldg(reinterpret_cast<const uint4*>(p.res1 + rrow * p.ldr1 + n_out));
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) f[j] += p.beta1 * __half2float(rr.h[j]);
+                                }
+                                if (p.res2) {
+                                    H8 rr;
+                                    rr.u = __ldg(reinterpret_cast<const uint4*>(p.res2 + rrow * p.ldr2 + n_out));
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) f[j] += p.beta2 * __half2float(rr.h[j]);
+                                }
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) v.h2[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+                            }
+                            *reinterpret_cast<uint4*>(p.out + rrow * p.ldc + n_out) = v.u;
+                        }
+                    }
+                    __syncwarp();
+                }
+            } else {
+                if constexpr (!kGeglu) {
+                    const int chunks = (p.bn + 31) / 32;
+                    for (int c = 0; c < chunks; ++c) {
+                        uint32_t acc[32];
+                        tmem_ld_32x32(taddr + c * 32, acc);
+                        tmem_ld_wait();
+                        if (valid) {
+    #pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const int ncol = c * 32 + g * 8;
+                                if (ncol < p.bn) {
+                                    const int n = nt * p.bn + ncol;
+                                    if (n < p.N_out) {
+                                        float v[8];
+    #pragma unroll
+                                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
+                                        epilogue_store8(p, v, row, group, n, n, p.act == 1, true);
+                                    }
                                 }
                             }
                         }
                     }
-                }
-            } else {
-                const int half_bn = p.bn >> 1;
-                const int chunks = half_bn / 32;
-                for (int c = 0; c < chunks; ++c) {
-                    uint32_t av[32], ag[32];
-                    tmem_ld_32x32(taddr + c * 32, av);
-                    tmem_ld_32x32(taddr + half_bn + c * 32, ag);
-                    tmem_ld_wait();
-                    if (valid) {
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const int ncol = c * 32 + g * 8;
-                            const int n_out = nt * half_bn + ncol;
-                            const int n_val = nt * p.bn + ncol;
-                            const int n_gate = n_val + half_bn;
-                            if (n_out < p.N_out) {
-                                float v[8];
-                                H8 bv, bg;
-                                bv.u = make_uint4(0, 0, 0, 0);
-                                bg.u = make_uint4(0, 0, 0, 0);
-                                if (p.bias) {
-                                    bv.u = *reinterpret_cast<const uint4*>(p.bias + n_val);
-                                    bg.u = *reinterpret_cast<const uint4*>(p.bias + n_gate);
+                } else {
+                    const int half_bn = p.bn >> 1;
+                    const int chunks = half_bn / 32;
+                    for (int c = 0; c < chunks; ++c) {
+                        uint32_t av[32], ag[32];
+                        tmem_ld_32x32(taddr + c * 32, av);
+                        tmem_ld_32x32(taddr + half_bn + c * 32, ag);
+                        tmem_ld_wait();
+                        if (valid) {
+    #pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const int ncol = c * 32 + g * 8;
+                                const int n_out = nt * half_bn + ncol;
+                                const int n_val = nt * p.bn + ncol;
+                                const int n_gate = n_val + half_bn;
+                                if (n_out < p.N_out) {
+                                    float v[8];
+                                    H8 bv, bg;
+                                    bv.u = make_uint4(0, 0, 0, 0);
+                                    bg.u = make_uint4(0, 0, 0, 0);
+                                    if (p.bias) {
+                                        bv.u = *reinterpret_cast<const uint4*>(p.bias + n_val);
+                                        bg.u = *reinterpret_cast<const uint4*>(p.bias + n_gate);
+                                    }
+    #pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        const float val = __uint_as_float(av[g * 8 + j]) + __half2float(bv.h[j]);
+                                        const float gate = __uint_as_float(ag[g * 8 + j]) + __half2float(bg.h[j]);
+                                        v[j] = val * gelu_erf_f(gate);
+                                    }
+                                    // bias already applied; reuse the common tail for alpha / residuals / store
+                                    epilogue_store8(p, v, row, 0, 0, n_out, false, false);
                                 }
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float val = __uint_as_float(av[g * 8 + j]) + __half2float(bv.h[j]);
-                                    const float gate = __uint_as_float(ag[g * 8 + j]) + __half2float(bg.h[j]);
-                                    v[j] = val * gelu_erf_f(gate);
-                                }
-                                // bias already applied; reuse the common tail for alpha / residuals / store
-                                epilogue_store8(p, v, row, 0, 0, n_out, false, false);
                             }
                         }
                     }
@@ -455,7 +572,8 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
         set_last_error("mofa_gemm: bad N=%d for bn=%d", a->N, bn);
         return MOFA_ERR_ARG;
     }
-    const bool vec_ok = (a->ldc % 8) == 0 && !(a->res1 && (a->ldr1 % 8)) && !(a->res2 && (a->ldr2 % 8)) &&
+    const int n_out_cols = geglu ? a->N / 2 : a->N;
+    const bool vec_ok = (n_out_cols % 8) == 0 && (a->ldc % 8) == 0 && !(a->res1 && (a->ldr1 % 8)) && !(a->res2 && (a->ldr2 % 8)) &&
                         !(a->rowbias && (a->ld_rowbias % 8));
     if (geglu && !vec_ok) {
         set_last_error("mofa_gemm: GEGLU needs ldc / ldr multiples of 8 elements");
@@ -577,7 +695,7 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     p.stages = stages;
-    const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
+    const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 4 * 4096 + (2 * stages + 4) * 8 + 16 + 1024;
 
     const long long total = static_cast<long long>(p.m_tiles) * p.n_tiles;
     int grid = num_sms();

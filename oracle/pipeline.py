@@ -65,6 +65,10 @@ def run_pipeline(vae, image_encoder, unet, controlnet, scheduler, image, control
     do_cfg = max_guidance_scale > 1.0
     assert do_cfg, "Q5: without CFG the reference feeds the latents as condition (pipeline.py:393,396)"
     # 3. CLIP (Q3)                                                                           :114-141
+    if isinstance(image, torch.Tensor) and image.ndim == 3:
+        image = image[None]
+    if isinstance(controlnet_condition, torch.Tensor) and controlnet_condition.ndim == 3:
+        controlnet_condition = controlnet_condition[None]
     img01 = pil_to_pt(image) if not isinstance(image, torch.Tensor) else image
     clip_in = resize_with_antialiasing(img01, (224, 224)).to(dtype)
     emb = image_encoder(clip_in).image_embeds.unsqueeze(1)
