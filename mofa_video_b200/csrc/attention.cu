@@ -21,6 +21,8 @@ namespace mofa {
 
 int make_tmap_f16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box);
+int attn_spatial_v1(const void* qkv, void* out, int32_t frames, int32_t L, int32_t heads, float scale,
+                    mofa_stream_t stream_);
 
 constexpr int kAttnThreads = 192;
 constexpr int kKVStages = 3;
@@ -382,8 +384,8 @@ attn_temporal_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
 
 using namespace mofa;
 
-int attn_spatial_v1(const void* qkv, void* out, int32_t frames, int32_t L, int32_t heads, float scale,
-                                 mofa_stream_t stream_) {
+int mofa::attn_spatial_v1(const void* qkv, void* out, int32_t frames, int32_t L, int32_t heads, float scale,
+                          mofa_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!qkv || !out || frames <= 0 || L <= 0 || heads <= 0) {
         set_last_error("mofa_attn_spatial: bad arguments");
