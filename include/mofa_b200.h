@@ -168,6 +168,20 @@ int mofa_softsplat_avg(const void* feat, const void* flow, float* acc, float* ws
 int mofa_cfg_euler_step(const void* noise, void* latents_h, const void* image_latents, void* next_in, int32_t T,
                         int32_t HW, float g_min, float g_max, float sigma, float sigma_next, mofa_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * VAE temporal decoder helpers (diffusers 0.24 TemporalDecoder, called from pipeline.py:194-220).
+ * The decoder's convolutions / GroupNorms / temporal convs reuse mofa_gemm / mofa_groupnorm; its single-head
+ * d=512 mid-block attention is GEMM -> mofa_softmax_rows -> GEMM.
+ * ---------------------------------------------------------------------------------------------- */
+/* in-place softmax over each row of x[rows, ld] (first L columns), fp16 storage, fp32 math, L % 8 == 0, L <= 16384 */
+int mofa_softmax_rows(void* x, int64_t rows, int32_t L, int64_t ld, mofa_stream_t stream);
+
+/* time_conv_out = Conv3d(3,3,(3,1,1),pad (1,0,0)) over the T frames of a chunk: y fp16 [T, HW, 3] channels-last,
+ * w fp32 [3(co),3(ci),3(kt)], b fp32 [3]; writes out_f32 NCHW [T,3,HW] (decoder `sample`) and/or out_u8
+ * [T,HW,3] = round(clamp(v/2+0.5,0,1)*255)  (VaeImageProcessor.postprocess, pipeline.py:57-69) */
+int mofa_vae_time_conv_out(const void* y, const float* w, const float* b, float* out_f32, void* out_u8, int32_t T,
+                           int64_t HW, mofa_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

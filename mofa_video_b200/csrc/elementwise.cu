@@ -599,3 +599,126 @@ extern "C" int mofa_cfg_euler_step(const void* noise, void* latents_h, const voi
         static_cast<__half*>(next_in), T, HW, g_min, g_max, sigma, sigma_next);
     return check_launch("mofa_cfg_euler_step");
 }
+
+// =============================================================================================
+// row softmax in place (VAE mid-block attention computed as GEMM -> softmax -> GEMM, head_dim 512)
+// =============================================================================================
+namespace mofa {
+
+__global__ void __launch_bounds__(128)
+softmax_rows_kernel(__half* __restrict__ x, long long rows, int L, long long ld) {
+    const long long row = blockIdx.x;
+    if (row >= rows) return;
+    __half* xr = x + row * ld;
+    const int vecs = L >> 3;
+    float v[16][8];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int vec = threadIdx.x + i * 128;
+        if (vec < vecs) {
+            V8 t;
+            t.u = *reinterpret_cast<const uint4*>(xr + vec * 8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[i][j] = __half2float(t.h[j]);
+                mx = fmaxf(mx, v[i][j]);
+            }
+        }
+    }
+    __shared__ float red[4];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    __syncthreads();
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int vec = threadIdx.x + i * 128;
+        if (vec < vecs) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[i][j] = __expf(v[i][j] - mx);
+                sum += v[i][j];
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    const float inv = 1.0f / (red[0] + red[1] + red[2] + red[3]);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int vec = threadIdx.x + i * 128;
+        if (vec < vecs) {
+            V8 o;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.h[j] = __float2half_rn(v[i][j] * inv);
+            *reinterpret_cast<uint4*>(xr + vec * 8) = o.u;
+        }
+    }
+}
+
+// TemporalDecoder tail: time_conv_out = Conv3d(3, 3, (3,1,1), padding (1,0,0)) over the frames of a chunk, then the
+// reference's post-processing (x/2+0.5).clamp(0,1)*255 -> uint8 (optional) -- SURVEY.md §8f row 3 "frame epilogue".
+__global__ void __launch_bounds__(256)
+vae_time_conv_out_kernel(const __half* __restrict__ y, const float* __restrict__ w, const float* __restrict__ b,
+                         float* __restrict__ out_f32, uint8_t* __restrict__ out_u8, int T, long long HW) {
+    const long long total = static_cast<long long>(T) * HW;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int t = static_cast<int>(idx / HW);
+        const long long p = idx - static_cast<long long>(t) * HW;
+        float acc[3] = {b[0], b[1], b[2]};
+#pragma unroll
+        for (int dt = 0; dt < 3; ++dt) {
+            const int tt = t + dt - 1;
+            if (tt < 0 || tt >= T) continue;
+            const __half* src = y + (static_cast<long long>(tt) * HW + p) * 3;
+            const float x0 = __half2float(src[0]), x1 = __half2float(src[1]), x2 = __half2float(src[2]);
+#pragma unroll
+            for (int co = 0; co < 3; ++co)  // w[co][ci][dt]
+                acc[co] += w[(co * 3 + 0) * 3 + dt] * x0 + w[(co * 3 + 1) * 3 + dt] * x1 + w[(co * 3 + 2) * 3 + dt] * x2;
+        }
+        if (out_f32) {
+#pragma unroll
+            for (int co = 0; co < 3; ++co) out_f32[(static_cast<long long>(t) * 3 + co) * HW + p] = acc[co];
+        }
+        if (out_u8) {
+#pragma unroll
+            for (int co = 0; co < 3; ++co) {
+                float u = fminf(fmaxf(acc[co] * 0.5f + 0.5f, 0.f), 1.f) * 255.f;
+                out_u8[(static_cast<long long>(t) * HW + p) * 3 + co] = static_cast<uint8_t>(__float2int_rn(u));
+            }
+        }
+    }
+}
+
+}  // namespace mofa
+
+extern "C" int mofa_softmax_rows(void* x, int64_t rows, int32_t L, int64_t ld, mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!x || rows <= 0 || L <= 0 || (L % 8) != 0 || L > 16384 || (ld % 8) != 0) {
+        set_last_error("mofa_softmax_rows: needs L %% 8 == 0 and L <= 16384 (L=%d)", L);
+        return MOFA_ERR_ARG;
+    }
+    mofa::softmax_rows_kernel<<<static_cast<unsigned>(rows), 128, 0, stream>>>(static_cast<__half*>(x), rows, L, ld);
+    return check_launch("mofa_softmax_rows");
+}
+
+extern "C" int mofa_vae_time_conv_out(const void* y, const float* w, const float* b, float* out_f32, void* out_u8,
+                                      int32_t T, int64_t HW, mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!y || !w || !b || (!out_f32 && !out_u8) || T <= 0 || HW <= 0) {
+        set_last_error("mofa_vae_time_conv_out: bad arguments");
+        return MOFA_ERR_ARG;
+    }
+    long long blocks = (static_cast<long long>(T) * HW + 255) / 256;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    mofa::vae_time_conv_out_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        static_cast<const __half*>(y), w, b, out_f32, static_cast<uint8_t*>(out_u8), T, HW);
+    return check_launch("mofa_vae_time_conv_out");
+}

@@ -1,19 +1,27 @@
 // Persistent, warp-specialised tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
 //
 //   warp 0 (1 lane)  : TMA producer  -- A tile (128 x 64 fp16) + B tile (bn x 64 fp16) per k-block
-//   warp 1 (1 lane)  : MMA issuer    -- 4 x tcgen05.mma (M=128, N=bn, K=16) per k-block, fp32 in TMEM
-//   warps 2..5       : epilogue      -- tcgen05.ld 32x32b, fused bias / row-group bias / SiLU / GEGLU /
-//                                       scaled residuals, fp16 stores straight from registers
+//   warp 1 (1 lane)  : MMA issuer    -- 4 x tcgen05.mma (M=128, N<=bn, K=16) per k-block, fp32 in TMEM
+//   warps 2..9       : epilogue      -- two warps per TMEM lane quarter, alternating 64-column chunks:
+//                                       tcgen05.ld 32x32b -> bias / row-group bias / SiLU / GEGLU / alpha /
+//                                       scaled residuals in registers (row-owner layout, residual loads issued
+//                                       as one batch) -> fp16 into a SWIZZLE_128B staging tile -> TMA store
+//                                       (hardware clips ragged rows/columns; no per-thread global stores)
 //   two TMEM accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
 //
 // The A operand is always a K-major SWIZZLE_128B tile written by TMA; what changes between a Linear,
 // a 3x3 convolution and a (3,1,1) temporal convolution is only the tensor map and the coordinates of
 // the box fetched for each k-block (shifted boxes; the halo is zero-filled by TMA OOB handling).
+// The last N tile of a row may be narrower: its MMA N shrinks (instruction descriptor per tile).
 //
 // Replaces (reference = diffusers 0.24 blocks instantiated at
 // /root/reference/MOFA-Video-Traj/models/unet_spatio_temporal_condition_controlnet.py:169-233 and
 // /root/reference/MOFA-Video-Traj/models/controlnet_sdv.py:270-309): cuDNN Conv2d/Conv3d and cuBLAS
 // Linear inside ResnetBlock2D / TemporalResnetBlock / BasicTransformerBlock / FeedForward(GEGLU).
+//
+// Round-1 profile notes (profiles/): the first version stored straight from registers (16 B per thread per
+// row: half-used sectors) and its unrolled epilogue was > 64 KB of SASS: ncu showed stall_no_inst and
+// exposed residual-load latency dominating K=320 GEMMs (15 % tensor-pipe).  Hence the compact loops here.
 #include <stdarg.h>
 #include <stdio.h>
 
@@ -24,16 +32,20 @@ namespace mofa {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kABytes = BM * BK * 2;
 constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kStagingBytes = 4096;  // 32 rows x 128 B per epilogue warp
 
 struct GemmKernelParams {
     int mode, act;
     int m_tiles, n_tiles, num_kb, kb_per_tap, kb_split;
+    int N;      // weight rows
     int N_out;  // valid output columns (N, or N/2 for GEGLU)
     int bn;     // weight rows per N tile
     int stages;
+    int tma_out;  // epilogue through staging + TMA store (needs 16-byte aligned rows, N_out >= 64)
     long long M;
     int H, W, tiles_x, tiles_y, BH, BW;
     int T, HW, tiles_p;
@@ -44,7 +56,7 @@ struct GemmKernelParams {
     long long ld_rowbias;
     long long rows_per_group;
     long long rowbias_mod;  // > 0: group = row % rowbias_mod instead of row / rows_per_group
-    int vec_ok;             // all leading dimensions are multiples of 8 -> 16-byte epilogue accesses
+    int vec_ok;             // leading dimensions multiples of 8 -> 16-byte accesses allowed
     const __half* res1;
     long long ldr1;
     const __half* res2;
@@ -84,31 +96,28 @@ union H8 {
     __half h[8];
 };
 
-// one group of 8 consecutive output columns of one row: bias / rowbias / activation / residuals / store
-MOFA_DEVICE void epilogue_store8(const GemmKernelParams& p, float (&v)[8], long long row, long long group, int n_bias,
-                                 int n_out, bool act_silu, bool add_bias) {
+// fallback for narrow / unaligned outputs (N = 3, 4, 16, ...): scalar or 16-byte stores straight from registers
+__device__ __noinline__ void epilogue_direct8(const GemmKernelParams& p, const float* vin, long long row,
+                                              long long group, int n_bias, int n_out, bool act_silu) {
     const bool full = p.vec_ok && (n_out + 8 <= p.N_out);
-    const bool use_bias = add_bias && p.bias != nullptr;
-    const bool use_rowbias = add_bias && p.rowbias != nullptr;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = vin[j];
     if (full) {
-        if (use_bias) {
+        if (p.bias) {
             H8 b;
             b.u = *reinterpret_cast<const uint4*>(p.bias + n_bias);
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] += __half2float(b.h[j]);
         }
-        if (use_rowbias) {
+        if (p.rowbias) {
             H8 b;
             b.u = *reinterpret_cast<const uint4*>(p.rowbias + group * p.ld_rowbias + n_bias);
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] += __half2float(b.h[j]);
         }
-        if (act_silu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] *= p.alpha;
+        for (int j = 0; j < 8; ++j) v[j] = (act_silu ? silu_f(v[j]) : v[j]) * p.alpha;
         if (p.res1) {
             H8 r;
             r.u = *reinterpret_cast<const uint4*>(p.res1 + row * p.ldr1 + n_out);
@@ -129,8 +138,8 @@ MOFA_DEVICE void epilogue_store8(const GemmKernelParams& p, float (&v)[8], long 
         for (int j = 0; j < 8; ++j) {
             if (n_out + j >= p.N_out) break;
             float x = v[j];
-            if (use_bias) x += __half2float(p.bias[n_bias + j]);
-            if (use_rowbias) x += __half2float(p.rowbias[group * p.ld_rowbias + n_bias + j]);
+            if (p.bias) x += __half2float(p.bias[n_bias + j]);
+            if (p.rowbias) x += __half2float(p.rowbias[group * p.ld_rowbias + n_bias + j]);
             if (act_silu) x = silu_f(x);
             x *= p.alpha;
             if (p.res1) x += p.beta1 * __half2float(p.res1[row * p.ldr1 + n_out + j]);
@@ -143,15 +152,16 @@ MOFA_DEVICE void epilogue_store8(const GemmKernelParams& p, float (&v)[8], long 
 template <bool kGeglu>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmB, const GemmKernelParams p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+               const GemmKernelParams p) {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024 B alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
     const uint32_t b_bytes = static_cast<uint32_t>(p.bn) * (BK * 2);
     const uint32_t stage_bytes = kABytes + b_bytes;
-    uint8_t* staging = smem + static_cast<size_t>(p.stages) * stage_bytes;  // 4 epilogue warps x 4 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 4 * 4096);
+    uint8_t* staging = smem + static_cast<size_t>(p.stages) * stage_bytes;  // kEpiWarps x 4 KB, 1024-aligned
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kEpiWarps * kStagingBytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + p.stages;
     uint64_t* tfull_bar = bars + 2 * p.stages;
@@ -165,17 +175,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmA2);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmOut);
         for (int i = 0; i < p.stages; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);
+            mbar_init(&tempty_bar[i], kEpiWarps);
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_ptr_smem, kTmemCols);
+    if (warp == 1) tmem_alloc(tmem_ptr_smem, kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -223,11 +234,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (threadIdx.x == 32) {
         // ===================== MMA issuer =====================
-        const uint32_t idesc = umma_idesc_f16(static_cast<uint32_t>(p.bn), false);
         int stage = 0;
         uint32_t phase = 0;
         uint32_t iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+            const int nt = tile % p.n_tiles;
+            int n_this = p.N - nt * p.bn;             // the last N tile of a row may be narrower
+            n_this = n_this >= p.bn ? p.bn : ((n_this + 15) & ~15);
+            const uint32_t idesc = umma_idesc_f16(static_cast<uint32_t>(n_this), false);
             const uint32_t as = iter & 1u;
             const uint32_t aphase = (iter >> 1) & 1u;
             mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -254,8 +268,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp >= 2) {
         // ===================== epilogue =====================
-        const int q = warp & 3;  // TMEM lane quarter this warp may touch
+        const int e = warp - 2;
+        const int q = warp & 3;   // TMEM lane quarter this warp may touch
+        const int half = e >> 2;  // which of the two warps sharing that quarter
         const int r = q * 32 + lane;
+        uint8_t* stg = staging + e * kStagingBytes;
+        const int half_bn = p.bn >> 1;
         uint32_t iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
             const int mt = tile / p.n_tiles;
@@ -281,181 +299,148 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             const long long group =
                 (p.rowbias && valid) ? (p.rowbias_mod > 0 ? row % p.rowbias_mod : row / p.rows_per_group) : 0;
+            const int out_cols_tile = kGeglu ? half_bn : p.bn;          // output columns per full N tile
+            int out_cols = p.N_out - nt * out_cols_tile;                // ... of this tile
+            out_cols = out_cols > out_cols_tile ? out_cols_tile : out_cols;
 
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * acc_stride;
 
-            if (p.vec_ok) {
-                // ---- staged epilogue: (1) row-owner layout: bias / row-group bias / activation / alpha, fp16 into a
-                //      swizzled per-warp staging tile; (2) coalesced layout (8 lanes x 16 B = one 128 B row segment):
-                //      residual loads and the global store.  Only __syncwarp() is needed: a warp re-reads its own rows.
-                uint8_t* stg = staging + (warp - 2) * 4096;
-                const int sub = lane >> 3, chk = lane & 7;
-                const int out_cols = kGeglu ? (p.bn >> 1) : p.bn;  // output columns of this N tile
+            if (p.tma_out) {
                 const int n_chunks = (out_cols + 63) >> 6;
-                for (int c = 0; c < n_chunks; ++c) {
-#pragma unroll
+#pragma unroll 1
+                for (int c = half; c < n_chunks; c += 2) {
+                    // the staging tile is free once the previous TMA store of this warp has read it
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+#pragma unroll 1
                     for (int hlf = 0; hlf < 2; ++hlf) {
-                        const int col0 = c * 64 + hlf * 32;
-                        if (col0 < out_cols) {
-                            uint32_t acc[32];
-                            tmem_ld_32x32(taddr + col0, acc);
-                            if constexpr (kGeglu) {
-                                uint32_t ag[32];
-                                tmem_ld_32x32(taddr + (p.bn >> 1) + col0, ag);
-                                tmem_ld_wait();
+                        const int col0 = c * 64 + hlf * 32;           // column inside the tile's output
+                        if (col0 >= out_cols) break;
+                        const int n_out0 = nt * out_cols_tile + col0; // global output column
+                        // residual loads first (one batch in flight), consumed after the TMEM load
+                        uint4 r1[4], r2[4];
+                        const bool do1 = p.res1 != nullptr && valid, do2 = p.res2 != nullptr && valid;
 #pragma unroll
-                                for (int g = 0; g < 4; ++g) {
-                                    const int nb = nt * p.bn + col0 + g * 8;
-                                    H8 bv, bg;
-                                    bv.u = make_uint4(0, 0, 0, 0);
-                                    bg.u = make_uint4(0, 0, 0, 0);
-                                    if (p.bias) {
-                                        bv.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nb));
-                                        bg.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nb + (p.bn >> 1)));
-                                    }
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) {
-                                        const float val = __uint_as_float(acc[g * 8 + j]) + __half2float(bv.h[j]);
-                                        const float gate = __uint_as_float(ag[g * 8 + j]) + __half2float(bg.h[j]);
-                                        acc[g * 8 + j] = __float_as_uint(val * gelu_erf_f(gate) * p.alpha);
-                                    }
-                                }
-                            } else {
-                                tmem_ld_wait();
-                                const bool silu = p.act == 1;
-#pragma unroll
-                                for (int g = 0; g < 4; ++g) {
-                                    const int nb = nt * p.bn + col0 + g * 8;
-                                    float add[8];
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) add[j] = 0.f;
-                                    if (nb < p.N_out) {  // N_out % 8 == 0 on this path
-                                        if (p.bias) {
-                                            H8 b;
-                                            b.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nb));
-#pragma unroll
-                                            for (int j = 0; j < 8; ++j) add[j] += __half2float(b.h[j]);
-                                        }
-                                        if (p.rowbias) {
-                                            H8 b;
-                                            b.u = __ldg(reinterpret_cast<const uint4*>(p.rowbias + group * p.ld_rowbias + nb));
-#pragma unroll
-                                            for (int j = 0; j < 8; ++j) add[j] += __half2float(b.h[j]);
-                                        }
-                                    }
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) {
-                                        float v = __uint_as_float(acc[g * 8 + j]) + add[j];
-                                        if (silu) v = silu_f(v);
-                                        acc[g * 8 + j] = __float_as_uint(v * p.alpha);
-                                    }
-                                }
+                        for (int g = 0; g < 4; ++g) {
+                            r1[g] = make_uint4(0, 0, 0, 0);
+                            r2[g] = make_uint4(0, 0, 0, 0);
+                            if (n_out0 + g * 8 < p.N_out) {
+                                if (do1) r1[g] = __ldg(reinterpret_cast<const uint4*>(p.res1 + row * p.ldr1 + n_out0) + g);
+                                if (do2) r2[g] = __ldg(reinterpret_cast<const uint4*>(p.res2 + row * p.ldr2 + n_out0) + g);
                             }
+                        }
+                        uint32_t acc[32];
+                        tmem_ld_32x32(taddr + col0, acc);
+                        if constexpr (kGeglu) {
+                            uint32_t ag[32];
+                            tmem_ld_32x32(taddr + half_bn + col0, ag);
+                            tmem_ld_wait();
 #pragma unroll
                             for (int g = 0; g < 4; ++g) {
-                                H8 o;
-#pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    o.h2[j] = __floats2half2_rn(__uint_as_float(acc[g * 8 + 2 * j]),
-                                                                __uint_as_float(acc[g * 8 + 2 * j + 1]));
-                                const int ci = hlf * 4 + g;
-                                *reinterpret_cast<uint4*>(stg + lane * 128 + ((ci ^ (lane & 7)) << 4)) = o.u;
-                            }
-                        }
-                    }
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int rl = i * 4 + sub;
-                        const long long rrow = __shfl_sync(0xffffffffu, row, rl);
-                        const int rvalid = __shfl_sync(0xffffffffu, valid ? 1 : 0, rl);
-                        const int ncol = c * 64 + chk * 8;
-                        const int n_out = nt * out_cols + ncol;
-                        if (rvalid && ncol < out_cols && n_out < p.N_out) {
-                            H8 v;
-                            v.u = *reinterpret_cast<const uint4*>(stg + rl * 128 + ((chk ^ (rl & 7)) << 4));
-                            if (p.res1 || p.res2) {
-                                float f[8];
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) f[j] = __half2float(v.h[j]);
-                                if (p.res1) {
-                                    H8 rr;
-                                    rr.u = __ldg(reinterpret_cast<const uint4*>(p.res1 + rrow * p.ldr1 + n_out));
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) f[j] += p.beta1 * __half2float(rr.h[j]);
-                                }
-                                if (p.res2) {
-                                    H8 rr;
-                                    rr.u = __ldg(reinterpret_cast<const uint4*>(p.res2 + rrow * p.ldr2 + n_out));
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) f[j] += p.beta2 * __half2float(rr.h[j]);
+                                const int nb = nt * p.bn + col0 + g * 8;
+                                H8 bv, bg;
+                                bv.u = make_uint4(0, 0, 0, 0);
+                                bg.u = make_uint4(0, 0, 0, 0);
+                                if (p.bias) {
+                                    bv.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nb));
+                                    bg.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nb + half_bn));
                                 }
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) v.h2[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+                                for (int j = 0; j < 8; ++j) {
+                                    const float val = __uint_as_float(acc[g * 8 + j]) + __half2float(bv.h[j]);
+                                    const float gate = __uint_as_float(ag[g * 8 + j]) + __half2float(bg.h[j]);
+                                    acc[g * 8 + j] = __float_as_uint(val * gelu_erf_f(gate) * p.alpha);
+                                }
                             }
-                            *reinterpret_cast<uint4*>(p.out + rrow * p.ldc + n_out) = v.u;
+                        } else {
+                            tmem_ld_wait();
+                            const bool silu = p.act == 1;
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const int nb = nt * p.bn + col0 + g * 8;
+                                float add[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) add[j] = 0.f;
+                                if (nb < p.N_out) {
+                                    if (p.bias) {
+                                        H8 b;
+                                        b.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nb));
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) add[j] += __half2float(b.h[j]);
+                                    }
+                                    if (p.rowbias) {
+                                        H8 b;
+                                        b.u = __ldg(reinterpret_cast<const uint4*>(p.rowbias + group * p.ld_rowbias + nb));
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) add[j] += __half2float(b.h[j]);
+                                    }
+                                }
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    float v = __uint_as_float(acc[g * 8 + j]) + add[j];
+                                    if (silu) v = silu_f(v);
+                                    acc[g * 8 + j] = __float_as_uint(v * p.alpha);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            H8 a1, a2, o;
+                            a1.u = r1[g];
+                            a2.u = r2[g];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float x0 = __uint_as_float(acc[g * 8 + 2 * j]);
+                                float x1 = __uint_as_float(acc[g * 8 + 2 * j + 1]);
+                                if (do1) {
+                                    x0 += p.beta1 * __half2float(a1.h[2 * j]);
+                                    x1 += p.beta1 * __half2float(a1.h[2 * j + 1]);
+                                }
+                                if (do2) {
+                                    x0 += p.beta2 * __half2float(a2.h[2 * j]);
+                                    x1 += p.beta2 * __half2float(a2.h[2 * j + 1]);
+                                }
+                                o.h2[j] = __floats2half2_rn(x0, x1);
+                            }
+                            const int ci = hlf * 4 + g;  // 16-byte chunk inside the 128-byte staging row
+                            *reinterpret_cast<uint4*>(stg + lane * 128 + ((ci ^ (lane & 7)) << 4)) = o.u;
                         }
                     }
+                    fence_proxy_async_smem();
                     __syncwarp();
+                    if (lane == 0) {
+                        const int n0 = nt * out_cols_tile + c * 64;
+                        if (p.mode == MOFA_A_LINEAR) {
+                            tma_store_2d(&tmOut, stg, n0, static_cast<int>(tc.m0) + q * 32);
+                        } else if (p.mode == MOFA_A_CONV3X3) {
+                            tma_store_4d(&tmOut, stg, n0, tc.x0, tc.y0 + (q * 32) / p.BW, tc.n_img);
+                        } else {
+                            const int b = tc.frame / p.T;
+                            tma_store_4d(&tmOut, stg, n0, tc.p0 + q * 32, tc.frame - b * p.T, b);
+                        }
+                        tma_store_commit();
+                    }
                 }
             } else {
-                if constexpr (!kGeglu) {
-                    const int chunks = (p.bn + 31) / 32;
-                    for (int c = 0; c < chunks; ++c) {
-                        uint32_t acc[32];
-                        tmem_ld_32x32(taddr + c * 32, acc);
-                        tmem_ld_wait();
-                        if (valid) {
-    #pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                const int ncol = c * 32 + g * 8;
-                                if (ncol < p.bn) {
-                                    const int n = nt * p.bn + ncol;
-                                    if (n < p.N_out) {
-                                        float v[8];
-    #pragma unroll
-                                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
-                                        epilogue_store8(p, v, row, group, n, n, p.act == 1, true);
-                                    }
-                                }
-                            }
-                        }
-                    }
-                } else {
-                    const int half_bn = p.bn >> 1;
-                    const int chunks = half_bn / 32;
-                    for (int c = 0; c < chunks; ++c) {
-                        uint32_t av[32], ag[32];
-                        tmem_ld_32x32(taddr + c * 32, av);
-                        tmem_ld_32x32(taddr + half_bn + c * 32, ag);
-                        tmem_ld_wait();
-                        if (valid) {
-    #pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                const int ncol = c * 32 + g * 8;
-                                const int n_out = nt * half_bn + ncol;
-                                const int n_val = nt * p.bn + ncol;
-                                const int n_gate = n_val + half_bn;
-                                if (n_out < p.N_out) {
-                                    float v[8];
-                                    H8 bv, bg;
-                                    bv.u = make_uint4(0, 0, 0, 0);
-                                    bg.u = make_uint4(0, 0, 0, 0);
-                                    if (p.bias) {
-                                        bv.u = *reinterpret_cast<const uint4*>(p.bias + n_val);
-                                        bg.u = *reinterpret_cast<const uint4*>(p.bias + n_gate);
-                                    }
-    #pragma unroll
-                                    for (int j = 0; j < 8; ++j) {
-                                        const float val = __uint_as_float(av[g * 8 + j]) + __half2float(bv.h[j]);
-                                        const float gate = __uint_as_float(ag[g * 8 + j]) + __half2float(bg.h[j]);
-                                        v[j] = val * gelu_erf_f(gate);
-                                    }
-                                    // bias already applied; reuse the common tail for alpha / residuals / store
-                                    epilogue_store8(p, v, row, 0, 0, n_out, false, false);
-                                }
+                // narrow / unaligned outputs: 32-column chunks straight from registers
+                const int chunks = (p.bn + 31) / 32;
+#pragma unroll 1
+                for (int c = half; c < chunks; c += 2) {
+                    uint32_t acc[32];
+                    tmem_ld_32x32(taddr + c * 32, acc);
+                    tmem_ld_wait();
+                    if (valid) {
+#pragma unroll 1
+                        for (int g = 0; g < 4; ++g) {
+                            const int ncol = c * 32 + g * 8;
+                            const int n = nt * p.bn + ncol;
+                            if (ncol < p.bn && n < p.N_out) {
+                                float v[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
+                                epilogue_direct8(p, v, row, group, n, n, p.act == 1);
                             }
                         }
                     }
@@ -465,11 +450,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[as]);
         }
+        if (lane == 0) tma_store_wait_all<0>();  // smem must outlive the last bulk store
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
@@ -564,7 +550,7 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
     }
     const bool geglu = a->act == 2;
     const int bn = a->bn;
-    if (bn < 16 || bn > 256 || (bn % 16) != 0 || (geglu && (bn % 64) != 0)) {
+    if (bn < 16 || bn > 256 || (bn % 16) != 0 || (geglu && (bn % 128) != 0)) {
         set_last_error("mofa_gemm: unsupported bn=%d (act=%d)", bn, a->act);
         return MOFA_ERR_ARG;
     }
@@ -573,10 +559,17 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
         return MOFA_ERR_ARG;
     }
     const int n_out_cols = geglu ? a->N / 2 : a->N;
-    const bool vec_ok = (n_out_cols % 8) == 0 && (a->ldc % 8) == 0 && !(a->res1 && (a->ldr1 % 8)) && !(a->res2 && (a->ldr2 % 8)) &&
-                        !(a->rowbias && (a->ld_rowbias % 8));
-    if (geglu && !vec_ok) {
-        set_last_error("mofa_gemm: GEGLU needs ldc / ldr multiples of 8 elements");
+    const bool vec_ok = (n_out_cols % 8) == 0 && (a->ldc % 8) == 0 && !(a->res1 && (a->ldr1 % 8)) &&
+                        !(a->res2 && (a->ldr2 % 8)) && !(a->rowbias && (a->ld_rowbias % 8)) &&
+                        (reinterpret_cast<uintptr_t>(a->out) % 16) == 0;
+    // TMA-store epilogue: 64-column chunks must not straddle N tiles (bn, or bn/2 for GEGLU, multiple of 64)
+    const bool tma_out = vec_ok && n_out_cols >= 64 && ((geglu ? bn / 2 : bn) % 64) == 0;
+    if (geglu && !tma_out) {
+        set_last_error("mofa_gemm: GEGLU needs 16-byte aligned rows and bn %% 128 == 0");
+        return MOFA_ERR_ARG;
+    }
+    if (geglu && a->rowbias) {
+        set_last_error("mofa_gemm: GEGLU does not take a row-group bias");
         return MOFA_ERR_ARG;
     }
 
@@ -585,8 +578,10 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
     p.mode = a->mode;
     p.act = a->act;
     p.bn = bn;
+    p.N = a->N;
     p.n_tiles = (a->N + bn - 1) / bn;
-    p.N_out = geglu ? a->N / 2 : a->N;
+    p.N_out = n_out_cols;
+    p.tma_out = tma_out ? 1 : 0;
     p.out = static_cast<__half*>(a->out);
     p.ldc = a->ldc;
     p.bias = static_cast<const __half*>(a->bias);
@@ -609,9 +604,10 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
     p.T = 1;
     p.HW = 1;
 
-    CUtensorMap tmA, tmA2, tmB;
+    CUtensorMap tmA, tmA2, tmB, tmOut;
     long long Ktot = 0;
     int rc;
+    const uint64_t ldc_b = static_cast<uint64_t>(a->ldc) * 2;
     if (a->mode == MOFA_A_LINEAR) {
         if (a->M <= 0 || a->K <= 0 || (a->K % 8) != 0 || (a->lda % 8) != 0) {
             set_last_error("mofa_gemm linear: bad M=%lld K=%lld lda=%lld", (long long)a->M, (long long)a->K,
@@ -640,6 +636,12 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
         } else {
             tmA2 = tmA;
         }
+        if (tma_out) {
+            uint64_t od[2] = {static_cast<uint64_t>(n_out_cols), static_cast<uint64_t>(a->M)};
+            uint64_t os[1] = {ldc_b};
+            uint32_t ob[2] = {64, 32};
+            if ((rc = make_tmap_f16(&tmOut, a->out, 2, od, os, ob)) != MOFA_OK) return rc;
+        }
     } else if (a->mode == MOFA_A_CONV3X3) {
         if (a->n_img <= 0 || a->H <= 0 || a->W <= 0 || a->C <= 0 || (a->C % BK) != 0) {
             set_last_error("mofa_gemm conv3x3: needs C %% 64 == 0 (C=%d)", a->C);
@@ -661,6 +663,12 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
         uint32_t box[4] = {BK, (uint32_t)p.BW, (uint32_t)p.BH, 1};
         if ((rc = make_tmap_f16(&tmA, a->a, 4, dims, strides, box)) != MOFA_OK) return rc;
         tmA2 = tmA;
+        if (tma_out) {
+            uint64_t od[4] = {(uint64_t)n_out_cols, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
+            uint64_t os[3] = {ldc_b, (uint64_t)a->W * ldc_b, (uint64_t)a->H * a->W * ldc_b};
+            uint32_t ob[4] = {64, (uint32_t)p.BW, (uint32_t)(32 / p.BW), 1};
+            if ((rc = make_tmap_f16(&tmOut, a->out, 4, od, os, ob)) != MOFA_OK) return rc;
+        }
     } else if (a->mode == MOFA_A_TEMPORAL3) {
         if (a->B <= 0 || a->T <= 0 || a->HW <= 0 || a->C <= 0 || (a->C % BK) != 0) {
             set_last_error("mofa_gemm temporal3: needs C %% 64 == 0 (C=%d)", a->C);
@@ -679,10 +687,17 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
         uint32_t box[4] = {BK, BM, 1, 1};
         if ((rc = make_tmap_f16(&tmA, a->a, 4, dims, strides, box)) != MOFA_OK) return rc;
         tmA2 = tmA;
+        if (tma_out) {
+            uint64_t od[4] = {(uint64_t)n_out_cols, (uint64_t)a->HW, (uint64_t)a->T, (uint64_t)a->B};
+            uint64_t os[3] = {ldc_b, (uint64_t)a->HW * ldc_b, (uint64_t)a->T * a->HW * ldc_b};
+            uint32_t ob[4] = {64, 32, 1, 1};
+            if ((rc = make_tmap_f16(&tmOut, a->out, 4, od, os, ob)) != MOFA_OK) return rc;
+        }
     } else {
         set_last_error("mofa_gemm: unknown mode %d", a->mode);
         return MOFA_ERR_ARG;
     }
+    if (!tma_out) tmOut = tmA;
     {
         uint64_t dims[2] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(a->N)};
         uint64_t strides[1] = {static_cast<uint64_t>(Ktot) * 2};
@@ -691,40 +706,34 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
     }
 
     const uint32_t stage_bytes = kABytes + static_cast<uint32_t>(bn) * BK * 2;
-    int stages = static_cast<int>((200u * 1024u) / stage_bytes);
+    const size_t fixed = kEpiWarps * kStagingBytes + 1024 + 256;
+    int stages = static_cast<int>((227u * 1024u - fixed) / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     p.stages = stages;
-    const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + 4 * 4096 + (2 * stages + 4) * 8 + 16 + 1024;
+    const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + kEpiWarps * kStagingBytes +
+                              (2 * stages + 4) * 8 + 16 + 1024;
 
     const long long total = static_cast<long long>(p.m_tiles) * p.n_tiles;
     int grid = num_sms();
     if (a->max_ctas > 0 && a->max_ctas < grid) grid = a->max_ctas;
     if (total < grid) grid = static_cast<int>(total);
 
-    cudaError_t e;
-    if (geglu) {
-        static size_t configured = 0;
-        if (configured < smem_bytes) {
-            e = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            if (e != cudaSuccess) {
-                set_last_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-                return MOFA_ERR_CUDA;
-            }
-            configured = 227 * 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e1 = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              227 * 1024);
+        cudaError_t e2 = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              227 * 1024);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) {
+            set_last_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+            return MOFA_ERR_CUDA;
         }
-        gemm_tc_kernel<true><<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, p);
-    } else {
-        static size_t configured = 0;
-        if (configured < smem_bytes) {
-            e = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            if (e != cudaSuccess) {
-                set_last_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-                return MOFA_ERR_CUDA;
-            }
-            configured = 227 * 1024;
-        }
-        gemm_tc_kernel<false><<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, p);
+        configured = true;
     }
+    if (geglu)
+        gemm_tc_kernel<true><<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, tmOut, p);
+    else
+        gemm_tc_kernel<false><<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, tmOut, p);
     return check_launch("mofa_gemm");
 }

@@ -204,10 +204,13 @@ class Net:
         r["n1"], r["c1"] = pk.norm(sp + ".norm1"), pk.conv3(sp + ".conv1")
         r["n2"], r["c2"] = pk.norm(sp + ".norm2"), pk.conv3(sp + ".conv2")
         r["sc"] = pk.conv1(sp + ".conv_shortcut") if (sp + ".conv_shortcut.weight") in pk.sd else None
-        r["temb_sp"] = self.temb.add(pk.get(sp + ".time_emb_proj.weight"), pk.get(sp + ".time_emb_proj.bias"))
+        has_temb = (sp + ".time_emb_proj.weight") in pk.sd  # the VAE's blocks have no time embedding
+        r["temb_sp"] = self.temb.add(pk.get(sp + ".time_emb_proj.weight"),
+                                     pk.get(sp + ".time_emb_proj.bias")) if has_temb else None
         r["tn1"], r["tc1"] = pk.norm(tp + ".norm1"), pk.tconv(tp + ".conv1")
         r["tn2"], r["tc2"] = pk.norm(tp + ".norm2"), pk.tconv(tp + ".conv2")
-        r["temb_tp"] = self.temb.add(pk.get(tp + ".time_emb_proj.weight"), pk.get(tp + ".time_emb_proj.bias"))
+        r["temb_tp"] = self.temb.add(pk.get(tp + ".time_emb_proj.weight"),
+                                     pk.get(tp + ".time_emb_proj.bias")) if has_temb else None
         a = torch.sigmoid(pk.get(pre + ".time_mixer.mix_factor").float()).item()
         r["alpha"] = (1.0 - a) if switch else a
         return r
@@ -292,7 +295,8 @@ class Net:
         ops.groupnorm(x, r["n1"][0], r["n1"][1], h, hw, r["eps"], True, stats, x2=x2)
         h1 = self.new(rows, cout)
         ops.gemm(ops.A_CONV3X3, h, r["c1"][0], h1, N=cout, n_img=n_img, H=H, W=W, C=cin, bias=r["c1"][1],
-                 rowbias=temb_all[:, r["temb_sp"]:r["temb_sp"] + cout], rows_per_group=T * hw)
+                 rowbias=None if r["temb_sp"] is None else temb_all[:, r["temb_sp"]:r["temb_sp"] + cout],
+                 rows_per_group=T * hw)
         ops.groupnorm(h1, r["n2"][0], r["n2"][1], h1n := self.new(rows, cout), hw, r["eps"], True, stats)
         if r["sc"] is not None:
             xs = self.new(rows, cout)
@@ -311,7 +315,8 @@ class Net:
         ops.groupnorm(hs, r["tn1"][0], r["tn1"][1], g, T * hw, r["teps"], True, stats)
         g1 = self.new(rows, cout)
         ops.gemm(ops.A_TEMPORAL3, g, r["tc1"][0], g1, N=cout, B=B, T=T, HW=hw, C=cout, bias=r["tc1"][1],
-                 rowbias=temb_all[:, r["temb_tp"]:r["temb_tp"] + cout], rows_per_group=T * hw)
+                 rowbias=None if r["temb_tp"] is None else temb_all[:, r["temb_tp"]:r["temb_tp"] + cout],
+                 rows_per_group=T * hw)
         ops.groupnorm(g1, r["tn2"][0], r["tn2"][1], g, T * hw, r["teps"], True, stats)
         out = self.new(rows, cout)
         # alpha*hs + (1-alpha)*(hs + conv) = hs + (1-alpha)*conv

@@ -31,7 +31,8 @@ def make_clip_vit_h(projection_dim=1024):
     return CLIPVisionModelWithProjection(cfg)
 
 
-def build_synthetic_pipeline(config=None, device="cuda", seed=0, tiny_encoders=False, vae_channels=None):
+def build_synthetic_pipeline(config=None, device="cuda", seed=0, tiny_encoders=False, vae_channels=None,
+                             native_vae=True):
     cfg_u, sd_u = synthetic.unet_state_dict(config, seed=seed)
     cfg_a, sd_a = synthetic.adapter_state_dict(config, seed=seed + 1)
     unet = UNetSpatioTemporalConditionControlNetModel.from_state_dict(sd_u, cfg_u, device=device)
@@ -40,13 +41,16 @@ def build_synthetic_pipeline(config=None, device="cuda", seed=0, tiny_encoders=F
     del sd_a
     torch.manual_seed(seed + 2)
     if tiny_encoders:
-        vae = AutoencoderKLTemporalDecoder(block_out_channels=vae_channels or (32, 32, 64, 64))
+        vae = AutoencoderKLTemporalDecoder(block_out_channels=vae_channels or (64, 64, 128, 128))
         clip = _TinyImageEncoder(cfg_u["cross_attention_dim"])
     else:
         vae = AutoencoderKLTemporalDecoder()
         clip = make_clip_vit_h(cfg_u["cross_attention_dim"])
     vae = vae.to(device=device, dtype=torch.float16).eval()
     clip = clip.to(device=device, dtype=torch.float16).eval()
+    if native_vae:
+        from mofa_video_b200.vae_engine import NativeTemporalDecoderVAE
+        vae = NativeTemporalDecoderVAE(vae, device=device)  # decode on the sm_100a kernels; encode stays PyTorch
     pipe = FlowControlNetPipeline(vae=vae, image_encoder=clip, unet=unet, controlnet=controlnet,
                                   scheduler=EulerDiscreteScheduler())
     return pipe.to(device)

@@ -20,7 +20,8 @@ EXPORTS = [
     "mofa_last_error", "mofa_version", "mofa_launch_count", "mofa_launch_count_reset", "mofa_gemm",
     "mofa_attn_spatial", "mofa_attn_temporal", "mofa_groupnorm", "mofa_layernorm", "mofa_axpy_bcast",
     "mofa_im2col3x3", "mofa_upsample2x", "mofa_nchw_to_nhwc", "mofa_nhwc_to_nchw", "mofa_linear_small",
-    "mofa_timestep_embedding", "mofa_softsplat_avg", "mofa_cfg_euler_step",
+    "mofa_timestep_embedding", "mofa_softsplat_avg", "mofa_cfg_euler_step", "mofa_softmax_rows",
+    "mofa_vae_time_conv_out",
 ]
 
 
@@ -72,6 +73,8 @@ def load():
     lib.mofa_timestep_embedding.argtypes = [vp, vp, i32, i32, vp]
     lib.mofa_softsplat_avg.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.mofa_cfg_euler_step.argtypes = [vp, vp, vp, vp, i32, i32, f32, f32, f32, f32, vp]
+    lib.mofa_softmax_rows.argtypes = [vp, i64, i32, i64, vp]
+    lib.mofa_vae_time_conv_out.argtypes = [vp, vp, vp, vp, vp, i32, i64, vp]
     _lib = lib
     return lib
 
@@ -146,20 +149,19 @@ def launch_count_reset():
 def pick_bn(n, geglu=False):
     """N tile for mofa_gemm: the widest tile (<=256) that wastes the least of N."""
     if geglu:
-        for bn in (256, 192, 128, 64):
+        for bn in (256, 128):
             if n % bn == 0:
                 return bn
         raise ValueError(f"GEGLU N={n} has no valid tile")
     if n <= 256:
         return max(16, (n + 15) // 16 * 16)
-    best, best_cost = None, None
-    for bn in range(256, 111, -16):
-        tiles = (n + bn - 1) // bn
-        cost = tiles * bn  # padded columns computed
-        # prefer less padding; tie -> larger tile
-        if best is None or cost < best_cost:
-            best, best_cost = bn, cost
-    return best
+    # multiples of 64 so the 64-column TMA-store chunks never straddle tiles; the last tile of a row may be
+    # narrower (its MMA N shrinks), so prefer the split whose remainder is not a sliver
+    for bn in (256, 192, 128):
+        rem = n % bn
+        if rem == 0 or rem >= 128:
+            return bn
+    return 256
 
 
 def gemm(mode, a, w, out, *, N, bn=None, act=ACT_NONE, a2=None, M=0, K=0, K1=0, lda=0, lda2=0, n_img=0, H=0, W=0,
@@ -302,3 +304,18 @@ def cfg_euler_step(noise, latents_h, image_latents, next_in, T, HW, g_min, g_max
     _check(load().mofa_cfg_euler_step(_p(noise), _p(latents_h), _p(image_latents), _p(next_in), T, HW, g_min, g_max,
                                       sigma, sigma_next, _stream()), "mofa_cfg_euler_step")
     return next_in
+
+
+def softmax_rows(x, L=None):
+    """In-place softmax over the rows of a fp16 matrix [rows, ld] (first L columns)."""
+    _chk_h(x)
+    rows, ld = x.shape
+    _check(load().mofa_softmax_rows(_p(x), rows, L if L is not None else ld, ld, _stream()), "mofa_softmax_rows")
+    return x
+
+
+def vae_time_conv_out(y, w, b, out_f32, out_u8, T, HW):
+    _chk_h(y)
+    assert w.dtype == torch.float32 and b.dtype == torch.float32
+    _check(load().mofa_vae_time_conv_out(_p(y), _p(w), _p(b), _p(out_f32), _p(out_u8), T, HW, _stream()),
+           "mofa_vae_time_conv_out")

@@ -315,11 +315,23 @@ class FlowControlNetPipeline:
         latents = lat_h.reshape(1, T, 4, h, w)
         ev["loop"].record()
 
-        if output_type != "latent":
-            frames = self.decode_latents(latents.to(self.vae.dtype), num_frames, decode_chunk_size)
-            frames = self._postprocess(frames, output_type)
-        else:
+        if output_type == "latent":
             frames = latents
+        elif output_type in ("pil", "uint8", "uint8_pt") and hasattr(self.vae, "decode_uint8"):
+            # native decoder: time_conv_out + (x/2+0.5).clamp*255 -> uint8 fused in the decoder's tail kernel
+            lat = latents.to(torch.float16).flatten(0, 1) * (1 / self.vae.config.scaling_factor)
+            u8 = torch.cat([self.vae.decode_uint8(lat[i:i + decode_chunk_size],
+                                                  num_frames=lat[i:i + decode_chunk_size].shape[0])
+                            for i in range(0, lat.shape[0], decode_chunk_size)], dim=0)  # [T, H, W, 3]
+            if output_type == "uint8_pt":
+                frames = [u8]
+            elif output_type == "uint8":
+                frames = [u8.cpu().numpy()]
+            else:
+                frames = [[PIL.Image.fromarray(f) for f in u8.cpu().numpy()]]
+        else:
+            frames = self.decode_latents(latents.to(self.vae.dtype), num_frames, decode_chunk_size)
+            frames = self._postprocess(frames, "uint8" if output_type == "uint8_pt" else output_type)
         ev["dec"].record()
         self._events = ev
         controlnet_flow_out = controlnet_flow

@@ -227,3 +227,19 @@ def cfg_euler_step(noise, latents_h, image_latents, next_in, T, HW, g_min, g_max
     o[:, :, :, :4] = scaled.permute(0, 2, 1)[None]
     o[:, :, :, 4:] = image_latents.view(2, 1, 4, HW).permute(0, 1, 3, 2)
     return next_in
+
+
+def softmax_rows(x, L=None):
+    L = L if L is not None else x.shape[1]
+    x[:, :L] = torch.softmax(x[:, :L].float(), dim=-1).half()
+    return x
+
+
+def vae_time_conv_out(y, w, b, out_f32, out_u8, T, HW):
+    yy = y.float().view(T, HW, 3).permute(2, 0, 1)[None, :, :, :, None]  # [1, 3, T, HW, 1]
+    o = F.conv3d(yy, w.view(3, 3, 3, 1, 1), b, padding=(1, 0, 0))[0, :, :, :, 0]  # [3, T, HW]
+    if out_f32 is not None:
+        out_f32.view(T, 3, HW).copy_(o.permute(1, 0, 2))
+    if out_u8 is not None:
+        u = ((o / 2 + 0.5).clamp(0, 1) * 255).round().to(torch.uint8)
+        out_u8.view(T, HW, 3).copy_(u.permute(1, 2, 0))

@@ -42,7 +42,11 @@ def close(a, b, atol, rtol, what=""):
     (256, 72, 320, 160),        # K not a multiple of 64 (conv_in im2col): TMA zero-fills the K tail
     (128 * 300, 256, 640, 160),  # 1200 tiles > 148 CTAs: persistent loop, phase wrap, TMEM double buffering
     (512, 2880, 4, 16),         # tiny N (conv_out): scalar tail stores
-    (700, 1280, 960, 240),      # bn = 240 (qkv at level 0)
+    (700, 1280, 960, 240),      # bn = 240: not a multiple of 64 -> direct-store epilogue
+    (1000, 320, 320, 192),      # TMA-store epilogue, narrower last N tile (192 + 128)
+    (700, 1280, 960, 256),      # 256,256,256,192
+    (300, 128, 640, 256),       # ragged M with TMA-store clipping, last tile 128
+    (128 * 150, 320, 960, None),  # auto tile, many tiles per CTA
 ])
 def test_gemm_linear_plain(M, K, N, bn):
     lib = L()
@@ -55,14 +59,15 @@ def test_gemm_linear_plain(M, K, N, bn):
     close(out, ref, 2e-2, 1e-2, f"linear {M}x{K}x{N}")
 
 
-def test_gemm_linear_epilogue():
+@pytest.mark.parametrize("bn", [160, 192, 256])
+def test_gemm_linear_epilogue(bn):
     lib = L()
     M, K, N = 900, 320, 320
     a, w = rnd(M, K, scale=0.5), rnd(N, K, scale=0.05)
     bias, rowbias = rnd(N), rnd(3, N)
     res1, res2 = rnd(M, N), rnd(M, N)
     kw = dict(bias=bias, rowbias=rowbias, rows_per_group=300, res1=res1, res2=res2, alpha=0.7, beta1=1.0, beta2=-0.5,
-              act=R.ACT_SILU, bn=160)
+              act=R.ACT_SILU, bn=bn)
     out = torch.zeros(M, N, dtype=torch.half, device=DEV)
     ref = torch.zeros_like(out)
     lib.linear(a, w, out, **kw)
