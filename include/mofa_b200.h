@@ -56,7 +56,7 @@ void mofa_launch_count_reset(void);
 
 typedef struct mofa_gemm_args {
   int32_t mode;
-  int32_t act;            /* 0 none, 1 silu, 2 geglu */
+  int32_t act;            /* 0 none, 1 silu, 2 geglu, 3 relu, 4 sigmoid */
   const void* a;          /* fp16 */
   const void* a2;         /* fp16, LINEAR split-K second source or NULL */
   const void* w;          /* fp16 [N, Ktot] row-major */
@@ -82,6 +82,7 @@ typedef struct mofa_gemm_args {
   int64_t ldr2;
   float alpha, beta1, beta2;
   int32_t max_ctas;       /* 0 = one per SM */
+  int32_t dilation;       /* CONV3X3 only: tap spacing (0/1 = dense; 2, 4 = CMP's dilated ResNet stages) */
 } mofa_gemm_args;
 
 int mofa_gemm(const mofa_gemm_args* args, mofa_stream_t stream);
@@ -181,6 +182,27 @@ int mofa_softmax_rows(void* x, int64_t rows, int32_t L, int64_t ld, mofa_stream_
  * [T,HW,3] = round(clamp(v/2+0.5,0,1)*255)  (VaeImageProcessor.postprocess, pipeline.py:57-69) */
 int mofa_vae_time_conv_out(const void* y, const float* w, const float* b, float* out_f32, void* out_u8, int32_t T,
                            int64_t HW, mofa_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CMP sparse-to-dense flow network helpers (reference:
+ * /root/reference/MOFA-Video-Traj/models/cmp/models/{backbone/resnet.py,modules/shallownet.py,modules/decoder.py},
+ * utils/visualize_utils.py:6-19).  Convolutions (BatchNorm folded at pack time, ReLU epilogue, dilation 2/4) run on
+ * mofa_gemm; these are the streaming pieces around them.  fp16 channels-last everywhere.
+ * ---------------------------------------------------------------------------------------------- */
+/* general im2col: out[(n,oy,ox), (ky,kx,c)] zero padded to Kpad columns (7x7/s2 stem, 5x5/s2, strided 1x1 / 3x3) */
+int mofa_im2col(const void* x, void* out, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t ksize,
+                int32_t stride, int32_t pad, int32_t dilation, int32_t Kpad, mofa_stream_t stream);
+/* nn.MaxPool2d (mode 0) / nn.AvgPool2d (mode 1) with kernel ksize, stride, padding */
+int mofa_pool2d(const void* x, void* out, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t ksize,
+                int32_t stride, int32_t pad, int32_t mode, mofa_stream_t stream);
+/* F.interpolate(bilinear, align_corners=True) to Ho x Wo, written into channels [c_off, c_off+C) of rows of ldo */
+int mofa_resize_bilinear_ac(const void* x, void* out, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t Ho,
+                            int32_t Wo, int32_t ldo, int32_t c_off, mofa_stream_t stream);
+/* Fuser.convert_flow: logits fp16 [rows, 2*nbins] -> expected flow fp16 [rows, 2] */
+int mofa_cmp_fuser(const void* logits, void* flow, int64_t rows, int32_t nbins, float fmax, mofa_stream_t stream);
+/* dst[r, c_off + c] = src[r % period_rows, c]: channel-concat assembly, broadcasting a per-image tensor over frames */
+int mofa_copy_cols(const void* src, void* dst, int64_t rows, int32_t C, int64_t period_rows, int32_t ldo,
+                   int32_t c_off, mofa_stream_t stream);
 
 #ifdef __cplusplus
 }

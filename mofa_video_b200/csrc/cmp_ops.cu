@@ -1,0 +1,214 @@
+// Streaming kernels used by the CMP sparse-to-dense flow network and by the
+// Keypoint adapter's occlusion nets: general im2col, max/avg pooling, align_corners bilinear resize, the
+// Fuser softmax-expectation head, and a broadcast copy into a channel slice (concat assembly).
+// All tensors fp16 channels-last [n, H, W, C] (rows = pixels).  HBM-bound, once per clip.
+#include "../../include/mofa_b200.h"
+#include "common.cuh"
+
+namespace mofa {
+
+// out[(n,oy,ox), (ky,kx,c)] = x[n, oy*s + ky*d - pad, ox*s + kx*d - pad, c]; zero outside; K padded to Kpad
+__global__ void __launch_bounds__(256)
+im2col_kernel(const __half* __restrict__ x, __half* __restrict__ out, int n_img, int H, int W, int C, int ks, int stride,
+              int pad, int dil, int Ho, int Wo, int Kpad) {
+    const long long total = static_cast<long long>(n_img) * Ho * Wo * Kpad;
+    const int K = ks * ks * C;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long row = idx / Kpad;
+        const int k = static_cast<int>(idx - row * Kpad);
+        __half v = __float2half(0.f);
+        if (k < K) {
+            const int tap = k / C;
+            const int c = k - tap * C;
+            const int ky = tap / ks, kx = tap - ky * ks;
+            const int ox = static_cast<int>(row % Wo);
+            const long long t = row / Wo;
+            const int oy = static_cast<int>(t % Ho);
+            const int n = static_cast<int>(t / Ho);
+            const int iy = oy * stride + ky * dil - pad;
+            const int ix = ox * stride + kx * dil - pad;
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[((static_cast<long long>(n) * H + iy) * W + ix) * C + c];
+        }
+        out[idx] = v;
+    }
+}
+
+// mode 0 = max (padding ignored, like nn.MaxPool2d), 1 = average over the full window (nn.AvgPool2d, pad = 0)
+__global__ void __launch_bounds__(256)
+pool2d_kernel(const __half* __restrict__ x, __half* __restrict__ out, int n_img, int H, int W, int C, int ks, int stride,
+              int pad, int Ho, int Wo, int mode) {
+    const long long total = static_cast<long long>(n_img) * Ho * Wo * C;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(idx % C);
+        long long t = idx / C;
+        const int ox = static_cast<int>(t % Wo);
+        t /= Wo;
+        const int oy = static_cast<int>(t % Ho);
+        const int n = static_cast<int>(t / Ho);
+        float acc = mode == 0 ? -INFINITY : 0.f;
+        for (int ky = 0; ky < ks; ++ky) {
+            const int iy = oy * stride + ky - pad;
+            if (iy < 0 || iy >= H) continue;
+            for (int kx = 0; kx < ks; ++kx) {
+                const int ix = ox * stride + kx - pad;
+                if (ix < 0 || ix >= W) continue;
+                const float v = __half2float(x[((static_cast<long long>(n) * H + iy) * W + ix) * C + c]);
+                acc = mode == 0 ? fmaxf(acc, v) : acc + v;
+            }
+        }
+        if (mode == 1) acc /= static_cast<float>(ks * ks);
+        out[idx] = __float2half_rn(acc);
+    }
+}
+
+// F.interpolate(mode="bilinear", align_corners=True); writes channels [c_off, c_off+C) of rows of width ldo
+__global__ void __launch_bounds__(256)
+resize_bilinear_ac_kernel(const __half* __restrict__ x, __half* __restrict__ out, int n_img, int H, int W, int C, int Ho,
+                          int Wo, int ldo, int c_off) {
+    const long long total = static_cast<long long>(n_img) * Ho * Wo * C;
+    const float sy = Ho > 1 ? static_cast<float>(H - 1) / static_cast<float>(Ho - 1) : 0.f;
+    const float sx = Wo > 1 ? static_cast<float>(W - 1) / static_cast<float>(Wo - 1) : 0.f;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(idx % C);
+        long long t = idx / C;
+        const int ox = static_cast<int>(t % Wo);
+        t /= Wo;
+        const int oy = static_cast<int>(t % Ho);
+        const int n = static_cast<int>(t / Ho);
+        const float fy = oy * sy, fx = ox * sx;
+        const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+        const int y1 = y0 + 1 < H ? y0 + 1 : H - 1, x1 = x0 + 1 < W ? x0 + 1 : W - 1;
+        const float wy = fy - y0, wx = fx - x0;
+        const __half* b = x + static_cast<long long>(n) * H * W * C + c;
+        const float v00 = __half2float(b[(static_cast<long long>(y0) * W + x0) * C]);
+        const float v01 = __half2float(b[(static_cast<long long>(y0) * W + x1) * C]);
+        const float v10 = __half2float(b[(static_cast<long long>(y1) * W + x0) * C]);
+        const float v11 = __half2float(b[(static_cast<long long>(y1) * W + x1) * C]);
+        const float v = (1.f - wy) * ((1.f - wx) * v00 + wx * v01) + wy * ((1.f - wx) * v10 + wx * v11);
+        out[((static_cast<long long>(n) * Ho + oy) * Wo + ox) * ldo + c_off + c] = __float2half_rn(v);
+    }
+}
+
+// Fuser.convert_flow: two softmax distributions over nbins bins -> expected value with bin centres
+// (k + 0.5) * 2*fmax/nbins - fmax.  One warp per pixel.  logits [rows, 2*nbins] fp16 -> flow [rows, 2] fp16.
+__global__ void __launch_bounds__(256)
+cmp_fuser_kernel(const __half* __restrict__ logits, __half* __restrict__ flow, long long rows, int nbins, float fmax) {
+    const int lane = threadIdx.x & 31;
+    const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float step = 2.f * fmax / static_cast<float>(nbins);
+    for (int comp = 0; comp < 2; ++comp) {
+        const __half* l = logits + row * 2 * nbins + comp * nbins;
+        float mx = -INFINITY;
+        for (int k = lane; k < nbins; k += 32) mx = fmaxf(mx, __half2float(l[k]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float se = 0.f, sv = 0.f;
+        for (int k = lane; k < nbins; k += 32) {
+            const float e = __expf(__half2float(l[k]) - mx);
+            se += e;
+            sv += e * (static_cast<float>(k) * step - fmax + 0.5f * step);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            se += __shfl_xor_sync(0xffffffffu, se, o);
+            sv += __shfl_xor_sync(0xffffffffu, sv, o);
+        }
+        if (lane == 0) flow[row * 2 + comp] = __float2half_rn(sv / se);
+    }
+}
+
+// dst[r, c_off + c] = src[r % period_rows, c]  (concat assembly; period_rows < rows broadcasts over frames)
+__global__ void __launch_bounds__(256)
+copy_cols_kernel(const __half* __restrict__ src, __half* __restrict__ dst, long long rows, int C, long long period_rows,
+                 int ldo, int c_off) {
+    const long long total = rows * C;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = idx / C;
+        const int c = static_cast<int>(idx - r * C);
+        dst[r * ldo + c_off + c] = src[(r % period_rows) * C + c];
+    }
+}
+
+static int grid_for2(long long work_items) {
+    long long g = (work_items + 255) / 256;
+    const long long cap = 148LL * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return static_cast<int>(g);
+}
+
+}  // namespace mofa
+
+using namespace mofa;
+
+extern "C" int mofa_im2col(const void* x, void* out, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t ksize,
+                           int32_t stride, int32_t pad, int32_t dilation, int32_t Kpad, mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!x || !out || n_img <= 0 || H <= 0 || W <= 0 || C <= 0 || ksize <= 0 || stride <= 0 || dilation <= 0 ||
+        Kpad < ksize * ksize * C) {
+        set_last_error("mofa_im2col: bad arguments");
+        return MOFA_ERR_ARG;
+    }
+    const int Ho = (H + 2 * pad - dilation * (ksize - 1) - 1) / stride + 1;
+    const int Wo = (W + 2 * pad - dilation * (ksize - 1) - 1) / stride + 1;
+    const long long total = static_cast<long long>(n_img) * Ho * Wo * Kpad;
+    im2col_kernel<<<grid_for2(total), 256, 0, stream>>>(static_cast<const __half*>(x), static_cast<__half*>(out), n_img,
+                                                       H, W, C, ksize, stride, pad, dilation, Ho, Wo, Kpad);
+    return check_launch("mofa_im2col");
+}
+
+extern "C" int mofa_pool2d(const void* x, void* out, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t ksize,
+                           int32_t stride, int32_t pad, int32_t mode, mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!x || !out || ksize <= 0 || stride <= 0 || (mode != 0 && mode != 1)) {
+        set_last_error("mofa_pool2d: bad arguments");
+        return MOFA_ERR_ARG;
+    }
+    const int Ho = (H + 2 * pad - ksize) / stride + 1, Wo = (W + 2 * pad - ksize) / stride + 1;
+    const long long total = static_cast<long long>(n_img) * Ho * Wo * C;
+    pool2d_kernel<<<grid_for2(total), 256, 0, stream>>>(static_cast<const __half*>(x), static_cast<__half*>(out), n_img,
+                                                       H, W, C, ksize, stride, pad, Ho, Wo, mode);
+    return check_launch("mofa_pool2d");
+}
+
+extern "C" int mofa_resize_bilinear_ac(const void* x, void* out, int32_t n_img, int32_t H, int32_t W, int32_t C,
+                                       int32_t Ho, int32_t Wo, int32_t ldo, int32_t c_off, mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!x || !out || Ho <= 0 || Wo <= 0 || ldo < c_off + C) {
+        set_last_error("mofa_resize_bilinear_ac: bad arguments");
+        return MOFA_ERR_ARG;
+    }
+    const long long total = static_cast<long long>(n_img) * Ho * Wo * C;
+    resize_bilinear_ac_kernel<<<grid_for2(total), 256, 0, stream>>>(
+        static_cast<const __half*>(x), static_cast<__half*>(out), n_img, H, W, C, Ho, Wo, ldo, c_off);
+    return check_launch("mofa_resize_bilinear_ac");
+}
+
+extern "C" int mofa_cmp_fuser(const void* logits, void* flow, int64_t rows, int32_t nbins, float fmax,
+                              mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!logits || !flow || rows <= 0 || nbins <= 0) {
+        set_last_error("mofa_cmp_fuser: bad arguments");
+        return MOFA_ERR_ARG;
+    }
+    cmp_fuser_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
+        static_cast<const __half*>(logits), static_cast<__half*>(flow), rows, nbins, fmax);
+    return check_launch("mofa_cmp_fuser");
+}
+
+extern "C" int mofa_copy_cols(const void* src, void* dst, int64_t rows, int32_t C, int64_t period_rows, int32_t ldo,
+                              int32_t c_off, mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!src || !dst || rows <= 0 || C <= 0 || period_rows <= 0 || ldo < c_off + C) {
+        set_last_error("mofa_copy_cols: bad arguments");
+        return MOFA_ERR_ARG;
+    }
+    copy_cols_kernel<<<grid_for2(rows * C), 256, 0, stream>>>(static_cast<const __half*>(src), static_cast<__half*>(dst),
+                                                             rows, C, period_rows, ldo, c_off);
+    return check_launch("mofa_copy_cols");
+}

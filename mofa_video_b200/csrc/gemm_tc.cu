@@ -47,7 +47,7 @@ struct GemmKernelParams {
     int stages;
     int tma_out;  // epilogue through staging + TMA store (needs 16-byte aligned rows, N_out >= 64)
     long long M;
-    int H, W, tiles_x, tiles_y, BH, BW;
+    int H, W, tiles_x, tiles_y, BH, BW, dil;
     int T, HW, tiles_p;
     __half* out;
     long long ldc;
@@ -96,6 +96,14 @@ union H8 {
     __half h[8];
 };
 
+// act: 0 none, 1 SiLU, (2 GEGLU handled separately), 3 ReLU, 4 sigmoid
+MOFA_DEVICE float apply_act(float v, int act) {
+    if (act == 1) return silu_f(v);
+    if (act == 3) return fmaxf(v, 0.f);
+    if (act == 4) return __fdividef(1.0f, 1.0f + __expf(-v));
+    return v;
+}
+
 // fallback for narrow / unaligned outputs (N = 3, 4, 16, ...): scalar or 16-byte stores straight from registers
 __device__ __noinline__ void epilogue_direct8(const GemmKernelParams& p, const float* vin, long long row,
                                               long long group, int n_bias, int n_out, bool act_silu) {
@@ -117,7 +125,7 @@ __device__ __noinline__ void epilogue_direct8(const GemmKernelParams& p, const f
             for (int j = 0; j < 8; ++j) v[j] += __half2float(b.h[j]);
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (act_silu ? silu_f(v[j]) : v[j]) * p.alpha;
+        for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], p.act) * p.alpha;
         if (p.res1) {
             H8 r;
             r.u = *reinterpret_cast<const uint4*>(p.res1 + row * p.ldr1 + n_out);
@@ -140,7 +148,7 @@ __device__ __noinline__ void epilogue_direct8(const GemmKernelParams& p, const f
             float x = v[j];
             if (p.bias) x += __half2float(p.bias[n_bias + j]);
             if (p.rowbias) x += __half2float(p.rowbias[group * p.ld_rowbias + n_bias + j]);
-            if (act_silu) x = silu_f(x);
+            x = apply_act(x, p.act);
             x *= p.alpha;
             if (p.res1) x += p.beta1 * __half2float(p.res1[row * p.ldr1 + n_out + j]);
             if (p.res2) x += p.beta2 * __half2float(p.res2[row * p.ldr2 + n_out + j]);
@@ -217,7 +225,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int tap = kb / p.kb_per_tap;
                     const int c0 = (kb - tap * p.kb_per_tap) * BK;
                     const int ky = tap / 3, kx = tap - ky * 3;
-                    tma_load_4d(&tmA, &full_bar[stage], sa, c0, tc.x0 + kx - 1, tc.y0 + ky - 1, tc.n_img);
+                    tma_load_4d(&tmA, &full_bar[stage], sa, c0, tc.x0 + (kx - 1) * p.dil, tc.y0 + (ky - 1) * p.dil,
+                                tc.n_img);
                 } else {
                     const int tap = kb / p.kb_per_tap;
                     const int c0 = (kb - tap * p.kb_per_tap) * BK;
@@ -356,7 +365,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                         } else {
                             tmem_ld_wait();
-                            const bool silu = p.act == 1;
+                            const bool silu = p.act == 1, relu = p.act == 3, sigm = p.act == 4;
 #pragma unroll
                             for (int g = 0; g < 4; ++g) {
                                 const int nb = nt * p.bn + col0 + g * 8;
@@ -381,6 +390,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 for (int j = 0; j < 8; ++j) {
                                     float v = __uint_as_float(acc[g * 8 + j]) + add[j];
                                     if (silu) v = silu_f(v);
+                                    if (relu) v = fmaxf(v, 0.f);
+                                    if (sigm) v = __fdividef(1.0f, 1.0f + __expf(-v));
                                     acc[g * 8 + j] = __float_as_uint(v * p.alpha);
                                 }
                             }
@@ -650,6 +661,7 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
         Ktot = 9LL * a->C;
         p.H = a->H;
         p.W = a->W;
+        p.dil = a->dilation > 0 ? a->dilation : 1;
         p.BW = floor_pow2(a->W < 32 ? a->W : 32);
         p.BH = BM / p.BW;
         p.tiles_x = (a->W + p.BW - 1) / p.BW;

@@ -14,14 +14,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmofa_b200.so")
 
 A_LINEAR, A_CONV3X3, A_TEMPORAL3 = 0, 1, 2
-ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3, 4
 
 EXPORTS = [
     "mofa_last_error", "mofa_version", "mofa_launch_count", "mofa_launch_count_reset", "mofa_gemm",
     "mofa_attn_spatial", "mofa_attn_temporal", "mofa_groupnorm", "mofa_layernorm", "mofa_axpy_bcast",
     "mofa_im2col3x3", "mofa_upsample2x", "mofa_nchw_to_nhwc", "mofa_nhwc_to_nchw", "mofa_linear_small",
     "mofa_timestep_embedding", "mofa_softsplat_avg", "mofa_cfg_euler_step", "mofa_softmax_rows",
-    "mofa_vae_time_conv_out",
+    "mofa_vae_time_conv_out", "mofa_im2col", "mofa_pool2d", "mofa_resize_bilinear_ac", "mofa_cmp_fuser",
+    "mofa_copy_cols",
 ]
 
 
@@ -39,7 +40,7 @@ class GemmArgs(ctypes.Structure):
         ("rows_per_group", ctypes.c_int64), ("rowbias_mod", ctypes.c_int64),
         ("res1", ctypes.c_void_p), ("ldr1", ctypes.c_int64), ("res2", ctypes.c_void_p), ("ldr2", ctypes.c_int64),
         ("alpha", ctypes.c_float), ("beta1", ctypes.c_float), ("beta2", ctypes.c_float),
-        ("max_ctas", ctypes.c_int32),
+        ("max_ctas", ctypes.c_int32), ("dilation", ctypes.c_int32),
     ]
 
 
@@ -75,6 +76,11 @@ def load():
     lib.mofa_cfg_euler_step.argtypes = [vp, vp, vp, vp, i32, i32, f32, f32, f32, f32, vp]
     lib.mofa_softmax_rows.argtypes = [vp, i64, i32, i64, vp]
     lib.mofa_vae_time_conv_out.argtypes = [vp, vp, vp, vp, vp, i32, i64, vp]
+    lib.mofa_im2col.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.mofa_pool2d.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.mofa_resize_bilinear_ac.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.mofa_cmp_fuser.argtypes = [vp, vp, i64, i32, f32, vp]
+    lib.mofa_copy_cols.argtypes = [vp, vp, i64, i32, i64, i32, i32, vp]
     _lib = lib
     return lib
 
@@ -166,7 +172,7 @@ def pick_bn(n, geglu=False):
 
 def gemm(mode, a, w, out, *, N, bn=None, act=ACT_NONE, a2=None, M=0, K=0, K1=0, lda=0, lda2=0, n_img=0, H=0, W=0,
          C=0, B=0, T=0, HW=0, ldc=None, bias=None, rowbias=None, rows_per_group=1, rowbias_mod=0, res1=None, res2=None,
-         alpha=1.0, beta1=1.0, beta2=1.0, max_ctas=0):
+         alpha=1.0, beta1=1.0, beta2=1.0, max_ctas=0, dilation=1):
     lib = load()
     _chk_h(a, a2, w, out, bias, res1, res2)
     if rowbias is not None:  # may be a column slice of a wider [groups, total] matrix
@@ -192,6 +198,7 @@ def gemm(mode, a, w, out, *, N, bn=None, act=ACT_NONE, a2=None, M=0, K=0, K1=0, 
     g.ldr2 = res2.shape[-1] if res2 is not None else 0
     g.alpha, g.beta1, g.beta2 = alpha, beta1, beta2
     g.max_ctas = max_ctas
+    g.dilation = dilation
     if _prof is not None:
         if mode == A_LINEAR:
             kind, work = "gemm_linear", 2.0 * M * N * K
@@ -319,3 +326,40 @@ def vae_time_conv_out(y, w, b, out_f32, out_u8, T, HW):
     assert w.dtype == torch.float32 and b.dtype == torch.float32
     _check(load().mofa_vae_time_conv_out(_p(y), _p(w), _p(b), _p(out_f32), _p(out_u8), T, HW, _stream()),
            "mofa_vae_time_conv_out")
+
+
+def conv_out_size(n, k, stride, pad, dil=1):
+    return (n + 2 * pad - dil * (k - 1) - 1) // stride + 1
+
+
+def im2col(x, out, n_img, H, W, C, ksize, stride, pad, dilation, Kpad):
+    _chk_h(x, out)
+    _check(load().mofa_im2col(_p(x), _p(out), n_img, H, W, C, ksize, stride, pad, dilation, Kpad, _stream()),
+           "mofa_im2col")
+    return out
+
+
+def pool2d(x, out, n_img, H, W, C, ksize, stride, pad, mode):
+    """mode 0 = max, 1 = average."""
+    _chk_h(x, out)
+    _check(load().mofa_pool2d(_p(x), _p(out), n_img, H, W, C, ksize, stride, pad, mode, _stream()), "mofa_pool2d")
+    return out
+
+
+def resize_bilinear_ac(x, out, n_img, H, W, C, Ho, Wo, ldo=None, c_off=0):
+    _chk_h(x, out)
+    _check(load().mofa_resize_bilinear_ac(_p(x), _p(out), n_img, H, W, C, Ho, Wo, ldo if ldo is not None else C,
+                                          c_off, _stream()), "mofa_resize_bilinear_ac")
+    return out
+
+
+def cmp_fuser(logits, flow, nbins=99, fmax=50.0):
+    _chk_h(logits, flow)
+    _check(load().mofa_cmp_fuser(_p(logits), _p(flow), logits.shape[0], nbins, fmax, _stream()), "mofa_cmp_fuser")
+    return flow
+
+
+def copy_cols(src, dst, rows, C, period_rows, ldo, c_off):
+    _chk_h(src, dst)
+    _check(load().mofa_copy_cols(_p(src), _p(dst), rows, C, period_rows, ldo, c_off, _stream()), "mofa_copy_cols")
+    return dst

@@ -171,8 +171,66 @@ def make_adapter_encoders():
     print("adapter encoder golden written:", [tuple(t.shape) for t in flow_out])
 
 
+def make_cmp():
+    """Run the reference's CMP module files (pure PyTorch) on CPU: ResNet-50-dilated + ShallowNet +
+    MotionDecoderSkipLayer + Fuser arithmetic, with weights from oracle.cmp.seeded_state_dict."""
+    import importlib.util
+    import torch.nn.functional as F
+    base = os.path.join(REF, "models", "cmp")
+
+    def load(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(base, rel))
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        return m
+
+    resnet = load("ref_cmp_resnet", "models/backbone/resnet.py")
+    shallow = load("ref_cmp_shallow", "models/modules/shallownet.py")
+    decoder = load("ref_cmp_decoder", "models/modules/decoder.py")
+    # modules/cmp.py looks its parts up through `models.cmp.models`: give it exactly those namespaces
+    pkg = _mod("models")
+    _mod("models.cmp")
+    parts = _mod("models.cmp.models.modules", shallownet8x=shallow.shallownet8x,
+                 MotionDecoderSkipLayer=decoder.MotionDecoderSkipLayer)
+    mm = _mod("models.cmp.models", backbone=resnet, modules=parts)
+    pkg.cmp = sys.modules["models.cmp"]
+    sys.modules["models.cmp"].models = mm
+    cmpmod = load("ref_cmp_module", "models/modules/cmp.py")
+    params = dict(img_enc_dim=256, sparse_enc_dim=16, output_dim=198, pretrained_image_encoder=False,
+                  decoder_combo=[1, 2, 4], skip_layer=True, image_encoder="resnet50", sparse_encoder="shallownet8x",
+                  flow_decoder="MotionDecoderSkipLayer")
+    torch.manual_seed(0)
+    ref = cmpmod.CMP(params).eval()
+    from oracle import cmp as ocmp
+    ref.load_state_dict(ocmp.seeded_state_dict(ref, seed=3))
+    g = torch.Generator().manual_seed(5)
+    image = torch.rand(2, 3, 128, 128, generator=g)
+    sparse = torch.zeros(2, 2, 128, 128)
+    mask = torch.zeros(2, 2, 128, 128)
+    idx = torch.randint(0, 128, (2, 12, 2), generator=g)
+    for b in range(2):
+        for (y, x) in idx[b].tolist():
+            sparse[b, :, y, x] = torch.randn(2, generator=g) * 10
+            mask[b, :, y, x] = 1
+    with torch.no_grad():
+        logits = ref((image * 2 - 1), torch.cat([sparse, mask], dim=1))
+        # Fuser.convert_flow arithmetic (visualize_utils.py:13-19; its mesh is built with .cuda() so the lines are
+        # restated on CPU here) + CMP_demo.run's align_corners upsample (FCN.py:56-60)
+        nb, fmax = 99, 50
+        step = 2 * fmax / float(nb)
+        mesh = torch.arange(nb).view(1, -1, 1, 1).float() * step - fmax + step / 2
+        px = F.softmax(logits[:, :nb], dim=1) * mesh
+        py = F.softmax(logits[:, nb:], dim=1) * mesh
+        flow = torch.cat([px.sum(1, keepdim=True), py.sum(1, keepdim=True)], dim=1)
+        flow_up = F.interpolate(flow, size=(128, 128), mode="bilinear", align_corners=True)
+    torch.save({"image": image, "sparse": sparse, "mask": mask, "logits_sub": logits[:, ::9, ::4, ::4].clone(),
+                "flow": flow_up, "seed": 3}, os.path.join(OUT, "cmp_small.pt"))
+    print("cmp golden written:", tuple(logits.shape), float(flow_up.abs().mean()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     make_scheduler()
     if "--all" in sys.argv:
         make_adapter_encoders()
+        make_cmp()

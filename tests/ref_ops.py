@@ -12,7 +12,7 @@ import torch
 import torch.nn.functional as F
 
 A_LINEAR, A_CONV3X3, A_TEMPORAL3 = 0, 1, 2
-ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3, 4
 
 
 def pick_bn(n, geglu=False):
@@ -32,6 +32,10 @@ def _epilogue(acc, *, N, bn, act, bias, rowbias, rows_per_group, rowbias_mod, re
         v = v + rowbias.float()[grp]
     if act == ACT_SILU:
         v = F.silu(v)
+    elif act == ACT_RELU:
+        v = F.relu(v)
+    elif act == ACT_SIGMOID:
+        v = torch.sigmoid(v)
     elif act == ACT_GEGLU:
         # weight rows packed per N tile as [bn/2 value | bn/2 gate]
         t = v.view(rows, N // bn, 2, bn // 2)
@@ -46,7 +50,7 @@ def _epilogue(acc, *, N, bn, act, bias, rowbias, rows_per_group, rowbias_mod, re
 
 def gemm(mode, a, w, out, *, N, bn=None, act=ACT_NONE, a2=None, M=0, K=0, K1=0, lda=0, lda2=0, n_img=0, H=0, W=0,
          C=0, B=0, T=0, HW=0, ldc=None, bias=None, rowbias=None, rows_per_group=1, rowbias_mod=0, res1=None, res2=None,
-         alpha=1.0, beta1=1.0, beta2=1.0, max_ctas=0):
+         alpha=1.0, beta1=1.0, beta2=1.0, max_ctas=0, dilation=1):
     if bn is None:
         bn = pick_bn(N, act == ACT_GEGLU)
     wf = w.float()
@@ -58,7 +62,7 @@ def gemm(mode, a, w, out, *, N, bn=None, act=ACT_NONE, a2=None, M=0, K=0, K1=0, 
     elif mode == A_CONV3X3:
         x = a.float().reshape(n_img, H, W, C).permute(0, 3, 1, 2)
         wk = wf.reshape(N, 3, 3, C).permute(0, 3, 1, 2)
-        acc = F.conv2d(x, wk, padding=1).permute(0, 2, 3, 1).reshape(n_img * H * W, N)
+        acc = F.conv2d(x, wk, padding=dilation, dilation=dilation).permute(0, 2, 3, 1).reshape(n_img * H * W, N)
     else:
         x = a.float().reshape(B, T, HW, C)
         xp = F.pad(x, (0, 0, 0, 0, 1, 1))
@@ -243,3 +247,50 @@ def vae_time_conv_out(y, w, b, out_f32, out_u8, T, HW):
     if out_u8 is not None:
         u = ((o / 2 + 0.5).clamp(0, 1) * 255).round().to(torch.uint8)
         out_u8.view(T, HW, 3).copy_(u.permute(1, 2, 0))
+
+
+def conv_out_size(n, k, stride, pad, dil=1):
+    return (n + 2 * pad - dil * (k - 1) - 1) // stride + 1
+
+
+def im2col(x, out, n_img, H, W, C, ksize, stride, pad, dilation, Kpad):
+    xi = x.float().reshape(n_img, H, W, C).permute(0, 3, 1, 2)
+    cols = F.unfold(xi, ksize, dilation=dilation, padding=pad, stride=stride)  # [n, C*k*k, L] ordered (c, ky, kx)
+    Lo = cols.shape[-1]
+    kk = ksize * ksize
+    cols = cols.view(n_img, C, kk, Lo).permute(0, 3, 2, 1).reshape(n_img * Lo, kk * C)
+    o = out.view(n_img * Lo, Kpad)
+    o.zero_()
+    o[:, : kk * C] = cols.half()
+    return out
+
+
+def pool2d(x, out, n_img, H, W, C, ksize, stride, pad, mode):
+    xi = x.float().reshape(n_img, H, W, C).permute(0, 3, 1, 2)
+    o = F.max_pool2d(xi, ksize, stride, pad) if mode == 0 else F.avg_pool2d(xi, ksize, stride, pad)
+    out.view(n_img, o.shape[2], o.shape[3], C).copy_(o.permute(0, 2, 3, 1).half())
+    return out
+
+
+def resize_bilinear_ac(x, out, n_img, H, W, C, Ho, Wo, ldo=None, c_off=0):
+    ldo = ldo if ldo is not None else C
+    xi = x.float().reshape(n_img, H, W, C).permute(0, 3, 1, 2)
+    o = F.interpolate(xi, size=(Ho, Wo), mode="bilinear", align_corners=True)
+    out.view(n_img, Ho, Wo, ldo)[..., c_off:c_off + C] = o.permute(0, 2, 3, 1).half()
+    return out
+
+
+def cmp_fuser(logits, flow, nbins=99, fmax=50.0):
+    l = logits.float()
+    step = 2 * fmax / nbins
+    mesh = torch.arange(nbins, device=l.device).float() * step - fmax + step / 2
+    fx = (torch.softmax(l[:, :nbins], -1) * mesh).sum(-1)
+    fy = (torch.softmax(l[:, nbins:], -1) * mesh).sum(-1)
+    flow.copy_(torch.stack([fx, fy], -1).half())
+    return flow
+
+
+def copy_cols(src, dst, rows, C, period_rows, ldo, c_off):
+    idx = torch.arange(rows, device=src.device) % period_rows
+    dst.view(rows, ldo)[:, c_off:c_off + C] = src.view(-1, C)[idx]
+    return dst
