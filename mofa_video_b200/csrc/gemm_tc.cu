@@ -138,6 +138,10 @@ __device__ __noinline__ void epilogue_direct8(const GemmKernelParams& p, const f
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] += p.beta2 * __half2float(r.h[j]);
         }
+        if (p.act == 5) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
         H8 o;
 #pragma unroll
         for (int j = 0; j < 4; ++j) o.h2[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
@@ -152,6 +156,7 @@ __device__ __noinline__ void epilogue_direct8(const GemmKernelParams& p, const f
             x *= p.alpha;
             if (p.res1) x += p.beta1 * __half2float(p.res1[row * p.ldr1 + n_out + j]);
             if (p.res2) x += p.beta2 * __half2float(p.res2[row * p.ldr2 + n_out + j]);
+            if (p.act == 5) x = fmaxf(x, 0.f);
             p.out[row * p.ldc + n_out + j] = __float2half_rn(x);
         }
     }
@@ -412,6 +417,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 if (do2) {
                                     x0 += p.beta2 * __half2float(a2.h[2 * j]);
                                     x1 += p.beta2 * __half2float(a2.h[2 * j + 1]);
+                                }
+                                if (p.act == 5) {  // ReLU after the residual add (ResNet bottleneck)
+                                    x0 = fmaxf(x0, 0.f);
+                                    x1 = fmaxf(x1, 0.f);
                                 }
                                 o.h2[j] = __floats2half2_rn(x0, x1);
                             }

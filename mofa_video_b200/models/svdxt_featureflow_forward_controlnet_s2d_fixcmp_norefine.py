@@ -78,3 +78,53 @@ class FlowControlNet(EngineModel):
                                     controlnet_flow=controlnet_flow, cmp_output=None)
 
     __call__ = forward
+
+
+class CMP_demo:
+    """Sparse-to-dense flow (CMP) with the reference's entry point (same file, :26-62): CMP_demo(configfn, load_iter),
+    .to(device), .requires_grad_(False), .run(image [B,3,H,W] in [0,1], sparse [B,2,H,W], mask [B,2,H,W]) -> flow
+    [B,2,H,W] in the caller's dtype.  Reads `<dir(configfn)>/checkpoints/ckpt_iter_<load_iter>.pth.tar` (key
+    'state_dict', names prefixed 'module.'); like the reference (models/cmp/utils/common_utils.py:115-116) a missing
+    checkpoint is a warning and the network keeps its random initialisation."""
+
+    def __init__(self, configfn=None, load_iter=None, state_dict=None, device="cuda", ops=None):
+        import os
+        import warnings
+
+        from mofa_video_b200 import lib as _lib
+        from mofa_video_b200.cmp_engine import CmpNet
+        nbins, fmax = 99, 50.0
+        if configfn is not None:
+            import yaml
+            with open(configfn) as f:
+                cfg = yaml.full_load(f)
+            mod = cfg["model"]["module"]
+            nbins, fmax = mod.get("nbins", 99), float(mod.get("fmax", 50))
+            if mod.get("image_encoder") != "resnet50" or mod.get("flow_decoder") != "MotionDecoderSkipLayer":
+                raise NotImplementedError("only the resnet50 + MotionDecoderSkipLayer CMP of MOFA-Video is implemented")
+            if state_dict is None:
+                fn = os.path.join(os.path.dirname(configfn), "checkpoints", f"ckpt_iter_{load_iter}.pth.tar")
+                if os.path.isfile(fn):
+                    state_dict = torch.load(fn, map_location="cpu")["state_dict"]
+                else:
+                    warnings.warn(f"=> no checkpoint found at '{fn}': CMP keeps a random initialisation")
+        if state_dict is None:
+            from mofa_video_b200 import synthetic
+            state_dict = synthetic.cmp_state_dict()
+        self._ops = ops if ops is not None else _lib
+        if ops is None:
+            _lib.load()
+        self.net = CmpNet(state_dict, self._ops, device, nbins=nbins, fmax=fmax)
+
+    def to(self, *a, **k):
+        return self
+
+    def requires_grad_(self, flag=False):
+        return self
+
+    def eval(self):
+        return self
+
+    def run(self, image, sparse, mask):
+        dtype = image.dtype
+        return self.net.forward(image, sparse, mask).to(dtype)

@@ -191,3 +191,59 @@ def adapter_state_dict(config=None, seed=1, dtype=torch.float16, zero_std=0.02):
         g.conv(f"flow_encoder.zeroconvs.{b}", boc[b], boc[b], k=1, std=zero_std)
         cin = boc[b]
     return cfg, g.sd
+
+
+def cmp_state_dict(seed=2, dtype=torch.float32, prefix="module."):
+    """Random-init CMP (ResNet-50-dilated + ShallowNet + MotionDecoderSkipLayer) in the reference checkpoint's
+    key layout (`module.` prefix of FixModule, models/cmp/models/modules/others.py:3-10).  BN gamma < 1 keeps the
+    50-layer residual stack fp16-finite with random weights."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(name, cout, cin, k, bias):
+        sd[name + ".weight"] = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)).to(dtype)
+        if bias:
+            sd[name + ".bias"] = torch.zeros(cout, dtype=dtype)
+
+    def bn(name, c):
+        sd[name + ".weight"] = (torch.rand(c, generator=g) * 0.4 + 0.3).to(dtype)
+        sd[name + ".bias"] = (torch.randn(c, generator=g) * 0.1).to(dtype)
+        sd[name + ".running_mean"] = (torch.randn(c, generator=g) * 0.1).to(dtype)
+        sd[name + ".running_var"] = (torch.rand(c, generator=g) + 0.5).to(dtype)
+        sd[name + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+
+    ie = "image_encoder."
+    conv(ie + "conv1", 64, 3, 7, False)
+    bn(ie + "bn1", 64)
+    inpl = 64
+    for li, (planes, blocks) in enumerate([(64, 3), (128, 4), (256, 6), (512, 3)]):
+        for bi in range(blocks):
+            pre = f"{ie}layer{li + 1}.{bi}."
+            conv(pre + "conv1", planes, inpl, 1, False)
+            bn(pre + "bn1", planes)
+            conv(pre + "conv2", planes, planes, 3, False)
+            bn(pre + "bn2", planes)
+            conv(pre + "conv3", planes * 4, planes, 1, False)
+            bn(pre + "bn3", planes * 4)
+            if bi == 0:
+                conv(pre + "downsample.0", planes * 4, inpl, 1, False)
+                bn(pre + "downsample.1", planes * 4)
+            inpl = planes * 4
+    conv(ie + "conv5", 256, 2048, 1, True)
+    fe = "flow_encoder.features."
+    conv(fe + "0", 16, 4, 5, True)
+    bn(fe + "1", 16)
+    conv(fe + "4", 16, 16, 3, True)
+    bn(fe + "5", 16)
+    fd = "flow_decoder."
+    for k in (1, 2, 4, 8):
+        off = 0 if k == 1 else 1
+        for j, cin in enumerate((272, 128, 128)):
+            conv(f"{fd}decoder{k}.{off + 3 * j}", 128, cin, 3, True)
+            bn(f"{fd}decoder{k}.{off + 3 * j + 1}", 128)
+    for name, cout, cin in (("fusion8", 256, 512), ("skipconv4", 128, 256), ("fusion4", 128, 384),
+                            ("skipconv2", 32, 64), ("fusion2", 64, 160)):
+        conv(f"{fd}{name}.0", cout, cin, 3, True)
+        bn(f"{fd}{name}.1", cout)
+    conv(fd + "head", 198, 64, 1, True)
+    return {prefix + k: v for k, v in sd.items()}

@@ -157,11 +157,13 @@ def seeded_state_dict(model, seed=0):
     for k, v in sorted(model.state_dict().items()):
         if k.endswith("num_batches_tracked"):
             sd[k] = v.clone()
-        elif k.endswith("running_var") or (k.endswith("weight") and v.ndim == 1):
+        elif k.endswith("running_var"):
             sd[k] = torch.rand(v.shape, generator=g) + 0.5
+        elif k.endswith("weight") and v.ndim == 1:          # BN gamma: < 1 so 50 residual layers stay fp16-finite
+            sd[k] = torch.rand(v.shape, generator=g) * 0.4 + 0.3
         elif v.ndim == 1:
             sd[k] = torch.randn(v.shape, generator=g) * 0.1
         else:
             fan_in = v[0].numel()
-            sd[k] = torch.randn(v.shape, generator=g) * (1.5 / fan_in ** 0.5)
+            sd[k] = torch.randn(v.shape, generator=g) * (1.0 / fan_in ** 0.5)
     return sd

@@ -45,6 +45,8 @@ def _epilogue(acc, *, N, bn, act, bias, rowbias, rows_per_group, rowbias_mod, re
         v = v + beta1 * res1.float().reshape(rows, -1)
     if res2 is not None:
         v = v + beta2 * res2.float().reshape(rows, -1)
+    if act == 5:  # ReLU after the residual add
+        v = F.relu(v)
     return v.half()
 
 
