@@ -83,6 +83,8 @@ typedef struct mofa_gemm_args {
   float alpha, beta1, beta2;
   int32_t max_ctas;       /* 0 = one per SM */
   int32_t dilation;       /* CONV3X3 only: tap spacing (0/1 = dense; 2, 4 = CMP's dilated ResNet stages) */
+  int32_t ksize;          /* CONV3X3 mode kernel size: 0/3 = 3x3, 5, 7 ("same" padding, K = ksize^2 * C;
+                             7x7 = ForegroundMatting heads of the Keypoint adapter) */
 } mofa_gemm_args;
 
 int mofa_gemm(const mofa_gemm_args* args, mofa_stream_t stream);

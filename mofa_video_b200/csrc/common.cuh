@@ -208,6 +208,18 @@ MOFA_DEVICE float fast_exp2(float x) {
     return y;
 }
 MOFA_DEVICE float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
-MOFA_DEVICE float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below fp16 output resolution): 2 MUFU + ~10 FMA-pipe
+// instructions instead of libm erff's two-branch polynomial -- the GEGLU epilogue is instruction-issue bound.
+MOFA_DEVICE float erf_fast(float x) {
+    const float ax = fabsf(x);
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float r = fmaf(-poly * t, __expf(-ax * ax), 1.0f);
+    return copysignf(r, x);
+}
+MOFA_DEVICE float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f)); }
 
 }  // namespace mofa

@@ -47,7 +47,7 @@ struct GemmKernelParams {
     int stages;
     int tma_out;  // epilogue through staging + TMA store (needs 16-byte aligned rows, N_out >= 64)
     long long M;
-    int H, W, tiles_x, tiles_y, BH, BW, dil;
+    int H, W, tiles_x, tiles_y, BH, BW, dil, ks;
     int T, HW, tiles_p;
     __half* out;
     long long ldc;
@@ -229,9 +229,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 } else if (p.mode == MOFA_A_CONV3X3) {
                     const int tap = kb / p.kb_per_tap;
                     const int c0 = (kb - tap * p.kb_per_tap) * BK;
-                    const int ky = tap / 3, kx = tap - ky * 3;
-                    tma_load_4d(&tmA, &full_bar[stage], sa, c0, tc.x0 + (kx - 1) * p.dil, tc.y0 + (ky - 1) * p.dil,
-                                tc.n_img);
+                    const int ky = tap / p.ks, kx = tap - ky * p.ks;
+                    const int half_k = p.ks >> 1;  // "same" padding: taps centred on the output pixel
+                    tma_load_4d(&tmA, &full_bar[stage], sa, c0, tc.x0 + (kx - half_k) * p.dil,
+                                tc.y0 + (ky - half_k) * p.dil, tc.n_img);
                 } else {
                     const int tap = kb / p.kb_per_tap;
                     const int c0 = (kb - tap * p.kb_per_tap) * BK;
@@ -333,97 +334,124 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int col0 = c * 64 + hlf * 32;           // column inside the tile's output
                         if (col0 >= out_cols) break;
                         const int n_out0 = nt * out_cols_tile + col0; // global output column
-                        // residual loads first (one batch in flight), consumed after the TMEM load
+                        // Every optional step below sits behind a WARP-UNIFORM branch around a whole 32-element
+                        // loop, so the common case issues only: residual loads, tcgen05.ld, bias add, convert, store.
+                        // (ncu on the first version: predicated-off activation/residual code still cost issue slots,
+                        //  ~15 instructions per output element.)
+                        const bool has1 = p.res1 != nullptr, has2 = p.res2 != nullptr;  // uniform
                         uint4 r1[4], r2[4];
-                        const bool do1 = p.res1 != nullptr && valid, do2 = p.res2 != nullptr && valid;
+                        if (has1) {  // one batch of loads in flight, consumed after the TMEM load
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            r1[g] = make_uint4(0, 0, 0, 0);
-                            r2[g] = make_uint4(0, 0, 0, 0);
-                            if (n_out0 + g * 8 < p.N_out) {
-                                if (do1) r1[g] = __ldg(reinterpret_cast<const uint4*>(p.res1 + row * p.ldr1 + n_out0) + g);
-                                if (do2) r2[g] = __ldg(reinterpret_cast<const uint4*>(p.res2 + row * p.ldr2 + n_out0) + g);
+                            for (int g = 0; g < 4; ++g) {
+                                r1[g] = make_uint4(0, 0, 0, 0);
+                                if (valid && n_out0 + g * 8 < p.N_out)
+                                    r1[g] = __ldg(reinterpret_cast<const uint4*>(p.res1 + row * p.ldr1 + n_out0) + g);
                             }
                         }
-                        uint32_t acc[32];
-                        tmem_ld_32x32(taddr + col0, acc);
-                        if constexpr (kGeglu) {
-                            uint32_t ag[32];
-                            tmem_ld_32x32(taddr + half_bn + col0, ag);
-                            tmem_ld_wait();
+                        if (has2) {
 #pragma unroll
                             for (int g = 0; g < 4; ++g) {
-                                const int nb = nt * p.bn + col0 + g * 8;
-                                H8 bv, bg;
-                                bv.u = make_uint4(0, 0, 0, 0);
-                                bg.u = make_uint4(0, 0, 0, 0);
-                                if (p.bias) {
-                                    bv.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nb));
-                                    bg.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nb + half_bn));
-                                }
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float val = __uint_as_float(acc[g * 8 + j]) + __half2float(bv.h[j]);
-                                    const float gate = __uint_as_float(ag[g * 8 + j]) + __half2float(bg.h[j]);
-                                    acc[g * 8 + j] = __float_as_uint(val * gelu_erf_f(gate) * p.alpha);
-                                }
+                                r2[g] = make_uint4(0, 0, 0, 0);
+                                if (valid && n_out0 + g * 8 < p.N_out)
+                                    r2[g] = __ldg(reinterpret_cast<const uint4*>(p.res2 + row * p.ldr2 + n_out0) + g);
                             }
-                        } else {
-                            tmem_ld_wait();
-                            const bool silu = p.act == 1, relu = p.act == 3, sigm = p.act == 4;
+                        }
+                        float v[32];
+                        {
+                            uint32_t acc[32];
+                            tmem_ld_32x32(taddr + col0, acc);
+                            if constexpr (kGeglu) {
+                                uint32_t ag[32];
+                                tmem_ld_32x32(taddr + half_bn + col0, ag);
+                                tmem_ld_wait();
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                const int nb = nt * p.bn + col0 + g * 8;
-                                float add[8];
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) add[j] = 0.f;
-                                if (nb < p.N_out) {
+                                for (int g = 0; g < 4; ++g) {
+                                    const int nb = nt * p.bn + col0 + g * 8;
+                                    H8 bv, bg;
+                                    bv.u = make_uint4(0, 0, 0, 0);
+                                    bg.u = make_uint4(0, 0, 0, 0);
                                     if (p.bias) {
-                                        H8 b;
-                                        b.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nb));
-#pragma unroll
-                                        for (int j = 0; j < 8; ++j) add[j] += __half2float(b.h[j]);
+                                        bv.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nb));
+                                        bg.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nb + half_bn));
                                     }
-                                    if (p.rowbias) {
-                                        H8 b;
-                                        b.u = __ldg(reinterpret_cast<const uint4*>(p.rowbias + group * p.ld_rowbias + nb));
 #pragma unroll
-                                        for (int j = 0; j < 8; ++j) add[j] += __half2float(b.h[j]);
+                                    for (int j = 0; j < 8; ++j) {
+                                        const float val = __uint_as_float(acc[g * 8 + j]) + __half2float(bv.h[j]);
+                                        const float gate = __uint_as_float(ag[g * 8 + j]) + __half2float(bg.h[j]);
+                                        v[g * 8 + j] = val * gelu_erf_f(gate);
                                     }
                                 }
+                            } else {
+                                tmem_ld_wait();
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    float v = __uint_as_float(acc[g * 8 + j]) + add[j];
-                                    if (silu) v = silu_f(v);
-                                    if (relu) v = fmaxf(v, 0.f);
-                                    if (sigm) v = __fdividef(1.0f, 1.0f + __expf(-v));
-                                    acc[g * 8 + j] = __float_as_uint(v * p.alpha);
+                                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+                                if (p.bias) {
+#pragma unroll
+                                    for (int g = 0; g < 4; ++g) {
+                                        const int nb = nt * p.bn + col0 + g * 8;
+                                        if (nb < p.N_out) {
+                                            H8 b;
+                                            b.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nb));
+#pragma unroll
+                                            for (int j = 0; j < 8; ++j) v[g * 8 + j] += __half2float(b.h[j]);
+                                        }
+                                    }
+                                }
+                                if (p.rowbias) {
+#pragma unroll
+                                    for (int g = 0; g < 4; ++g) {
+                                        const int nb = nt * p.bn + col0 + g * 8;
+                                        if (nb < p.N_out) {
+                                            H8 b;
+                                            b.u = __ldg(reinterpret_cast<const uint4*>(p.rowbias + group * p.ld_rowbias + nb));
+#pragma unroll
+                                            for (int j = 0; j < 8; ++j) v[g * 8 + j] += __half2float(b.h[j]);
+                                        }
+                                    }
+                                }
+                                if (p.act == 1) {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+                                } else if (p.act == 3) {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                                } else if (p.act == 4) {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) v[j] = __fdividef(1.0f, 1.0f + __expf(-v[j]));
                                 }
                             }
                         }
+                        if (p.alpha != 1.0f) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+                        }
+                        if (has1) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                H8 a;
+                                a.u = r1[g];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[g * 8 + j] = fmaf(p.beta1, __half2float(a.h[j]), v[g * 8 + j]);
+                            }
+                        }
+                        if (has2) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                H8 a;
+                                a.u = r2[g];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[g * 8 + j] = fmaf(p.beta2, __half2float(a.h[j]), v[g * 8 + j]);
+                            }
+                        }
+                        if (p.act == 5) {  // ReLU after the residual add (ResNet bottleneck)
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                        }
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
-                            H8 a1, a2, o;
-                            a1.u = r1[g];
-                            a2.u = r2[g];
+                            H8 o;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float x0 = __uint_as_float(acc[g * 8 + 2 * j]);
-                                float x1 = __uint_as_float(acc[g * 8 + 2 * j + 1]);
-                                if (do1) {
-                                    x0 += p.beta1 * __half2float(a1.h[2 * j]);
-                                    x1 += p.beta1 * __half2float(a1.h[2 * j + 1]);
-                                }
-                                if (do2) {
-                                    x0 += p.beta2 * __half2float(a2.h[2 * j]);
-                                    x1 += p.beta2 * __half2float(a2.h[2 * j + 1]);
-                                }
-                                if (p.act == 5) {  // ReLU after the residual add (ResNet bottleneck)
-                                    x0 = fmaxf(x0, 0.f);
-                                    x1 = fmaxf(x1, 0.f);
-                                }
-                                o.h2[j] = __floats2half2_rn(x0, x1);
-                            }
+                            for (int j = 0; j < 4; ++j) o.h2[j] = __floats2half2_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
                             const int ci = hlf * 4 + g;  // 16-byte chunk inside the 128-byte staging row
                             *reinterpret_cast<uint4*>(stg + lane * 128 + ((ci ^ (lane & 7)) << 4)) = o.u;
                         }
@@ -667,7 +695,12 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
             set_last_error("mofa_gemm conv3x3: needs C %% 64 == 0 (C=%d)", a->C);
             return MOFA_ERR_ARG;
         }
-        Ktot = 9LL * a->C;
+        p.ks = a->ksize > 0 ? a->ksize : 3;
+        if ((p.ks & 1) == 0 || p.ks > 7) {
+            set_last_error("mofa_gemm conv: odd kernel size <= 7 expected (ksize=%d)", p.ks);
+            return MOFA_ERR_ARG;
+        }
+        Ktot = static_cast<long long>(p.ks) * p.ks * a->C;
         p.H = a->H;
         p.W = a->W;
         p.dil = a->dilation > 0 ? a->dilation : 1;
@@ -677,7 +710,7 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
         p.tiles_y = (a->H + p.BH - 1) / p.BH;
         p.m_tiles = a->n_img * p.tiles_x * p.tiles_y;
         p.kb_per_tap = a->C / BK;
-        p.num_kb = 9 * p.kb_per_tap;
+        p.num_kb = p.ks * p.ks * p.kb_per_tap;
         p.kb_split = p.num_kb;
         uint64_t dims[4] = {(uint64_t)a->C, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
         uint64_t strides[3] = {(uint64_t)a->C * 2, (uint64_t)a->W * a->C * 2, (uint64_t)a->H * a->W * a->C * 2};

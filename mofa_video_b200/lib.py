@@ -40,7 +40,7 @@ class GemmArgs(ctypes.Structure):
         ("rows_per_group", ctypes.c_int64), ("rowbias_mod", ctypes.c_int64),
         ("res1", ctypes.c_void_p), ("ldr1", ctypes.c_int64), ("res2", ctypes.c_void_p), ("ldr2", ctypes.c_int64),
         ("alpha", ctypes.c_float), ("beta1", ctypes.c_float), ("beta2", ctypes.c_float),
-        ("max_ctas", ctypes.c_int32), ("dilation", ctypes.c_int32),
+        ("max_ctas", ctypes.c_int32), ("dilation", ctypes.c_int32), ("ksize", ctypes.c_int32),
     ]
 
 
@@ -172,7 +172,7 @@ def pick_bn(n, geglu=False):
 
 def gemm(mode, a, w, out, *, N, bn=None, act=ACT_NONE, a2=None, M=0, K=0, K1=0, lda=0, lda2=0, n_img=0, H=0, W=0,
          C=0, B=0, T=0, HW=0, ldc=None, bias=None, rowbias=None, rows_per_group=1, rowbias_mod=0, res1=None, res2=None,
-         alpha=1.0, beta1=1.0, beta2=1.0, max_ctas=0, dilation=1):
+         alpha=1.0, beta1=1.0, beta2=1.0, max_ctas=0, dilation=1, ksize=3):
     lib = load()
     _chk_h(a, a2, w, out, bias, res1, res2)
     if rowbias is not None:  # may be a column slice of a wider [groups, total] matrix
@@ -199,11 +199,12 @@ def gemm(mode, a, w, out, *, N, bn=None, act=ACT_NONE, a2=None, M=0, K=0, K1=0, 
     g.alpha, g.beta1, g.beta2 = alpha, beta1, beta2
     g.max_ctas = max_ctas
     g.dilation = dilation
+    g.ksize = ksize
     if _prof is not None:
         if mode == A_LINEAR:
             kind, work = "gemm_linear", 2.0 * M * N * K
         elif mode == A_CONV3X3:
-            kind, work = "gemm_conv3x3", 2.0 * n_img * H * W * N * 9 * C
+            kind, work = "gemm_conv3x3", 2.0 * n_img * H * W * N * ksize * ksize * C
         else:
             kind, work = "gemm_temporal3", 2.0 * B * T * HW * N * 3 * C
         with _Timed(kind, work):

@@ -52,7 +52,7 @@ def _epilogue(acc, *, N, bn, act, bias, rowbias, rows_per_group, rowbias_mod, re
 
 def gemm(mode, a, w, out, *, N, bn=None, act=ACT_NONE, a2=None, M=0, K=0, K1=0, lda=0, lda2=0, n_img=0, H=0, W=0,
          C=0, B=0, T=0, HW=0, ldc=None, bias=None, rowbias=None, rows_per_group=1, rowbias_mod=0, res1=None, res2=None,
-         alpha=1.0, beta1=1.0, beta2=1.0, max_ctas=0, dilation=1):
+         alpha=1.0, beta1=1.0, beta2=1.0, max_ctas=0, dilation=1, ksize=3):
     if bn is None:
         bn = pick_bn(N, act == ACT_GEGLU)
     wf = w.float()
@@ -63,8 +63,9 @@ def gemm(mode, a, w, out, *, N, bn=None, act=ACT_NONE, a2=None, M=0, K=0, K1=0, 
         acc = af @ wf[:, :K].t()
     elif mode == A_CONV3X3:
         x = a.float().reshape(n_img, H, W, C).permute(0, 3, 1, 2)
-        wk = wf.reshape(N, 3, 3, C).permute(0, 3, 1, 2)
-        acc = F.conv2d(x, wk, padding=dilation, dilation=dilation).permute(0, 2, 3, 1).reshape(n_img * H * W, N)
+        wk = wf.reshape(N, ksize, ksize, C).permute(0, 3, 1, 2)
+        acc = F.conv2d(x, wk, padding=dilation * (ksize // 2), dilation=dilation).permute(0, 2, 3, 1)
+        acc = acc.reshape(n_img * H * W, N)
     else:
         x = a.float().reshape(B, T, HW, C)
         xp = F.pad(x, (0, 0, 0, 0, 1, 1))
