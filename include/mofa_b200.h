@@ -206,6 +206,22 @@ int mofa_cmp_fuser(const void* logits, void* flow, int64_t rows, int32_t nbins, 
 int mofa_copy_cols(const void* src, void* dst, int64_t rows, int32_t C, int64_t period_rows, int32_t ldo,
                    int32_t c_off, mofa_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Keypoint / Hybrid adapter helpers
+ * ---------------------------------------------------------------------------------------------- */
+/* flow pyramid level written into a channel slice: out[(f,y,x), c_off + c] = fp16(flow[f,c,y*s,x*s] / s), s = Hf/hs
+ * (/root/reference/MOFA-Video-Keypoint/models/ldmk_ctrlnet.py:409-417; input of the occlusion hourglass :299-301) */
+int mofa_flow_pyramid(const void* flow, void* out, int32_t F, int32_t hs, int32_t ws, int32_t Hf, int32_t Wf,
+                      int32_t ldo, int32_t c_off, mofa_stream_t stream);
+/* out = a * m + b * (1 - m), m = mask[row % period_rows] fp16: ForegroundMatting blend
+ * (/root/reference/MOFA-Video-Keypoint/models/occlusion/hourglass.py:278) and the Hybrid residual blend
+ * (/root/reference/MOFA-Video-Hybrid/pipeline/pipeline.py:479-488) */
+int mofa_mask_blend(const void* a, const void* b, const void* mask, void* out, int64_t rows, int32_t C,
+                    int64_t period_rows, mofa_stream_t stream);
+/* nearest F.interpolate(scale_factor = 1/s) on channels-last data (landmark embedding pyramid, ldmk_ctrlnet.py:403-407) */
+int mofa_downsample_nearest(const void* x, void* out, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t s,
+                            mofa_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

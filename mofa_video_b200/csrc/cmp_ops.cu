@@ -212,3 +212,106 @@ extern "C" int mofa_copy_cols(const void* src, void* dst, int64_t rows, int32_t 
                                                              rows, C, period_rows, ldo, c_off);
     return check_launch("mofa_copy_cols");
 }
+
+// ---------------------------------------------------------------------------------------------
+// Keypoint / Hybrid adapter helpers
+// ---------------------------------------------------------------------------------------------
+namespace mofa {
+
+// adapter flow pyramid materialised (K/models/ldmk_ctrlnet.py:409-417): out[(f,y,x), c_off + c] = half(flow[f,c,y*s,x*s] / s)
+__global__ void __launch_bounds__(256)
+flow_pyramid_kernel(const __half* __restrict__ flow, __half* __restrict__ out, int F, int hs, int ws, int Hf, int Wf,
+                    int s, int ldo, int c_off) {
+    const long long total = static_cast<long long>(F) * hs * ws * 2;
+    const float inv = 1.0f / static_cast<float>(s);
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(idx & 1);
+        long long t = idx >> 1;
+        const int x = static_cast<int>(t % ws);
+        t /= ws;
+        const int y = static_cast<int>(t % hs);
+        const int f = static_cast<int>(t / hs);
+        const float v = __half2float(flow[((static_cast<long long>(f) * 2 + c) * Hf + y * s) * Wf + x * s]) * inv;
+        out[((static_cast<long long>(f) * hs + y) * ws + x) * ldo + c_off + c] = __float2half_rn(v);
+    }
+}
+
+// out[r, c] = a[r, c] * m + b[r, c] * (1 - m),  m = mask[r % period_rows]   (matting blend / hybrid residual blend)
+__global__ void __launch_bounds__(256)
+mask_blend_kernel(const __half* __restrict__ a, const __half* __restrict__ b, const __half* __restrict__ mask,
+                  __half* __restrict__ out, long long rows, int C, long long period_rows) {
+    const int cv = C >> 3;
+    const long long total = rows * cv;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = idx / cv;
+        const float m = __half2float(mask[r % period_rows]);
+        union { uint4 u; __half h[8]; } va, vb, vo;
+        va.u = __ldg(reinterpret_cast<const uint4*>(a) + idx);
+        vb.u = __ldg(reinterpret_cast<const uint4*>(b) + idx);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            vo.h[j] = __float2half_rn(__half2float(va.h[j]) * m + __half2float(vb.h[j]) * (1.0f - m));
+        reinterpret_cast<uint4*>(out)[idx] = vo.u;
+    }
+}
+
+// F.interpolate(scale_factor=1/s) nearest on channels-last data: out[n,y,x,:] = x[n, y*s, x*s, :]
+__global__ void __launch_bounds__(256)
+downsample_nearest_kernel(const __half* __restrict__ x, __half* __restrict__ out, int n_img, int H, int W, int C, int s) {
+    const int Ho = H / s, Wo = W / s, cv = C >> 3;
+    const long long total = static_cast<long long>(n_img) * Ho * Wo * cv;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c8 = static_cast<int>(idx % cv);
+        long long t = idx / cv;
+        const int ox = static_cast<int>(t % Wo);
+        t /= Wo;
+        const int oy = static_cast<int>(t % Ho);
+        const int n = static_cast<int>(t / Ho);
+        reinterpret_cast<uint4*>(out)[idx] = __ldg(
+            reinterpret_cast<const uint4*>(x + ((static_cast<long long>(n) * H + oy * s) * W + ox * s) * C) + c8);
+    }
+}
+
+}  // namespace mofa
+
+extern "C" int mofa_flow_pyramid(const void* flow, void* out, int32_t F, int32_t hs, int32_t ws, int32_t Hf,
+                                 int32_t Wf, int32_t ldo, int32_t c_off, mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!flow || !out || F <= 0 || hs <= 0 || ws <= 0 || Hf % hs != 0 || Wf % ws != 0 || Hf / hs != Wf / ws ||
+        ldo < c_off + 2) {
+        set_last_error("mofa_flow_pyramid: bad arguments");
+        return MOFA_ERR_ARG;
+    }
+    flow_pyramid_kernel<<<grid_for2(static_cast<long long>(F) * hs * ws * 2), 256, 0, stream>>>(
+        static_cast<const __half*>(flow), static_cast<__half*>(out), F, hs, ws, Hf, Wf, Hf / hs, ldo, c_off);
+    return check_launch("mofa_flow_pyramid");
+}
+
+extern "C" int mofa_mask_blend(const void* a, const void* b, const void* mask, void* out, int64_t rows, int32_t C,
+                               int64_t period_rows, mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!a || !b || !mask || !out || rows <= 0 || C <= 0 || (C % 8) != 0 || period_rows <= 0) {
+        set_last_error("mofa_mask_blend: bad arguments (C must be a multiple of 8)");
+        return MOFA_ERR_ARG;
+    }
+    mask_blend_kernel<<<grid_for2(rows * (C / 8)), 256, 0, stream>>>(
+        static_cast<const __half*>(a), static_cast<const __half*>(b), static_cast<const __half*>(mask),
+        static_cast<__half*>(out), rows, C, period_rows);
+    return check_launch("mofa_mask_blend");
+}
+
+extern "C" int mofa_downsample_nearest(const void* x, void* out, int32_t n_img, int32_t H, int32_t W, int32_t C,
+                                       int32_t s, mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!x || !out || s <= 0 || H % s != 0 || W % s != 0 || (C % 8) != 0) {
+        set_last_error("mofa_downsample_nearest: bad arguments");
+        return MOFA_ERR_ARG;
+    }
+    const long long total = static_cast<long long>(n_img) * (H / s) * (W / s) * (C / 8);
+    downsample_nearest_kernel<<<grid_for2(total), 256, 0, stream>>>(static_cast<const __half*>(x),
+                                                                   static_cast<__half*>(out), n_img, H, W, C, s);
+    return check_launch("mofa_downsample_nearest");
+}

@@ -22,7 +22,7 @@ EXPORTS = [
     "mofa_im2col3x3", "mofa_upsample2x", "mofa_nchw_to_nhwc", "mofa_nhwc_to_nchw", "mofa_linear_small",
     "mofa_timestep_embedding", "mofa_softsplat_avg", "mofa_cfg_euler_step", "mofa_softmax_rows",
     "mofa_vae_time_conv_out", "mofa_im2col", "mofa_pool2d", "mofa_resize_bilinear_ac", "mofa_cmp_fuser",
-    "mofa_copy_cols",
+    "mofa_copy_cols", "mofa_flow_pyramid", "mofa_mask_blend", "mofa_downsample_nearest",
 ]
 
 
@@ -81,6 +81,9 @@ def load():
     lib.mofa_resize_bilinear_ac.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.mofa_cmp_fuser.argtypes = [vp, vp, i64, i32, f32, vp]
     lib.mofa_copy_cols.argtypes = [vp, vp, i64, i32, i64, i32, i32, vp]
+    lib.mofa_flow_pyramid.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.mofa_mask_blend.argtypes = [vp, vp, vp, vp, i64, i32, i64, vp]
+    lib.mofa_downsample_nearest.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     _lib = lib
     return lib
 
@@ -172,14 +175,16 @@ def pick_bn(n, geglu=False):
 
 def gemm(mode, a, w, out, *, N, bn=None, act=ACT_NONE, a2=None, M=0, K=0, K1=0, lda=0, lda2=0, n_img=0, H=0, W=0,
          C=0, B=0, T=0, HW=0, ldc=None, bias=None, rowbias=None, rows_per_group=1, rowbias_mod=0, res1=None, res2=None,
-         alpha=1.0, beta1=1.0, beta2=1.0, max_ctas=0, dilation=1, ksize=3):
+         alpha=1.0, beta1=1.0, beta2=1.0, max_ctas=0, dilation=1, ksize=3, c_off=0):
+    """c_off: first output column inside rows of width ldc (in-place channel concat; multiple of 8)."""
     lib = load()
     _chk_h(a, a2, w, out, bias, res1, res2)
     if rowbias is not None:  # may be a column slice of a wider [groups, total] matrix
         assert rowbias.is_cuda and rowbias.dtype == torch.float16 and rowbias.stride(-1) == 1
     g = GemmArgs()
     g.mode, g.act = mode, act
-    g.a, g.a2, g.w, g.out = a.data_ptr(), (a2.data_ptr() if a2 is not None else None), w.data_ptr(), out.data_ptr()
+    g.a, g.a2, g.w = a.data_ptr(), (a2.data_ptr() if a2 is not None else None), w.data_ptr()
+    g.out = out.data_ptr() + 2 * c_off
     n_out = N // 2 if act == ACT_GEGLU else N
     g.ldc = ldc if ldc is not None else n_out
     g.M, g.K, g.K1, g.lda, g.lda2 = M, K, K1, lda, lda2
@@ -364,3 +369,23 @@ def copy_cols(src, dst, rows, C, period_rows, ldo, c_off):
     _chk_h(src, dst)
     _check(load().mofa_copy_cols(_p(src), _p(dst), rows, C, period_rows, ldo, c_off, _stream()), "mofa_copy_cols")
     return dst
+
+
+def flow_pyramid(flow, out, F, hs, ws, Hf, Wf, ldo, c_off):
+    _chk_h(flow, out)
+    _check(load().mofa_flow_pyramid(_p(flow), _p(out), F, hs, ws, Hf, Wf, ldo, c_off, _stream()), "mofa_flow_pyramid")
+    return out
+
+
+def mask_blend(a, b, mask, out, period_rows=None):
+    _chk_h(a, b, mask, out)
+    rows, C = a.shape
+    _check(load().mofa_mask_blend(_p(a), _p(b), _p(mask), _p(out), rows, C,
+                                  period_rows if period_rows is not None else rows, _stream()), "mofa_mask_blend")
+    return out
+
+
+def downsample_nearest(x, out, n_img, H, W, C, s):
+    _chk_h(x, out)
+    _check(load().mofa_downsample_nearest(_p(x), _p(out), n_img, H, W, C, s, _stream()), "mofa_downsample_nearest")
+    return out

@@ -228,9 +228,30 @@ def make_cmp():
     print("cmp golden written:", tuple(logits.shape), float(flow_up.abs().mean()))
 
 
+def make_hourglass():
+    """ForegroundMatting of the Keypoint adapter, executed from the reference file (pure PyTorch)."""
+    import importlib.util
+    fn = "/root/reference/MOFA-Video-Keypoint/models/occlusion/hourglass.py"
+    spec = importlib.util.spec_from_file_location("ref_hourglass", fn)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    from oracle import cmp as ocmp
+    fm = m.ForegroundMatting(64).eval()
+    fm.load_state_dict(ocmp.seeded_state_dict(fm, seed=7))   # weights regenerated from the seed by the test
+    g = torch.Generator().manual_seed(2)
+    ref_img, flow, warped = (torch.randn(2, 64, 12, 10, generator=g), torch.randn(2, 2, 12, 10, generator=g),
+                             torch.randn(2, 64, 12, 10, generator=g))
+    with torch.no_grad():
+        out, mask = fm(ref_img, flow, warped)
+    torch.save({"seed": 7, "ref": ref_img, "flow": flow, "warped": warped, "out": out, "mask": mask},
+               os.path.join(OUT, "hourglass_small.pt"))
+    print("hourglass golden written:", tuple(out.shape), tuple(mask.shape))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     make_scheduler()
     if "--all" in sys.argv:
         make_adapter_encoders()
         make_cmp()
+        make_hourglass()

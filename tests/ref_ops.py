@@ -52,7 +52,7 @@ def _epilogue(acc, *, N, bn, act, bias, rowbias, rows_per_group, rowbias_mod, re
 
 def gemm(mode, a, w, out, *, N, bn=None, act=ACT_NONE, a2=None, M=0, K=0, K1=0, lda=0, lda2=0, n_img=0, H=0, W=0,
          C=0, B=0, T=0, HW=0, ldc=None, bias=None, rowbias=None, rows_per_group=1, rowbias_mod=0, res1=None, res2=None,
-         alpha=1.0, beta1=1.0, beta2=1.0, max_ctas=0, dilation=1, ksize=3):
+         alpha=1.0, beta1=1.0, beta2=1.0, max_ctas=0, dilation=1, ksize=3, c_off=0):
     if bn is None:
         bn = pick_bn(N, act == ACT_GEGLU)
     wf = w.float()
@@ -75,7 +75,7 @@ def gemm(mode, a, w, out, *, N, bn=None, act=ACT_NONE, a2=None, M=0, K=0, K1=0, 
                     res1=res1, res2=res2, alpha=alpha, beta1=beta1, beta2=beta2)
     n_out = res.shape[1]
     ld = ldc if ldc is not None else n_out
-    out.view(-1, ld)[: res.shape[0], :n_out] = res
+    out.view(-1, ld)[: res.shape[0], c_off:c_off + n_out] = res
     return out
 
 
@@ -297,3 +297,23 @@ def copy_cols(src, dst, rows, C, period_rows, ldo, c_off):
     idx = torch.arange(rows, device=src.device) % period_rows
     dst.view(rows, ldo)[:, c_off:c_off + C] = src.view(-1, C)[idx]
     return dst
+
+
+def flow_pyramid(flow, out, F_, hs, ws, Hf, Wf, ldo, c_off):
+    s = Hf // hs
+    fl = (flow.view(F_, 2, Hf, Wf)[:, :, ::s, ::s].float() / s).half()  # [F,2,hs,ws]
+    out.view(F_, hs, ws, ldo)[..., c_off:c_off + 2] = fl.permute(0, 2, 3, 1)
+    return out
+
+
+def mask_blend(a, b, mask, out, period_rows=None):
+    rows = a.shape[0]
+    period_rows = period_rows if period_rows is not None else rows
+    m = mask.float().view(-1)[torch.arange(rows, device=a.device) % period_rows][:, None]
+    out.copy_((a.float() * m + b.float() * (1 - m)).half())
+    return out
+
+
+def downsample_nearest(x, out, n_img, H, W, C, s):
+    out.view(n_img, H // s, W // s, C).copy_(x.view(n_img, H, W, C)[:, ::s, ::s])
+    return out
