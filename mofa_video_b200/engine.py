@@ -182,8 +182,10 @@ class Net:
                 convs += [(f"{ce}.blocks.{2 * k}", 1), (f"{ce}.blocks.{2 * k + 1}", 2)]
             convs.append((ce + ".conv_out", 1))
             p["cond_convs"] = [self._pack_im2col_conv(pk, name, s) for name, s in convs]
+            # the Keypoint variant's first-frame encoder has no zero-convs (K/models/ldmk_ctrlnet.py:144-161)
             p["flow_enc"] = [(self._pack_im2col_conv(pk, f"flow_encoder.encoders.{k}.conv_in", 2),
-                              pk.conv1(f"flow_encoder.zeroconvs.{k}")) for k in range(3)]
+                              pk.conv1(f"flow_encoder.zeroconvs.{k}")
+                              if f"flow_encoder.zeroconvs.{k}.weight" in state_dict else None) for k in range(3)]
         self.temb.finish(pk)
         self.p = p
 
@@ -490,11 +492,15 @@ class Net:
             x, H, W = self.conv_im2col(c, x, 1, H, W, act=0 if last else ops.ACT_SILU)
         feats = [(x, H, W)]
         f = x
-        for (enc, (zw, zb)) in self.p["flow_enc"]:
+        for (enc, zc) in self.p["flow_enc"]:
             f, H, W = self.conv_im2col(enc, f, 1, H, W, act=ops.ACT_SILU)
-            z = self.new(H * W, zw.shape[0])
-            ops.linear(f, zw, z, bias=zb)
+            if zc is not None:
+                z = self.new(H * W, zc[0].shape[0])
+                ops.linear(f, zc[0], z, bias=zc[1])
+            else:
+                z = f
             feats.append((z, H, W))
+        self.cond_feats = feats
         warped = []
         Fn = T - 1
         for (ft, hs, ws) in feats:
@@ -508,6 +514,15 @@ class Net:
         self.warped = warped
         return warped
 
+    def _add_landmarks(self, x, H):
+        """x += landmark embedding at this resolution (per frame, broadcast over the CFG batch); no-op for Traj."""
+        ld = getattr(self, "ldmk", None)
+        if not ld:
+            return x
+        out = self.new(*x.shape)
+        self.ops.axpy_bcast(x, ld[H], out, 1.0)
+        return out
+
     def adapter_forward(self, x_in, t_value, H, W, conditioning_scale=1.0):
         """Trunk (FCN.py:284-376) on the hoisted warped features. Returns (12 residuals, mid residual)."""
         assert self.kind == "adapter"
@@ -519,6 +534,7 @@ class Net:
         wp = self.warped
         x = self.new(*x0.shape)
         ops.axpy_bcast(x0, wp[0], x, 1.0)          # FCN.py:328
+        x = self._add_landmarks(x, H)              # Keypoint variant only (ldmk_ctrlnet.py:474)
         skips = [(x, hw, H, W)]
         count, length = 1, len(wp)
         for blk in self.p["down"]:
@@ -526,6 +542,8 @@ class Net:
             xa = self.new(*x.shape)
             ops.axpy_bcast(x, wp[min(count, length - 1)], xa, 1.0)   # FCN.py:348 (Q2: skips recorded before the add)
             x = xa
+            if x.shape[1] == self.boc[0]:
+                x = self._add_landmarks(x, H)      # Q14: only where the trunk has boc[0] channels (:501-504)
             count += 1
         xa = self.new(*x.shape)
         ops.axpy_bcast(x, wp[-1], xa, 1.0)         # FCN.py:354

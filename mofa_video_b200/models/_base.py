@@ -55,10 +55,13 @@ class EngineModel:
         self._ops = ops if ops is not None else _lib
         if ops is None:
             _lib.load()  # fail loudly right here when the CUDA library is missing
-        self.net = engine.Net(self.kind, state_dict, cfg, self._ops, self._device)
+        self.net = self._make_net(state_dict, cfg)
         self.add_embedding = SimpleNamespace(linear_1=SimpleNamespace(
             in_features=int(state_dict["add_embedding.linear_1.weight"].shape[1])))
         self._clip_key = None
+
+    def _make_net(self, state_dict, cfg):
+        return engine.Net(self.kind, state_dict, cfg, self._ops, self._device)
 
     # -- construction --------------------------------------------------------------------------
     @classmethod

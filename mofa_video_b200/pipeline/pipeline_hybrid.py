@@ -1,0 +1,139 @@
+"""Hybrid pipeline (landmark adapter inside a face mask, trajectory adapter outside) with the reference's entry point
+(/root/reference/MOFA-Video-Hybrid/pipeline/pipeline.py:92-116 constructor, :291-322 __call__, :432-507 loop).
+
+Both adapters' conditioning branches are loop-invariant and run once per clip; per denoise step the two trunks run on
+the same fused CFG input, their 12 + 1 residuals are blended with the nearest-resized mask (one elementwise kernel per
+level, mask row period = h*w so it broadcasts over the 2*T frames; Q13: the mask is not CFG-duplicated), and the UNet +
+fused CFG/Euler kernel finish the step."""
+from typing import Callable, Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+
+from mofa_video_b200 import lib as _lib
+from mofa_video_b200.pipeline.pipeline import (FlowControlNetPipeline as _TrajPipeline, FlowControlNetPipelineOutput,
+                                               _get_add_time_ids, _to_unit_tensor)
+
+
+def level_masks(mask, h, w, n_levels, T, device):
+    """{rows of a residual: fp16 mask [h_l*w_l]} -- F.interpolate(mask, (h_l, w_l), mode='nearest') per level (:479-485)."""
+    m4 = mask.to(device=device, dtype=torch.float32).reshape(1, 1, *mask.shape[-2:])
+    out, hh, ww = {}, h, w
+    for _ in range(n_levels):
+        out[2 * T * hh * ww] = F.interpolate(m4, (hh, ww), mode="nearest").reshape(hh * ww).to(torch.float16).contiguous()
+        hh, ww = (hh - 1) // 2 + 1, (ww - 1) // 2 + 1
+    return out
+
+
+def denoise_hybrid(ops, unet_net, face_net, drag_net, by_rows, lat, il, sig, tsteps, h, w, g_min, g_max, scale_ldmk,
+                   scale_traj, on_step=None):
+    """The loop of H/pipeline/pipeline.py:432-507 on channels-last fp16 buffers; lat fp16 [T, 4, hw] is updated in
+    place; both adapters' conditioning branches must already be prepared."""
+    T, _, hw = lat.shape
+    next_in = torch.empty(2 * T * hw, 8, dtype=torch.float16, device=lat.device)
+    ops.cfg_euler_step(None, lat, il, next_in, T, hw, g_min, g_max, 0.0, sig[0])
+    for i in range(len(tsteps)):
+        rf, mf = face_net.adapter_forward(next_in, tsteps[i], h, w, scale_ldmk)
+        rd, md = drag_net.adapter_forward(next_in, tsteps[i], h, w, scale_traj)
+        for a, b in zip(rf + [mf], rd + [md]):
+            m = by_rows[a.shape[0]]
+            ops.mask_blend(a, b, m, a, period_rows=m.shape[0])           # face inside the mask, drag outside
+        noise = unet_net.unet_forward(next_in, tsteps[i], h, w, rf, mf)
+        ops.cfg_euler_step(noise, lat, il, next_in, T, hw, g_min, g_max, sig[i], sig[i + 1])
+        if on_step is not None and on_step(i, lat) and i + 1 < len(tsteps):
+            ops.cfg_euler_step(None, lat, il, next_in, T, hw, g_min, g_max, 0.0, sig[i + 1])
+    return lat
+
+
+class FlowControlNetPipeline(_TrajPipeline):
+    def __init__(self, vae, image_encoder, unet, drag_controlnet, face_controlnet, scheduler, feature_extractor=None):
+        super().__init__(vae, image_encoder, unet, drag_controlnet, scheduler, feature_extractor)
+        self.drag_controlnet, self.face_controlnet = drag_controlnet, face_controlnet
+
+    @classmethod
+    def from_pretrained(cls, path, unet=None, drag_controlnet=None, face_controlnet=None, image_encoder=None, vae=None,
+                        scheduler=None, feature_extractor=None, torch_dtype=None, **_ignored):
+        base = _TrajPipeline.from_pretrained(path, unet=unet, controlnet=drag_controlnet, image_encoder=image_encoder,
+                                             vae=vae, scheduler=scheduler, feature_extractor=feature_extractor)
+        if face_controlnet is None:
+            raise ValueError("pass face_controlnet=")
+        return cls(vae, image_encoder, unet, drag_controlnet, face_controlnet, base.scheduler, feature_extractor)
+
+    @torch.no_grad()
+    def __call__(self, image, controlnet_condition=None, controlnet_flow=None, landmarks=None, drag_flow=None,
+                 mask=None, height: int = 576, width: int = 1024, num_frames: Optional[int] = None,
+                 num_inference_steps: int = 25, min_guidance_scale: float = 1.0, max_guidance_scale: float = 3.0,
+                 fps: int = 7, motion_bucket_id: int = 127, noise_aug_strength: float = 0.02,
+                 decode_chunk_size: Optional[int] = None, num_videos_per_prompt: Optional[int] = 1, generator=None,
+                 latents: Optional[torch.Tensor] = None, output_type: Optional[str] = "pil",
+                 callback_on_step_end: Optional[Callable[[int, int, Dict], None]] = None,
+                 callback_on_step_end_tensor_inputs: List[str] = ["latents"], return_dict: bool = True,
+                 ctrl_scale_traj=1.0, ctrl_scale_ldmk=1.0, batch_size=1):
+        ops = _lib
+        num_frames = num_frames if num_frames is not None else self.unet.config.num_frames
+        decode_chunk_size = decode_chunk_size if decode_chunk_size is not None else num_frames
+        self.check_inputs(image, height, width)
+        if batch_size != 1 or num_videos_per_prompt != 1:
+            raise NotImplementedError("one clip per call")
+        if num_frames != self.unet.config.num_frames:
+            raise ValueError(f"num_frames must equal the UNet's num_frames ({self.unet.config.num_frames})")
+        if max_guidance_scale <= 1.0:
+            raise ValueError("max_guidance_scale must be > 1 (classifier-free guidance is how the adapters are driven)")
+        device = self._device
+        image_embeddings = self._encode_image(image, device, 1, True)
+        emb_dtype = image_embeddings.dtype
+        img = _to_unit_tensor(image, height, width) * 2.0 - 1.0
+        gen_cpu = generator if isinstance(generator, torch.Generator) and generator.device.type == "cpu" else None
+        img = img + noise_aug_strength * torch.randn(img.shape, generator=gen_cpu, dtype=img.dtype).to(img.device)
+        needs_upcasting = self.vae.dtype == torch.float16 and self.vae.config.force_upcast
+        if needs_upcasting:
+            self.vae.to(dtype=torch.float32)
+        image_latents = self._encode_vae_image(img.to(self.vae.dtype), device, 1, True).to(emb_dtype)
+        if needs_upcasting:
+            self.vae.to(dtype=torch.float16)
+        added_time_ids = torch.cat([_get_add_time_ids(0.02, emb_dtype, 1, 6, 128, unet=self.unet)] * 2).to(device)
+        self.scheduler.set_timesteps(num_inference_steps, device=device)
+        latents = self.prepare_latents(1, num_frames, self.unet.config.in_channels, height, width, emb_dtype, device,
+                                       generator, latents)
+        cond = torch.cat([_to_unit_tensor(controlnet_condition, height, width) * 2.0 - 1.0] * 2).to(device, torch.float16)
+        flow = torch.cat([controlnet_flow] * 2).to(device, torch.float16)
+        dflow = torch.cat([drag_flow] * 2).to(device, torch.float16)
+        ldmk = torch.cat([landmarks] * 2).to(device, torch.float16)
+
+        h, w = height // self.vae_scale_factor, width // self.vae_scale_factor
+        hw, T = h * w, num_frames
+        unet_net, face, drag = self.unet.net, self.face_controlnet, self.drag_controlnet
+        for n in (unet_net, face.net, drag.net):
+            n.prepare_clip(image_embeddings, added_time_ids)
+        face.prepare_condition(cond, flow, ldmk)
+        drag.prepare_condition(cond, dflow)
+        by_rows = level_masks(mask, h, w, len(self.unet.config.block_out_channels), T, device)
+        lat = latents[0].to(torch.float16).reshape(T, 4, hw).contiguous()
+        il = image_latents.to(torch.float16).reshape(2, 4, hw).contiguous()
+        sig, tsteps = self.scheduler._sigmas_host, self.scheduler._timesteps_host
+        self._num_timesteps = len(tsteps)
+
+        def on_step(i, cur_lat):
+            """Returns True when the callback replaced the latents (the fused next-step input must be rebuilt)."""
+            self.scheduler._step_index = i + 1
+            if callback_on_step_end is None:
+                return False
+            cur = cur_lat.reshape(1, T, 4, h, w)
+            outs = callback_on_step_end(self, i, self.scheduler.timesteps[i], {"latents": cur}) or {}
+            new = outs.pop("latents", None)
+            if new is None or new is cur:
+                return False
+            cur_lat.copy_(new.reshape(T, 4, hw))
+            return True
+
+        denoise_hybrid(ops, unet_net, face.net, drag.net, by_rows, lat, il, sig, tsteps, h, w, min_guidance_scale,
+                       max_guidance_scale, ctrl_scale_ldmk, ctrl_scale_traj, on_step)
+        latents = lat.reshape(1, T, 4, h, w)
+        if output_type == "latent":
+            frames = latents
+        else:
+            frames = self.decode_latents(latents.to(self.vae.dtype), num_frames, decode_chunk_size)
+            frames = self._postprocess(frames, output_type)
+        if not return_dict:
+            return frames, controlnet_flow
+        return FlowControlNetPipelineOutput(frames=frames, controlnet_flow=controlnet_flow)

@@ -56,6 +56,23 @@ def resize_with_antialiasing(inp, size):  # pipeline.py:532-562
 
 
 @torch.no_grad()
+def prepare_inputs(vae, image_encoder, image, num_frames, generator=None, noise_aug_strength=0.02, dtype=torch.float32):
+    """CLIP embedding (Q3, pipeline.py:114-141) and VAE image latents (:339-356), both with the zero CFG half first."""
+    if isinstance(image, torch.Tensor) and image.ndim == 3:
+        image = image[None]
+    img01 = pil_to_pt(image) if not isinstance(image, torch.Tensor) else image
+    clip_in = resize_with_antialiasing(img01, (224, 224)).to(dtype)
+    emb = image_encoder(clip_in).image_embeds.unsqueeze(1)
+    emb = torch.cat([torch.zeros_like(emb), emb])
+    img = 2.0 * pil_to_pt(image) - 1.0 if not isinstance(image, torch.Tensor) else 2.0 * image - 1.0
+    noise = torch.randn(img.shape, generator=generator, dtype=img.dtype)
+    img = img + noise_aug_strength * noise
+    image_latents = vae.encode(img.to(dtype)).latent_dist.mode()
+    image_latents = torch.cat([torch.zeros_like(image_latents), image_latents]).to(emb.dtype)
+    return emb, image_latents.unsqueeze(1).repeat(1, num_frames, 1, 1, 1)
+
+
+@torch.no_grad()
 def run_pipeline(vae, image_encoder, unet, controlnet, scheduler, image, controlnet_condition, controlnet_flow,
                  height=576, width=1024, num_frames=None, num_inference_steps=25, min_guidance_scale=1.0,
                  max_guidance_scale=3.0, noise_aug_strength=0.02, decode_chunk_size=None, generator=None,
@@ -64,22 +81,9 @@ def run_pipeline(vae, image_encoder, unet, controlnet, scheduler, image, control
     decode_chunk_size = decode_chunk_size if decode_chunk_size is not None else num_frames  # :318
     do_cfg = max_guidance_scale > 1.0
     assert do_cfg, "Q5: without CFG the reference feeds the latents as condition (pipeline.py:393,396)"
-    # 3. CLIP (Q3)                                                                           :114-141
-    if isinstance(image, torch.Tensor) and image.ndim == 3:
-        image = image[None]
     if isinstance(controlnet_condition, torch.Tensor) and controlnet_condition.ndim == 3:
         controlnet_condition = controlnet_condition[None]
-    img01 = pil_to_pt(image) if not isinstance(image, torch.Tensor) else image
-    clip_in = resize_with_antialiasing(img01, (224, 224)).to(dtype)
-    emb = image_encoder(clip_in).image_embeds.unsqueeze(1)
-    emb = torch.cat([torch.zeros_like(emb), emb])
-    # 4. VAE encode                                                                          :339-356
-    img = 2.0 * pil_to_pt(image) - 1.0 if not isinstance(image, torch.Tensor) else 2.0 * image - 1.0
-    noise = torch.randn(img.shape, generator=generator, dtype=img.dtype)
-    img = img + noise_aug_strength * noise
-    image_latents = vae.encode(img.to(dtype)).latent_dist.mode()
-    image_latents = torch.cat([torch.zeros_like(image_latents), image_latents]).to(emb.dtype)
-    image_latents = image_latents.unsqueeze(1).repeat(1, num_frames, 1, 1, 1)
+    emb, image_latents = prepare_inputs(vae, image_encoder, image, num_frames, generator, noise_aug_strength, dtype)
     # 5. added time ids, overwritten by constants (Q4)                                       :430-440
     added_time_ids = torch.tensor([[6, 128, 0.02]], dtype=emb.dtype).repeat(2, 1)
     scheduler.set_timesteps(num_inference_steps)
