@@ -120,14 +120,15 @@ def profile_start():
     _prof = []
 
 
-def profile_stop():
-    """-> {kind: {"ms": device time, "work": algorithmic FLOPs (or bytes), "launches": n}}"""
+def profile_stop(detail=False):
+    """-> {kind: {"ms": device time, "work": algorithmic FLOPs (or bytes), "launches": n}}; detail=True keys the
+    same aggregates by (kind + shape/epilogue tag) instead."""
     global _prof
     rec, _prof = _prof, None
     torch.cuda.synchronize()
     out = {}
-    for kind, work, e0, e1 in rec or []:
-        d = out.setdefault(kind, {"ms": 0.0, "work": 0.0, "launches": 0})
+    for kind, work, e0, e1, tag in rec or []:
+        d = out.setdefault(f"{kind} {tag}" if detail else kind, {"ms": 0.0, "work": 0.0, "launches": 0})
         d["ms"] += e0.elapsed_time(e1)
         d["work"] += work
         d["launches"] += 1
@@ -135,8 +136,8 @@ def profile_stop():
 
 
 class _Timed:
-    def __init__(self, kind, work):
-        self.kind, self.work = kind, work
+    def __init__(self, kind, work, tag=""):
+        self.kind, self.work, self.tag = kind, work, tag
 
     def __enter__(self):
         if _prof is not None:
@@ -147,7 +148,7 @@ class _Timed:
         if _prof is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            _prof.append((self.kind, self.work, self.e0, e1))
+            _prof.append((self.kind, self.work, self.e0, e1, self.tag))
         return False
 
 
@@ -212,7 +213,10 @@ def gemm(mode, a, w, out, *, N, bn=None, act=ACT_NONE, a2=None, M=0, K=0, K1=0, 
             kind, work = "gemm_conv3x3", 2.0 * n_img * H * W * N * ksize * ksize * C
         else:
             kind, work = "gemm_temporal3", 2.0 * B * T * HW * N * 3 * C
-        with _Timed(kind, work):
+        rows = M or n_img * H * W or B * T * HW
+        tag = (f"M={rows} N={N} K={K or C} act={act} a2={int(a2 is not None)} rb={int(rowbias is not None)} "
+               f"res={int(res1 is not None) + int(res2 is not None)}")
+        with _Timed(kind, work, tag):
             _check(lib.mofa_gemm(ctypes.byref(g), _stream()), "mofa_gemm")
         return out
     _check(lib.mofa_gemm(ctypes.byref(g), _stream()), "mofa_gemm")
@@ -227,7 +231,7 @@ def linear(a, w, out, **kw):
 
 def attn_spatial(qkv, out, frames, L, heads, scale):
     _chk_h(qkv, out)
-    with _Timed("attn_spatial", 4.0 * frames * heads * L * L * 64):
+    with _Timed("attn_spatial", 4.0 * frames * heads * L * L * 64, f"L={L} heads={heads}"):
         _check(load().mofa_attn_spatial(_p(qkv), _p(out), frames, L, heads, scale, _stream()), "mofa_attn_spatial")
     return out
 

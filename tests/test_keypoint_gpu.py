@@ -208,7 +208,8 @@ def test_keypoint_and_hybrid_entry_points():
     assert e < 3e-2, f"keypoint windowed latents rel err {e}"
     out = pipe(image, image, flow, ldmk, height=Himg, width=Wimg, num_frames=F_frames, num_inference_steps=1,
                latents=lat0.clone().half(), output_type="pt", window_size=T, stride=stride, decode_chunk_size=2)
-    assert out.frames.shape[-2:] == (Himg, Wimg) and torch.isfinite(out.frames).all()
+    assert len(out.frames) == 1 and out.frames[0].shape == (F_frames, 3, Himg, Wimg)   # tensor2vid: list per clip
+    assert torch.isfinite(out.frames[0]).all()
 
     # ---- Hybrid: T frames, two adapters + mask
     emb, il = opipe.prepare_inputs(vae.float().cpu(), clip.float().cpu(), image, T, torch.Generator().manual_seed(11))

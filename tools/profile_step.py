@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--width", type=int, default=1024)
     ap.add_argument("--frames", type=int, default=25)
     ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--detail", action="store_true", help="time every op, keyed by shape (implies --profile)")
     a = ap.parse_args()
     dev = "cuda"
     H, W, T = a.height, a.width, a.frames
@@ -60,6 +61,23 @@ def main():
 
     for i in range(a.warmup):
         step(i)
+    if a.detail:
+        a.profile = True
+        skip = {"gemm", "linear", "attn_spatial", "load", "pick_bn", "profile_start", "profile_stop", "launch_count",
+                "launch_count_reset", "conv_out_size"}
+
+        def wrap(name, fn):
+            def f(*args, **kw):
+                t = next((x for x in args if isinstance(x, torch.Tensor)), None)
+                nbytes = sum(x.numel() * x.element_size() for x in args if isinstance(x, torch.Tensor))
+                with lib._Timed(name, float(nbytes), f"shape={tuple(t.shape) if t is not None else ()}"):
+                    return fn(*args, **kw)
+            return f
+        for name in dir(lib):
+            fn = getattr(lib, name)
+            if callable(fn) and not name.startswith("_") and name not in skip and getattr(fn, "__module__", "") == lib.__name__ \
+                    and not isinstance(fn, type):
+                setattr(lib, name, wrap(name, fn))
     torch.cuda.synchronize()
     if a.profile:
         lib.profile_start()
@@ -75,8 +93,12 @@ def main():
     print(f"steps={a.steps} device_ms_per_step={e0.elapsed_time(e1) / a.steps:.2f} host_s={host:.2f} "
           f"launches_per_step={lib.launch_count() / a.steps:.0f} finite={bool(torch.isfinite(lat.float()).all())}")
     if a.profile:
-        for k, v in sorted(lib.profile_stop().items()):
-            print(f"  {k}: {v['ms'] / a.steps:.2f} ms/step, {v['work'] / max(v['ms'], 1e-9) / 1e9:.1f} TFLOP/s, "
+        rec = lib.profile_stop(detail=a.detail)
+        items = sorted(rec.items(), key=lambda kv: -kv[1]["ms"]) if a.detail else sorted(rec.items())
+        tot = sum(v["ms"] for v in rec.values()) / a.steps
+        print(f"  sum of timed ops: {tot:.2f} ms/step")
+        for k, v in items[:60]:
+            print(f"  {k}: {v['ms'] / a.steps:.2f} ms/step, {v['work'] / max(v['ms'], 1e-9) / 1e9:.1f} T(FLOP|B)/s, "
                   f"{v['launches'] // a.steps} launches/step")
 
 
