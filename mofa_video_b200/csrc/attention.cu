@@ -8,8 +8,7 @@
 //   TMEM one tile late so the PV MMA of tile j overlaps the softmax of tile j+1).
 //   S is double-buffered in TMEM (2 x 128 columns), PV partials too (2 x 64 columns).
 //   V is consumed in place from the [tokens, 3C] qkv matrix as an MN-major B operand (no transpose).
-// mofa_attn_temporal: SIMT kernel, one warp per (batch, pixel, head), T <= 32 tokens, lane = query
-//   frame, K/V rows broadcast from shared memory.  0.1 % of the FLOPs; HBM-bound.
+// mofa_attn_temporal lives in attn_temporal.cu.
 //
 // Replaces diffusers Attention(AttnProcessor2_0) -> F.scaled_dot_product_attention for attn1 of
 // BasicTransformerBlock / TemporalBasicTransformerBlock (blocks created at
@@ -275,111 +274,6 @@ attn_spatial_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
     }
 }
 
-// =============================================================================================
-// temporal attention: one warp per (b, pixel, head)
-// =============================================================================================
-__global__ void __launch_bounds__(128)
-attn_temporal_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int B, int T, int HW, int heads,
-                     float scale) {
-    __shared__ __align__(16) __half sK[4][32][64];
-    __shared__ __align__(16) __half sV[4][32][64];
-    const int w = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int C = heads * 64;
-    const long long ld = 3LL * C;
-    const long long items = static_cast<long long>(B) * HW * heads;
-    const long long warps_total = static_cast<long long>(gridDim.x) * 4;
-    for (long long it = blockIdx.x * 4LL + w; it < items; it += warps_total) {
-        const int h = static_cast<int>(it % heads);
-        const long long t0 = it / heads;
-        const int px = static_cast<int>(t0 % HW);
-        const int b = static_cast<int>(t0 / HW);
-        const long long row0 = static_cast<long long>(b) * T * HW + px;  // row of token t = row0 + t*HW
-        __syncwarp();
-        for (int idx = lane; idx < T * 8; idx += 32) {
-            const int t = idx >> 3, ch = idx & 7;
-            const __half* src = qkv + (row0 + static_cast<long long>(t) * HW) * ld + h * 64 + ch * 8;
-            *reinterpret_cast<uint4*>(&sK[w][t][ch * 8]) = __ldg(reinterpret_cast<const uint4*>(src + C));
-            *reinterpret_cast<uint4*>(&sV[w][t][ch * 8]) = __ldg(reinterpret_cast<const uint4*>(src + 2 * C));
-        }
-        __syncwarp();
-        if (lane < T) {
-            const __half* qsrc = qkv + (row0 + static_cast<long long>(lane) * HW) * ld + h * 64;
-            __half2 q[32];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(qsrc) + i);
-                q[4 * i + 0] = *reinterpret_cast<const __half2*>(&u.x);
-                q[4 * i + 1] = *reinterpret_cast<const __half2*>(&u.y);
-                q[4 * i + 2] = *reinterpret_cast<const __half2*>(&u.z);
-                q[4 * i + 3] = *reinterpret_cast<const __half2*>(&u.w);
-            }
-            float s[32];
-            float mx = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                s[j] = -INFINITY;
-                if (j < T) {
-                    float acc = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const uint4 u = *reinterpret_cast<const uint4*>(&sK[w][j][i * 8]);
-                        const float2 k0 = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
-                        const float2 k1 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-                        const float2 k2 = __half22float2(*reinterpret_cast<const __half2*>(&u.z));
-                        const float2 k3 = __half22float2(*reinterpret_cast<const __half2*>(&u.w));
-                        const float2 q0 = __half22float2(q[4 * i + 0]), q1 = __half22float2(q[4 * i + 1]);
-                        const float2 q2 = __half22float2(q[4 * i + 2]), q3 = __half22float2(q[4 * i + 3]);
-                        acc += q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y + q2.x * k2.x + q2.y * k2.y +
-                               q3.x * k3.x + q3.y * k3.y;
-                    }
-                    s[j] = acc * scale;
-                    mx = fmaxf(mx, s[j]);
-                }
-            }
-            float l = 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                s[j] = (j < T) ? __expf(s[j] - mx) : 0.f;
-                l += s[j];
-            }
-            const float inv = 1.0f / l;
-            __half* dst = out + (row0 + static_cast<long long>(lane) * HW) * C + h * 64;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float acc[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (j < T) {
-                        const uint4 u = *reinterpret_cast<const uint4*>(&sV[w][j][i * 8]);
-                        const float2 v0 = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
-                        const float2 v1 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-                        const float2 v2 = __half22float2(*reinterpret_cast<const __half2*>(&u.z));
-                        const float2 v3 = __half22float2(*reinterpret_cast<const __half2*>(&u.w));
-                        acc[0] += s[j] * v0.x;
-                        acc[1] += s[j] * v0.y;
-                        acc[2] += s[j] * v1.x;
-                        acc[3] += s[j] * v1.y;
-                        acc[4] += s[j] * v2.x;
-                        acc[5] += s[j] * v2.y;
-                        acc[6] += s[j] * v3.x;
-                        acc[7] += s[j] * v3.y;
-                    }
-                }
-                uint32_t wv[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const __half2 hh = __floats2half2_rn(acc[2 * e] * inv, acc[2 * e + 1] * inv);
-                    wv[e] = *reinterpret_cast<const uint32_t*>(&hh);
-                }
-                *reinterpret_cast<uint4*>(dst + i * 8) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-            }
-        }
-    }
-}
-
 }  // namespace mofa
 
 using namespace mofa;
@@ -419,19 +313,4 @@ int mofa::attn_spatial_v1(const void* qkv, void* out, int32_t frames, int32_t L,
     dim3 grid((L + 127) / 128, heads, frames);
     attn_spatial_kernel<<<grid, kAttnThreads, smem_bytes, stream>>>(tm, p);
     return check_launch("mofa_attn_spatial");
-}
-
-extern "C" int mofa_attn_temporal(const void* qkv, void* out, int32_t B, int32_t T, int32_t HW, int32_t heads,
-                                  float scale, mofa_stream_t stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (!qkv || !out || B <= 0 || T <= 0 || T > 32 || HW <= 0 || heads <= 0) {
-        set_last_error("mofa_attn_temporal: needs 1 <= T <= 32");
-        return MOFA_ERR_ARG;
-    }
-    const long long items = static_cast<long long>(B) * HW * heads;
-    long long blocks = (items + 3) / 4;
-    if (blocks > 148LL * 16) blocks = 148LL * 16;
-    attn_temporal_kernel<<<static_cast<unsigned>(blocks), 128, 0, stream>>>(
-        static_cast<const __half*>(qkv), static_cast<__half*>(out), B, T, HW, heads, scale);
-    return check_launch("mofa_attn_temporal");
 }

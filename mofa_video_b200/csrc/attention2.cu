@@ -1,20 +1,22 @@
-// Spatial self-attention, version 2: two 128-query tiles per CTA ("ping-pong" softmax warpgroups).
+// Spatial self-attention (head_dim 64), two 128-query tiles per CTA.
 //
-// Why: with head_dim 64 the kernel is bound by the exponential (MUFU) and by instruction issue of the
-// softmax warps, not by the tensor core (per 128x128 tile: 512 MMA cycles vs >= 1024 MUFU cycles per
-// SMSP-warp).  Version 1 ran ONE softmax warp per SM sub-partition, so every tcgen05.ld / MUFU latency
-// was exposed (measured 315 TFLOP/s at L = 9216).  Here each SM sub-partition hosts two softmax warps
-// (one per query tile) that interleave, K/V tiles are loaded once for 256 queries, and the instruction
-// mix per score is trimmed: masking only on the ragged last tile, 3-input max, row sums of the unrounded
-// probabilities, lazy rescaling (the running maximum is only moved when it grows by more than 2^8, so the
-// 64-wide O rescale is skipped on almost every tile; P <= 256 stays well inside fp16).
+// With head_dim 64 the kernel is bound by the exponential (MUFU: 16 ex2 / clk / SM -> 2048 clk per 256 x 128 score
+// block) and by instruction issue of the softmax warps, not by the tensor core (1024 clk for the same block).  The
+// structure therefore keeps the MUFU busy and trims everything else:
+//   * one query row per thread, the 128 scores of a tile are read from TMEM ONCE into registers; the S buffer is
+//     released right after that read (s_free), so S_{j+1} = Q K_{j+1}^T is computed while the exponentials of tile j
+//     run -- the registers act as the second S buffer;
+//   * O accumulates in TMEM across KV tiles (tcgen05.mma accumulate), no per-tile read-back; the running maximum is
+//     lazy (moved only when it grows by more than 2^8, P <= 256 stays inside fp16), so the O rescale -- a TMEM
+//     load / scale / store by the owning warp -- happens on the first one or two tiles only;
+//   * the MMA-issuing thread multiplexes four barriers (s_free / p_full of both query tiles) with non-blocking probes
+//     and issues whatever is ready, so neither softmax warpgroup waits behind the other;
+//   * masking only on the ragged last tile, 3-input max, row sums of the unrounded probabilities.
 //
 //   warp 0 (1 lane) : TMA producer   Q0,Q1 once; K/V tiles through a 3-stage ring
-//   warp 1 (1 lane) : MMA issuer     S_w = Q_w K^T (TMEM, one buffer per query tile), O_w = P_w V
+//   warp 1 (1 lane) : MMA issuer     S_w = Q_w K^T (TMEM 2 x 128 cols), O_w += P_w V (TMEM 2 x 64 cols)
 //   warps 2..5      : softmax warpgroup 0 (query tile 0), one row per thread
 //   warps 6..9      : softmax warpgroup 1 (query tile 1)
-// Issue order per KV tile j:  [P0_j ready] PV0_j, S0_{j+1};  [P1_j ready] PV1_j, S1_{j+1}  -- so while
-// warpgroup 0 works on S0_{j+1} the tensor core runs PV1_j / S1_{j+1} and vice versa.
 #include "../../include/mofa_b200.h"
 #include <stdlib.h>
 
@@ -46,59 +48,6 @@ MOFA_DEVICE float max3(float a, float b, float c) {
     return d;
 }
 
-template <bool kMasked>
-MOFA_DEVICE float row_max(uint32_t ts, int kv_valid) {
-    float mx = -INFINITY;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-        uint32_t s[32];
-        tmem_ld_32x32(ts + c * 32, s);
-        tmem_ld_wait();
-        if (kMasked) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (c * 32 + i >= kv_valid) s[i] = 0xff800000u;  // -inf
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) mx = max3(mx, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-    }
-    return mx;
-}
-
-// p = exp2(s * sl2 - m) -> fp16 -> swizzled K-major P tile; returns the row sum of p
-template <bool kMasked>
-MOFA_DEVICE float exp_store(uint32_t ts, uint8_t* prow, int r, float sl2, float m, int kv_valid) {
-    float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-        uint32_t s[32];
-        tmem_ld_32x32(ts + c * 32, s);
-        tmem_ld_wait();
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            uint32_t packed[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float p0 = fast_exp2(fmaf(__uint_as_float(s[g * 8 + 2 * i]), sl2, -m));
-                float p1 = fast_exp2(fmaf(__uint_as_float(s[g * 8 + 2 * i + 1]), sl2, -m));
-                if (kMasked) {
-                    const int col = c * 32 + g * 8 + 2 * i;
-                    if (col >= kv_valid) p0 = 0.f;
-                    if (col + 1 >= kv_valid) p1 = 0.f;
-                }
-                sum0 += p0;
-                sum1 += p1;
-                const __half2 h = __floats2half2_rn(p0, p1);
-                packed[i] = *reinterpret_cast<const uint32_t*>(&h);
-            }
-            const int col0 = c * 32 + g * 8;
-            uint8_t* dst = prow + (col0 >> 6) * kTile + ((((col0 & 63) >> 3) ^ (r & 7)) << 4);
-            *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        }
-    }
-    return sum0 + sum1;
-}
-
 __global__ void __launch_bounds__(kThreads, 1)
 attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) {
     extern __shared__ uint8_t smem_raw[];
@@ -110,9 +59,10 @@ attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
     uint64_t* q_full = bars;
     uint64_t* kv_full = bars + 1;
     uint64_t* kv_empty = kv_full + kKVStages;
-    uint64_t* s_full = kv_empty + kKVStages;  // [2] per query tile
-    uint64_t* p_full = s_full + 2;            // [2]
-    uint64_t* o_full = p_full + 2;            // [2]
+    uint64_t* s_full = kv_empty + kKVStages;  // [2] per query tile: S_j landed in TMEM
+    uint64_t* s_free = s_full + 2;            // [2] S_j copied to registers, the buffer may be overwritten
+    uint64_t* p_full = s_free + 2;            // [2] P_j in shared memory (and O rescaled if needed)
+    uint64_t* o_full = p_full + 2;            // [2] P_j V_j accumulated
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + 2);
 
     const int warp = threadIdx.x >> 5;
@@ -131,6 +81,7 @@ attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s_full[i], 1);
+            mbar_init(&s_free[i], 128);
             mbar_init(&p_full[i], 128);
             mbar_init(&o_full[i], 1);
         }
@@ -181,45 +132,54 @@ attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
                 umma_commit(&s_full[w]);
             }
         }
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int j = 0; j < n_kv; ++j) {
-            int nstage = stage + 1;
-            uint32_t nphase = phase;
-            if (nstage == kKVStages) {
-                nstage = 0;
-                nphase ^= 1;
-            }
-            const bool have_next = j + 1 < n_kv;
-            const uint32_t va = smem_u32(sKV + stage * 2 * kTile + kTile);
-            const uint64_t dv = umma_desc_sw128_mnmajor(va, kTile);
-            uint64_t dk_next = 0;
+        // per query tile: next S tile to issue (with its ring stage / phase) and next PV tile to issue
+        int js[2] = {1, 1}, js_stage[2] = {1 % kKVStages, 1 % kKVStages};
+        uint32_t js_phase[2] = {(1 / kKVStages) & 1u, (1 / kKVStages) & 1u};
+        int jp[2] = {0, 0}, jp_stage[2] = {0, 0};
+        int released = 0, rel_stage = 0;
+        while (jp[0] < n_kv || jp[1] < n_kv) {
+            bool progress = false;
 #pragma unroll
             for (int w = 0; w < 2; ++w) {
-                mbar_wait(&p_full[w], j & 1);
-                tc_fence_after();
-                const uint32_t pa = smem_u32(sP + w * kPBytes);
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {
-                    const uint64_t dp = umma_desc_sw128_kmajor(pa + (kk >> 2) * kTile) + 2 * (kk & 3);
-                    umma_f16_ss(tmem_O + w * 64, dp, dv + 128 * kk, idesc_o, kk != 0);
-                }
-                umma_commit(&o_full[w]);
-                if (have_next) {
-                    if (w == 0) {
-                        mbar_wait(&kv_full[nstage], nphase);
-                        tc_fence_after();
-                        dk_next = umma_desc_sw128_kmajor(smem_u32(sKV + nstage * 2 * kTile));
-                    }
+                if (js[w] < n_kv && mbar_test(&s_free[w], (js[w] - 1) & 1) &&
+                    mbar_test(&kv_full[js_stage[w]], js_phase[w])) {
+                    tc_fence_after();
+                    const uint64_t dk = umma_desc_sw128_kmajor(smem_u32(sKV + js_stage[w] * 2 * kTile));
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_f16_ss(tmem_S + w * 128, dq[w] + 2 * k, dk_next + 2 * k, idesc_s, k != 0);
+                        umma_f16_ss(tmem_S + w * 128, dq[w] + 2 * k, dk + 2 * k, idesc_s, k != 0);
                     umma_commit(&s_full[w]);
+                    ++js[w];
+                    if (++js_stage[w] == kKVStages) {
+                        js_stage[w] = 0;
+                        js_phase[w] ^= 1u;
+                    }
+                    progress = true;
+                }
+                if (jp[w] < n_kv && mbar_test(&p_full[w], jp[w] & 1)) {
+                    tc_fence_after();
+                    const uint32_t va = smem_u32(sKV + jp_stage[w] * 2 * kTile + kTile);
+                    const uint64_t dv = umma_desc_sw128_mnmajor(va, kTile);
+                    const uint32_t pa = smem_u32(sP + w * kPBytes);
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const uint64_t dp = umma_desc_sw128_kmajor(pa + (kk >> 2) * kTile) + 2 * (kk & 3);
+                        umma_f16_ss(tmem_O + w * 64, dp, dv + 128 * kk, idesc_o, (jp[w] > 0) || (kk != 0));
+                    }
+                    umma_commit(&o_full[w]);
+                    ++jp[w];
+                    if (++jp_stage[w] == kKVStages) jp_stage[w] = 0;
+                    // a K/V stage is free once both query tiles have issued its PV (the commit covers every earlier MMA)
+                    const int done = jp[0] < jp[1] ? jp[0] : jp[1];
+                    if (done > released) {
+                        umma_commit(&kv_empty[rel_stage]);
+                        ++released;
+                        if (++rel_stage == kKVStages) rel_stage = 0;
+                    }
+                    progress = true;
                 }
             }
-            umma_commit(&kv_empty[stage]);
-            stage = nstage;
-            phase = nphase;
+            if (!progress) __nanosleep(20);
         }
     } else if (warp >= 2) {
         // ===================== softmax warpgroups =====================
@@ -232,71 +192,94 @@ attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
         uint8_t* prow = sP + w * kPBytes + r * 128;
         const float sl2 = p.scale_log2;
         float m = -INFINITY, l = 0.f;
-        float o[64];
-#pragma unroll
-        for (int i = 0; i < 64; ++i) o[i] = 0.f;
 
         for (int j = 0; j < n_kv; ++j) {
             mbar_wait(&s_full[w], j & 1);
             tc_fence_after();
+            uint32_t s[128];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld_32x32(ts + c * 32, reinterpret_cast<uint32_t(&)[32]>(s[c * 32]));
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&s_free[w]);  // S_{j+1} may now overwrite the TMEM buffer
             const int kv_valid = p.L - j * 128;
-            const bool masked = kv_valid < 128;  // warp-uniform
-            const float mx = (masked ? row_max<true>(ts, kv_valid) : row_max<false>(ts, kv_valid)) * sl2;
+            if (kv_valid < 128) {  // warp-uniform: ragged last tile
+#pragma unroll
+                for (int i = 0; i < 128; ++i)
+                    if (i >= kv_valid) s[i] = 0xff800000u;  // -inf
+            }
+            float mx = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 128; i += 2) mx = max3(mx, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+            mx *= sl2;
             // lazy rescale: move the reference maximum only when it grows by more than 2^8
             float alpha = 1.0f;
             if (mx > m + 8.0f) {
                 alpha = fast_exp2(m - mx);  // first tile: m = -inf -> 0
                 m = mx;
             }
-            // fold in the previous tile's PV partial (it is relative to the old m), then rescale
+            l *= alpha;
             if (j > 0) {
+                // P_{j-1} V_{j-1} done: the P buffer may be overwritten and O is stable
                 mbar_wait(&o_full[w], (j - 1) & 1);
                 tc_fence_after();
+                if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll 1
+                    for (int c = 0; c < 8; ++c) {
+                        uint32_t v[8];
+                        tmem_ld_32x8(to + c * 8, v);
+                        tmem_ld_wait();
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(to + c * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(v[i]);
+                        for (int i = 0; i < 8; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                        tmem_st_32x8(to + c * 8, v);
+                    }
+                    tmem_st_wait();
                 }
             }
-            if (alpha != 1.0f) {
+            float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-                for (int i = 0; i < 64; ++i) o[i] *= alpha;
-                l *= alpha;
+            for (int g = 0; g < 16; ++g) {
+                uint32_t packed[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float p0 = fast_exp2(fmaf(__uint_as_float(s[g * 8 + 2 * i]), sl2, -m));
+                    const float p1 = fast_exp2(fmaf(__uint_as_float(s[g * 8 + 2 * i + 1]), sl2, -m));
+                    sum0 += p0;
+                    sum1 += p1;
+                    const __half2 h = __floats2half2_rn(p0, p1);
+                    packed[i] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                const int col0 = g * 8;
+                uint8_t* dst = prow + (col0 >> 6) * kTile + ((((col0 & 63) >> 3) ^ (r & 7)) << 4);
+                *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
             }
-            l += masked ? exp_store<true>(ts, prow, r, sl2, m, kv_valid) : exp_store<false>(ts, prow, r, sl2, m, kv_valid);
+            l += sum0 + sum1;
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(&p_full[w]);
         }
-        {
-            const int j = n_kv - 1;
-            mbar_wait(&o_full[w], j & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(to + c * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(v[i]);
-            }
-        }
+        mbar_wait(&o_full[w], (n_kv - 1) & 1);
+        tc_fence_after();
         const int qrow = q0 + w * 128 + r;
-        if (qrow < p.L) {
-            const float inv = 1.0f / l;
-            __half* dst = p.out + (static_cast<long long>(frame) * p.L + qrow) * p.C + head * 64;
+        const float inv = 1.0f / l;
+        __half* dst = p.out + (static_cast<long long>(frame) * p.L + qrow) * p.C + head * 64;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                uint32_t wv[4];
+        for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(to + c * 32, v);
+            tmem_ld_wait();
+            if (qrow < p.L) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const __half2 h = __floats2half2_rn(o[g * 8 + 2 * i] * inv, o[g * 8 + 2 * i + 1] * inv);
-                    wv[i] = *reinterpret_cast<const uint32_t*>(&h);
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t wv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const __half2 h = __floats2half2_rn(__uint_as_float(v[g * 8 + 2 * i]) * inv,
+                                                            __uint_as_float(v[g * 8 + 2 * i + 1]) * inv);
+                        wv[i] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
                 }
-                *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
             }
         }
     }

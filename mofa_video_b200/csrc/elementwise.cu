@@ -13,8 +13,23 @@ union V8 {
 };
 
 // =============================================================================================
-// GroupNorm (torch.nn.GroupNorm(32, C, eps) [+ SiLU]) on channels-last data, optional concat input
+// GroupNorm (torch.nn.GroupNorm(32, C, eps) [+ SiLU]) on channels-last data, optional concat input.
+// Two streaming passes (statistics, then normalise): block = (VX vectors of 8 channels) x (VY rows), so a block reads
+// a contiguous slab with fully coalesced 16-B loads; every thread owns fixed channels (its per-channel scale / shift
+// are computed once per block) and keeps kUnroll independent loads in flight.
 // =============================================================================================
+constexpr int kGnUnroll = 4;
+
+__device__ __forceinline__ const __half* gn_src(const __half* x1, int C1, const __half* x2, int C2, int c,
+                                                long long& ld) {
+    if (c < C1) {
+        ld = C1;
+        return x1 + c;
+    }
+    ld = C2;
+    return x2 + (c - C1);
+}
+
 __global__ void __launch_bounds__(256)
 groupnorm_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2,
                        long long rows_per_stat, int rows_per_block, int groups, float* __restrict__ stats) {
@@ -39,38 +54,55 @@ groupnorm_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __re
 
     for (int vec = tx; vec < vecs; vec += VX) {
         const int c = vec << 3;
-        const __half* base;
         long long ld;
-        int cc;
-        if (c < C1) {
-            base = x1;
-            ld = C1;
-            cc = c;
-        } else {
-            base = x2;
-            ld = C2;
-            cc = c - C1;
-        }
+        const __half* base = gn_src(x1, C1, x2, C2, c, ld) + row0 * ld;
         float sum[8], sq[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
-        for (long long r = r_begin + ty; r < r_end; r += VY) {
+        long long r = r_begin + ty;
+        for (; r + static_cast<long long>(kGnUnroll - 1) * VY < r_end; r += static_cast<long long>(kGnUnroll) * VY) {
+            V8 v[kGnUnroll];
+#pragma unroll
+            for (int u = 0; u < kGnUnroll; ++u)
+                v[u].u = __ldg(reinterpret_cast<const uint4*>(base + (r + static_cast<long long>(u) * VY) * ld));
+#pragma unroll
+            for (int u = 0; u < kGnUnroll; ++u)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(v[u].h2[j]);
+                    sum[2 * j] += f.x;
+                    sq[2 * j] = fmaf(f.x, f.x, sq[2 * j]);
+                    sum[2 * j + 1] += f.y;
+                    sq[2 * j + 1] = fmaf(f.y, f.y, sq[2 * j + 1]);
+                }
+        }
+        for (; r < r_end; r += VY) {
             V8 v;
-            v.u = __ldg(reinterpret_cast<const uint4*>(base + (row0 + r) * ld + cc));
+            v.u = __ldg(reinterpret_cast<const uint4*>(base + r * ld));
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float f = __half2float(v.h[j]);
                 sum[j] += f;
-                sq[j] += f * f;
+                sq[j] = fmaf(f, f, sq[j]);
             }
         }
-        // flush: channels c..c+7 touch at most two groups when cpg >= 8, more when cpg < 8
+        // flush: merge the channels of one group before touching shared memory (cpg >= 8: at most two groups)
+        int g_prev = c / cpg;
+        float a_sum = 0.f, a_sq = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int g = (c + j) / cpg;
-            atomicAdd(&s_sum[g], sum[j]);
-            atomicAdd(&s_sq[g], sq[j]);
+            if (g != g_prev) {
+                atomicAdd(&s_sum[g_prev], a_sum);
+                atomicAdd(&s_sq[g_prev], a_sq);
+                a_sum = a_sq = 0.f;
+                g_prev = g;
+            }
+            a_sum += sum[j];
+            a_sq += sq[j];
         }
+        atomicAdd(&s_sum[g_prev], a_sum);
+        atomicAdd(&s_sq[g_prev], a_sq);
     }
     __syncthreads();
     if (tid < groups) {
@@ -82,26 +114,29 @@ groupnorm_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __re
 __global__ void __launch_bounds__(256)
 groupnorm_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2,
                        const __half* __restrict__ gamma, const __half* __restrict__ beta, __half* __restrict__ out,
-                       long long rows, long long rows_per_stat, int groups, float eps, int silu,
+                       long long rows_per_stat, int rows_per_block, int groups, float eps, int silu,
                        const float* __restrict__ stats) {
     const int C = C1 + C2;
     const int vecs = C >> 3;
     const int cpg = C / groups;
+    const int VX = blockDim.x, VY = blockDim.y;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const long long s = blockIdx.y;
+    const long long r_begin = static_cast<long long>(blockIdx.x) * rows_per_block;
+    long long r_end = r_begin + rows_per_block;
+    if (r_end > rows_per_stat) r_end = rows_per_stat;
+    const long long row0 = s * rows_per_stat;
     const float inv_cnt = 1.0f / (static_cast<float>(cpg) * static_cast<float>(rows_per_stat));
-    const long long total = rows * vecs;
-    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const long long row = idx / vecs;
-        const int c = static_cast<int>(idx - row * vecs) << 3;
-        const long long s = row / rows_per_stat;
-        V8 v;
-        if (c < C1)
-            v.u = __ldg(reinterpret_cast<const uint4*>(x1 + row * C1 + c));
-        else
-            v.u = __ldg(reinterpret_cast<const uint4*>(x2 + row * C2 + (c - C1)));
-        V8 g, b, o;
-        g.u = __ldg(reinterpret_cast<const uint4*>(gamma + c));
-        b.u = __ldg(reinterpret_cast<const uint4*>(beta + c));
+
+    for (int vec = tx; vec < vecs; vec += VX) {
+        const int c = vec << 3;
+        long long ld;
+        const __half* base = gn_src(x1, C1, x2, C2, c, ld) + row0 * ld;
+        __half* obase = out + row0 * C + c;
+        V8 gm, bt;
+        gm.u = __ldg(reinterpret_cast<const uint4*>(gamma + c));
+        bt.u = __ldg(reinterpret_cast<const uint4*>(beta + c));
+        float sc[8], sh[8];
         int gi_prev = -1;
         float mean = 0.f, rstd = 0.f;
 #pragma unroll
@@ -116,35 +151,75 @@ groupnorm_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __re
                 rstd = rsqrtf(var + eps);
                 gi_prev = gi;
             }
-            float y = (__half2float(v.h[j]) - mean) * rstd * __half2float(g.h[j]) + __half2float(b.h[j]);
-            if (silu) y = silu_f(y);
-            o.h[j] = __float2half_rn(y);
+            sc[j] = rstd * __half2float(gm.h[j]);
+            sh[j] = __half2float(bt.h[j]) - mean * sc[j];
         }
-        *reinterpret_cast<uint4*>(out + row * C + c) = o.u;
+        long long r = r_begin + ty;
+        for (; r + static_cast<long long>(kGnUnroll - 1) * VY < r_end; r += static_cast<long long>(kGnUnroll) * VY) {
+            V8 v[kGnUnroll];
+#pragma unroll
+            for (int u = 0; u < kGnUnroll; ++u)
+                v[u].u = __ldg(reinterpret_cast<const uint4*>(base + (r + static_cast<long long>(u) * VY) * ld));
+#pragma unroll
+            for (int u = 0; u < kGnUnroll; ++u) {
+                V8 o;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(v[u].h2[j]);
+                    float y0 = fmaf(f.x, sc[2 * j], sh[2 * j]);
+                    float y1 = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
+                    if (silu) {
+                        y0 = silu_f(y0);
+                        y1 = silu_f(y1);
+                    }
+                    o.h2[j] = __floats2half2_rn(y0, y1);
+                }
+                *reinterpret_cast<uint4*>(obase + (r + static_cast<long long>(u) * VY) * C) = o.u;
+            }
+        }
+        for (; r < r_end; r += VY) {
+            V8 v, o;
+            v.u = __ldg(reinterpret_cast<const uint4*>(base + r * ld));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float y = fmaf(__half2float(v.h[j]), sc[j], sh[j]);
+                if (silu) y = silu_f(y);
+                o.h[j] = __float2half_rn(y);
+            }
+            *reinterpret_cast<uint4*>(obase + r * C) = o.u;
+        }
     }
 }
 
 // =============================================================================================
-// LayerNorm over C (<= 2048) per row, one warp per row, optional per-row-group pre-add
+// LayerNorm over C (<= 2048) per row; LPR lanes share one row (8 / 16 / 32 for C = 320 / 640 / 1280, so every lane
+// carries <= VPL 16-byte vectors and a warp keeps 32/LPR rows in flight); optional per-row-group pre-add
 // =============================================================================================
-template <int kMaxVec>
+template <int LPR, int VPL>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma, const __half* __restrict__ beta,
                  __half* __restrict__ out, long long rows, int C, float eps, const __half* __restrict__ add,
                  long long rows_per_group, long long add_period, __half* __restrict__ sum_out) {
+    constexpr int RPW = 32 / LPR;
     const int lane = threadIdx.x & 31;
-    const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) return;
+    const int sub = lane % LPR;
+    const long long warp = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long row = warp * RPW + lane / LPR;
+    const bool live = row < rows;
     const int vecs = C >> 3;
-    float v[kMaxVec][8];
-    const __half* addrow = add ? add + ((row / rows_per_group) % add_period) * C : nullptr;
+    float v[VPL][8];
+    const __half* addrow = (add && live) ? add + ((row / rows_per_group) % add_period) * C : nullptr;
+    V8 t[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int vec = sub + i * LPR;
+        if (live && vec < vecs) t[i].u = __ldg(reinterpret_cast<const uint4*>(x + row * C + vec * 8));
+    }
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
-        const int vec = lane + i * 32;
-        if (vec < vecs) {
-            V8 t;
-            t.u = __ldg(reinterpret_cast<const uint4*>(x + row * C + vec * 8));
+    for (int i = 0; i < VPL; ++i) {
+        const int vec = sub + i * LPR;
+        if (live && vec < vecs) {
             if (addrow) {
                 V8 a;
                 a.u = __ldg(reinterpret_cast<const uint4*>(addrow + vec * 8));
@@ -152,40 +227,40 @@ layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     // the reference adds in fp16 (hidden_states + emb), so round the sum to fp16
-                    so.h[j] = __float2half_rn(__half2float(t.h[j]) + __half2float(a.h[j]));
+                    so.h[j] = __float2half_rn(__half2float(t[i].h[j]) + __half2float(a.h[j]));
                     v[i][j] = __half2float(so.h[j]);
                 }
                 if (sum_out) *reinterpret_cast<uint4*>(sum_out + row * C + vec * 8) = so.u;
             } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[i][j] = __half2float(t.h[j]);
+                for (int j = 0; j < 8; ++j) v[i][j] = __half2float(t[i].h[j]);
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) sum += v[i][j];
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float mean = sum / static_cast<float>(C);
     float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
-        const int vec = lane + i * 32;
-        if (vec < vecs) {
+    for (int i = 0; i < VPL; ++i) {
+        const int vec = sub + i * LPR;
+        if (live && vec < vecs) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float d = v[i][j] - mean;
-                sq += d * d;
+                sq = fmaf(d, d, sq);
             }
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     const float rstd = rsqrtf(sq / static_cast<float>(C) + eps);
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
-        const int vec = lane + i * 32;
-        if (vec < vecs) {
+    for (int i = 0; i < VPL; ++i) {
+        const int vec = sub + i * LPR;
+        if (live && vec < vecs) {
             V8 g, b, o;
             g.u = __ldg(reinterpret_cast<const uint4*>(gamma + vec * 8));
             b.u = __ldg(reinterpret_cast<const uint4*>(beta + vec * 8));
@@ -449,22 +524,31 @@ extern "C" int mofa_groupnorm(const void* x1, int32_t C1, const void* x2, int32_
     const long long nstat = rows / rows_per_stat;
     cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * nstat, stream);
     const int vecs = C / 8;
-    int VX = vecs < 256 ? vecs : 256;
+    const int nv = (vecs + 255) / 256;
+    const int VX = (vecs + nv - 1) / nv;
     int VY = 256 / VX;
     if (VY < 1) VY = 1;
-    int rows_per_block = 256;
-    if (rows_per_stat < rows_per_block) rows_per_block = static_cast<int>(rows_per_stat);
     dim3 block(VX, VY);
-    dim3 grid(static_cast<unsigned>((rows_per_stat + rows_per_block - 1) / rows_per_block),
-              static_cast<unsigned>(nstat));
-    groupnorm_stats_kernel<<<grid, block, 0, stream>>>(static_cast<const __half*>(x1), C1,
-                                                       static_cast<const __half*>(x2), C2, rows_per_stat,
-                                                       rows_per_block, groups, stats);
+    auto launch_grid = [&](int rows_per_block) {
+        return dim3(static_cast<unsigned>((rows_per_stat + rows_per_block - 1) / rows_per_block),
+                    static_cast<unsigned>(nstat));
+    };
+    // slabs sized so every thread streams >= 2 * kGnUnroll rows while the grid still covers the 148 SMs several times
+    auto pick_rows = [&](int want) {
+        long long rpb = want;
+        while (rpb > VY * kGnUnroll && ((rows_per_stat + rpb - 1) / rpb) * nstat < 148LL * 8) rpb >>= 1;
+        if (rpb > rows_per_stat) rpb = rows_per_stat;
+        return static_cast<int>(rpb < 1 ? 1 : rpb);
+    };
+    const int rpb_stats = pick_rows(VY * kGnUnroll * 8);
+    const int rpb_apply = pick_rows(VY * kGnUnroll * 4);
+    groupnorm_stats_kernel<<<launch_grid(rpb_stats), block, 0, stream>>>(
+        static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2, rows_per_stat, rpb_stats, groups, stats);
     int rc = check_launch("mofa_groupnorm(stats)");
     if (rc) return rc;
-    groupnorm_apply_kernel<<<grid_for(rows * vecs), 256, 0, stream>>>(
+    groupnorm_apply_kernel<<<launch_grid(rpb_apply), block, 0, stream>>>(
         static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2, static_cast<const __half*>(gamma),
-        static_cast<const __half*>(beta), static_cast<__half*>(out), rows, rows_per_stat, groups, eps, silu, stats);
+        static_cast<const __half*>(beta), static_cast<__half*>(out), rows_per_stat, rpb_apply, groups, eps, silu, stats);
     return check_launch("mofa_groupnorm(apply)");
 }
 
@@ -479,19 +563,24 @@ extern "C" int mofa_layernorm(const void* x, const void* gamma, const void* beta
     if (rows_per_group <= 0) rows_per_group = 1;
     if (add_period <= 0) add_period = 1;
     const int warps = 8;
-    const unsigned grid = static_cast<unsigned>((rows + warps - 1) / warps);
     const int vecs = C / 8;
-#define LN_LAUNCH(MV)                                                                                              \
-    layernorm_kernel<MV><<<grid, warps * 32, 0, stream>>>(                                                         \
-        static_cast<const __half*>(x), static_cast<const __half*>(gamma), static_cast<const __half*>(beta),        \
-        static_cast<__half*>(out), rows, C, eps, static_cast<const __half*>(add), rows_per_group, add_period,      \
-        static_cast<__half*>(sum_out))
-    if (vecs <= 64)
-        LN_LAUNCH(2);
-    else if (vecs <= 160)
-        LN_LAUNCH(5);
+#define LN_LAUNCH(LPR, VPL)                                                                                        \
+    do {                                                                                                           \
+        const long long nwarps = (rows + (32 / LPR) - 1) / (32 / LPR);                                             \
+        const unsigned grid = static_cast<unsigned>((nwarps + warps - 1) / warps);                                 \
+        layernorm_kernel<LPR, VPL><<<grid, warps * 32, 0, stream>>>(                                               \
+            static_cast<const __half*>(x), static_cast<const __half*>(gamma), static_cast<const __half*>(beta),    \
+            static_cast<__half*>(out), rows, C, eps, static_cast<const __half*>(add), rows_per_group, add_period,  \
+            static_cast<__half*>(sum_out));                                                                        \
+    } while (0)
+    if (vecs <= 8 * 5)
+        LN_LAUNCH(8, 5);
+    else if (vecs <= 16 * 5)
+        LN_LAUNCH(16, 5);
+    else if (vecs <= 32 * 5)
+        LN_LAUNCH(32, 5);
     else
-        LN_LAUNCH(8);
+        LN_LAUNCH(32, 8);
 #undef LN_LAUNCH
     return check_launch("mofa_layernorm");
 }

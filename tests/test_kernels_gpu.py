@@ -154,7 +154,8 @@ def test_attn_spatial(frames, Lq, heads):
     close(out, ref, 3e-3, 2e-2, f"attn_spatial L={Lq}")
 
 
-@pytest.mark.parametrize("B,T,HW,heads", [(2, 25, 144, 5), (1, 14, 16, 10), (2, 8, 100, 1)])
+@pytest.mark.parametrize("B,T,HW,heads", [(2, 25, 144, 5), (1, 14, 16, 10), (2, 8, 100, 1), (2, 32, 50, 2),
+                                            (2, 3, 256, 1), (1, 17, 2500, 3)])
 def test_attn_temporal(B, T, HW, heads):
     lib = L()
     C = heads * 64
@@ -170,7 +171,8 @@ def test_attn_temporal(B, T, HW, heads):
 # ------------------------------------------------------------------------------------------ norms & elementwise
 @pytest.mark.parametrize("rows,rps,C1,C2,silu", [(4 * 144, 144, 320, 0, True), (2 * 576, 576, 640, 320, True),
                                                  (2 * 5 * 64, 5 * 64, 1280, 0, False), (512, 256, 128, 0, True),
-                                                 (3 * 300, 300, 1280, 640, True)])
+                                                 (3 * 300, 300, 1280, 640, True), (2 * 5000, 5000, 320, 0, True),
+                                                 (2 * 3 * 16, 3 * 16, 64, 0, False), (2 * 700, 700, 1280, 1280, True)])
 def test_groupnorm(rows, rps, C1, C2, silu):
     lib = L()
     x1 = rnd(rows, C1, scale=2.0) + 0.5
@@ -186,7 +188,8 @@ def test_groupnorm(rows, rps, C1, C2, silu):
     close(out, ref, 4e-3, 4e-3, "groupnorm")
 
 
-@pytest.mark.parametrize("rows,C,with_add", [(1000, 320, False), (777, 640, True), (300, 1280, True)])
+@pytest.mark.parametrize("rows,C,with_add", [(1000, 320, False), (777, 640, True), (300, 1280, True), (99, 64, True),
+                                             (65, 256, False), (40, 2048, True)])
 def test_layernorm(rows, C, with_add):
     lib = L()
     x = rnd(rows, C, scale=2.0)
