@@ -31,7 +31,6 @@ int attn_spatial_v1(const void* qkv, void* out, int32_t frames, int32_t L, int32
 
 namespace v2 {
 
-constexpr int kThreads = 320;  // 2 role warps + 2 x 4 softmax warps: 204 registers per thread available
 constexpr int kKVStages = 3;
 constexpr uint32_t kTile = 128 * 64 * 2;  // 16 KB
 constexpr uint32_t kPBytes = 2 * kTile;   // one 128 x 128 fp16 P tile
@@ -48,7 +47,12 @@ MOFA_DEVICE float max3(float a, float b, float c) {
     return d;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+// kPolyEvery: every kPolyEvery-th pair of probabilities is computed by poly_exp2 on the FMA pipe instead of MUFU.EX2
+// (0 = none); kHandoff: alternate the exp phases of the two warps that share an SM sub-partition.
+// kSplit: threads per query row (1: 8 softmax warps, 128 scores per thread; 2: 16 softmax warps, 64 scores per thread,
+// the two halves of a row exchange their maxima / sums through shared memory).
+template <int kPolyEvery, bool kHandoff, int kSplit>
+__global__ void __launch_bounds__(64 + 256 * kSplit, 1)
 attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -64,6 +68,12 @@ attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
     uint64_t* p_full = s_free + 2;            // [2] P_j in shared memory (and O rescaled if needed)
     uint64_t* o_full = p_full + 2;            // [2] P_j V_j accumulated
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + 2);
+    float* fence_slots = reinterpret_cast<float*>(tmem_ptr_smem + 4);  // one word per thread (see the MUFU hand-off)
+    float* xchg = fence_slots + 64 + 256 * 2;  // [2 slots][2 tiles][2 halves][128 rows] (kSplit == 2)
+    static_assert(kSplit == 1 || kSplit == 2, "kSplit");
+    static_assert(!(kHandoff && kSplit == 2), "the hand-off pairs the two warps of a sub-partition: kSplit == 1 only");
+    constexpr int kCols = 128 / kSplit;  // scores per thread and KV tile
+    constexpr int kOc = 64 / kSplit;     // O columns per thread
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -81,8 +91,8 @@ attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s_full[i], 1);
-            mbar_init(&s_free[i], 128);
-            mbar_init(&p_full[i], 128);
+            mbar_init(&s_free[i], 128 * kSplit);
+            mbar_init(&p_full[i], 128 * kSplit);
             mbar_init(&o_full[i], 1);
         }
         fence_barrier_init();
@@ -182,35 +192,63 @@ attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
             if (!progress) __nanosleep(20);
         }
     } else if (warp >= 2) {
-        // ===================== softmax warpgroups =====================
-        const int w = (warp - 2) >> 2;  // query tile of this warpgroup
-        const int qd = warp & 3;
+        // ===================== softmax warps =====================
+        const int sw = warp - 2;
+        const int w = sw / (4 * kSplit);   // query tile
+        const int half = (sw >> 2) % kSplit;  // which kCols-wide slice of the score row
+        const int qd = warp & 3;           // TMEM lane quarter this warp may access
         const int r = qd * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
-        const uint32_t ts = tmem_S + lane_addr + w * 128;
-        const uint32_t to = tmem_O + lane_addr + w * 64;
-        uint8_t* prow = sP + w * kPBytes + r * 128;
+        const uint32_t ts = tmem_S + lane_addr + w * 128 + half * kCols;
+        const uint32_t to = tmem_O + lane_addr + w * 64 + half * kOc;
+        const uint32_t prow = smem_u32(sP + w * kPBytes + r * 128);
         const float sl2 = p.scale_log2;
         float m = -INFINITY, l = 0.f;
+        const uint32_t fence_slot = smem_u32(fence_slots + threadIdx.x);
+        // MUFU hand-off between the two warps that share an SM sub-partition (this warp and warp +-4): their exp
+        // phases strictly alternate, so one streams ex2 at the pipe's full rate while the other loads S / finds the
+        // maximum / stores P.  Left alone they fall into lockstep and the MUFU idles ~40 % of the time.
+        const int bar_mine = 1 + 2 * qd + w, bar_other = 1 + 2 * qd + (1 - w);
+        if (kHandoff && w == 1) asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory");
+        // kSplit == 2: the two warps holding the halves of the same rows meet at named barrier 1 + 4w + qd
+        const int bar_pair = 1 + 4 * w + qd;
+        const uint32_t x_mine = smem_u32(xchg + (w * 2 + half) * 128 + r);
+        const uint32_t x_peer = smem_u32(xchg + (w * 2 + (1 - half)) * 128 + r);
 
         for (int j = 0; j < n_kv; ++j) {
             mbar_wait(&s_full[w], j & 1);
             tc_fence_after();
-            uint32_t s[128];
+            uint32_t s[kCols];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld_32x32(ts + c * 32, reinterpret_cast<uint32_t(&)[32]>(s[c * 32]));
+            for (int c = 0; c < kCols / 32; ++c)
+                tmem_ld_32x32(ts + c * 32, reinterpret_cast<uint32_t(&)[32]>(s[c * 32]));
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(&s_free[w]);  // S_{j+1} may now overwrite the TMEM buffer
-            const int kv_valid = p.L - j * 128;
-            if (kv_valid < 128) {  // warp-uniform: ragged last tile
+            const int kv_valid = p.L - j * 128 - half * kCols;
+            if (kv_valid < kCols) {  // warp-uniform: ragged last tile
 #pragma unroll
-                for (int i = 0; i < 128; ++i)
+                for (int i = 0; i < kCols; ++i)
                     if (i >= kv_valid) s[i] = 0xff800000u;  // -inf
             }
-            float mx = -INFINITY;
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four chains: FMNMX3 latency, not issue
 #pragma unroll
-            for (int i = 0; i < 128; i += 2) mx = max3(mx, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+            for (int i = 0; i < kCols; i += 8) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    mx4[q] = max3(mx4[q], __uint_as_float(s[i + 2 * q]), __uint_as_float(s[i + 2 * q + 1]));
+            }
+            float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            if (kSplit == 2) {
+                // both halves must use the same reference maximum; slots alternate with j so a fast warp cannot
+                // overwrite a value its peer has not read yet
+                const uint32_t slot = static_cast<uint32_t>(j & 1) * (2 * 2 * 128 * 4);
+                float other;
+                asm volatile("st.volatile.shared.f32 [%0], %1;" ::"r"(x_mine + slot), "f"(mx) : "memory");
+                asm volatile("bar.sync %0, 64;" ::"r"(bar_pair) : "memory");
+                asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(other) : "r"(x_peer + slot) : "memory");
+                mx = fmaxf(mx, other);
+            }
             mx *= sl2;
             // lazy rescale: move the reference maximum only when it grows by more than 2^8
             float alpha = 1.0f;
@@ -219,13 +257,47 @@ attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
                 m = mx;
             }
             l *= alpha;
+            // exponentials first (registers only): they overlap P_{j-1} V_{j-1}, which still reads the P buffer
+            float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+            uint32_t packed[kCols / 2];
+            // the reference maximum takes a round trip through shared memory across the barrier (and the row sum is
+            // stored before the arrive below): ptxas keeps shared-memory accesses ordered around BAR, so the
+            // exponentials can neither be hoisted above the hand-off nor sunk below it
+            float m_x = m;
+            if (kHandoff) {
+                asm volatile("st.volatile.shared.f32 [%0], %1;" ::"r"(fence_slot), "f"(m) : "memory");
+                asm volatile("bar.sync %0, 64;" ::"r"(bar_mine) : "memory");
+                asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(m_x) : "r"(fence_slot) : "memory");
+            }
+#pragma unroll
+            for (int i = 0; i < kCols / 2; ++i) {
+                const float x0 = fmaf(__uint_as_float(s[2 * i]), sl2, -m_x);
+                const float x1 = fmaf(__uint_as_float(s[2 * i + 1]), sl2, -m_x);
+                const bool poly = kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == 0;
+                const float p0 = poly ? poly_exp2(x0) : fast_exp2(x0);
+                const float p1 = poly ? poly_exp2(x1) : fast_exp2(x1);
+                if (i & 1) {
+                    sum2 += p0;
+                    sum3 += p1;
+                } else {
+                    sum0 += p0;
+                    sum1 += p1;
+                }
+                const __half2 h = __floats2half2_rn(p0, p1);
+                packed[i] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            const float l_tile = (sum0 + sum1) + (sum2 + sum3);
+            if (kHandoff) {
+                asm volatile("st.volatile.shared.f32 [%0], %1;" ::"r"(fence_slot), "f"(l_tile) : "memory");
+                if (w == 0 || j + 1 < n_kv) asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory");
+            }
             if (j > 0) {
                 // P_{j-1} V_{j-1} done: the P buffer may be overwritten and O is stable
                 mbar_wait(&o_full[w], (j - 1) & 1);
                 tc_fence_after();
                 if (__any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll 1
-                    for (int c = 0; c < 8; ++c) {
+                    for (int c = 0; c < kOc / 8; ++c) {
                         uint32_t v[8];
                         tmem_ld_32x8(to + c * 8, v);
                         tmem_ld_wait();
@@ -236,35 +308,34 @@ attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
                     tmem_st_wait();
                 }
             }
-            float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-            for (int g = 0; g < 16; ++g) {
-                uint32_t packed[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float p0 = fast_exp2(fmaf(__uint_as_float(s[g * 8 + 2 * i]), sl2, -m));
-                    const float p1 = fast_exp2(fmaf(__uint_as_float(s[g * 8 + 2 * i + 1]), sl2, -m));
-                    sum0 += p0;
-                    sum1 += p1;
-                    const __half2 h = __floats2half2_rn(p0, p1);
-                    packed[i] = *reinterpret_cast<const uint32_t*>(&h);
-                }
-                const int col0 = g * 8;
-                uint8_t* dst = prow + (col0 >> 6) * kTile + ((((col0 & 63) >> 3) ^ (r & 7)) << 4);
-                *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            for (int g = 0; g < kCols / 8; ++g) {
+                const int col0 = half * kCols + g * 8;
+                const uint32_t dst = prow + (col0 >> 6) * kTile + ((((col0 & 63) >> 3) ^ (r & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[4 * g]),
+                             "r"(packed[4 * g + 1]), "r"(packed[4 * g + 2]), "r"(packed[4 * g + 3])
+                             : "memory");
             }
-            l += sum0 + sum1;
+            l += l_tile;
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(&p_full[w]);
+        }
+        if (kSplit == 2) {  // total row sum = sum of the two halves (both are relative to the same maximum)
+            const uint32_t slot = static_cast<uint32_t>(n_kv & 1) * (2 * 2 * 128 * 4);
+            float other;
+            asm volatile("st.volatile.shared.f32 [%0], %1;" ::"r"(x_mine + slot), "f"(l) : "memory");
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_pair) : "memory");
+            asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(other) : "r"(x_peer + slot) : "memory");
+            l += other;
         }
         mbar_wait(&o_full[w], (n_kv - 1) & 1);
         tc_fence_after();
         const int qrow = q0 + w * 128 + r;
         const float inv = 1.0f / l;
-        __half* dst = p.out + (static_cast<long long>(frame) * p.L + qrow) * p.C + head * 64;
+        __half* dst = p.out + (static_cast<long long>(frame) * p.L + qrow) * p.C + head * 64 + half * kOc;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < kOc / 32; ++c) {
             uint32_t v[32];
             tmem_ld_32x32(to + c * 32, v);
             tmem_ld_wait();
@@ -324,18 +395,45 @@ extern "C" int mofa_attn_spatial(const void* qkv, void* out, int32_t frames, int
     p.heads = heads;
     p.n_kv = (L + 127) / 128;
     p.scale_log2 = scale * 1.4426950408889634f;
-    const size_t smem_bytes = 2 * v2::kTile + v2::kKVStages * 2 * v2::kTile + 2 * v2::kPBytes + 16 * 8 + 16 + 1024;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(v2::attn_spatial2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    const size_t smem_bytes = 2 * v2::kTile + v2::kKVStages * 2 * v2::kTile + 2 * v2::kPBytes + 16 * 8 + 16 +
+                              (64 + 256 * 2) * 4 + 2 * 2 * 2 * 128 * 4 + 1024;
+    // variants (environment, read once): MOFA_ATTN_SPLIT = 1 | 2 threads per query row, MOFA_ATTN_HANDOFF = 0 | 1
+    // (kSplit 1 only), MOFA_ATTN_POLY = 0 | 2 | 4 (share of exponentials on the FMA pipe: none, 1/2, 1/4).
+    // Defaults are the measured best on B200 (profiles/).
+    using Kern = void (*)(const CUtensorMap, const v2::Params);
+    static Kern kern = nullptr;
+    static int threads = 0;
+    if (!kern) {
+        const char* ep = getenv("MOFA_ATTN_POLY");
+        const char* eh = getenv("MOFA_ATTN_HANDOFF");
+        const char* es = getenv("MOFA_ATTN_SPLIT");
+        const int poly = ep ? atoi(ep) : 0;
+        const int split = es ? atoi(es) : 1;
+        const bool handoff = eh ? (eh[0] == '1') : true;
+        Kern k;
+        if (split == 2) {
+            k = poly == 2   ? v2::attn_spatial2_kernel<2, false, 2>
+                : poly == 4 ? v2::attn_spatial2_kernel<4, false, 2>
+                            : v2::attn_spatial2_kernel<0, false, 2>;
+        } else if (handoff) {
+            k = poly == 2   ? v2::attn_spatial2_kernel<2, true, 1>
+                : poly == 4 ? v2::attn_spatial2_kernel<4, true, 1>
+                            : v2::attn_spatial2_kernel<0, true, 1>;
+        } else {
+            k = poly == 2   ? v2::attn_spatial2_kernel<2, false, 1>
+                : poly == 4 ? v2::attn_spatial2_kernel<4, false, 1>
+                            : v2::attn_spatial2_kernel<0, false, 1>;
+        }
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem_bytes));
         if (e != cudaSuccess) {
             set_last_error("mofa_attn_spatial: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return MOFA_ERR_CUDA;
         }
-        configured = true;
+        kern = k;
+        threads = 64 + 256 * (split == 2 ? 2 : 1);
     }
     dim3 grid((L + 255) / 256, heads, frames);
-    v2::attn_spatial2_kernel<<<grid, v2::kThreads, smem_bytes, stream>>>(tm, p);
+    kern<<<grid, threads, smem_bytes, stream>>>(tm, p);
     return check_launch("mofa_attn_spatial");
 }

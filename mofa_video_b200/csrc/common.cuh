@@ -246,6 +246,18 @@ MOFA_DEVICE float fast_exp2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// 2^x for x <= 0 on the FMA / integer pipes only (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, cubic
+// minimax for 2^f (relative error 7.5e-5, below the fp16 resolution of the probabilities it feeds), n added to the
+// exponent field.  x is clamped at -126 (results there are ~1e-38, i.e. zero after the fp16 conversion).
+MOFA_DEVICE float poly_exp2(float x) {
+    x = fmaxf(x, -126.0f);
+    const float r = x + 12582912.0f;  // 1.5 * 2^23: the integer part lands in the low mantissa bits
+    const float f = x - (r - 12582912.0f);
+    float q = fmaf(0.05517027f, f, 0.24260795f);
+    q = fmaf(q, f, 0.69326093f);
+    q = fmaf(q, f, 0.99992828f);
+    return __int_as_float(__float_as_int(q) + (__float_as_int(r) << 23));
+}
 MOFA_DEVICE float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 // erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below fp16 output resolution): 2 MUFU + ~10 FMA-pipe
 // instructions instead of libm erff's two-branch polynomial -- the GEGLU epilogue is instruction-issue bound.
