@@ -31,7 +31,7 @@ int attn_spatial_v1(const void* qkv, void* out, int32_t frames, int32_t L, int32
 
 namespace v2 {
 
-constexpr int kKVStages = 3;
+constexpr int kKVStages = 5;
 constexpr uint32_t kTile = 128 * 64 * 2;  // 16 KB
 constexpr uint32_t kPBytes = 2 * kTile;   // one 128 x 128 fp16 P tile
 
@@ -58,8 +58,7 @@ attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;                              // 2 x 16 KB
     uint8_t* sKV = sQ + 2 * kTile;                   // kKVStages x (K | V)
-    uint8_t* sP = sKV + kKVStages * 2 * kTile;       // 2 x 32 KB (one per query tile)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + kKVStages * 2 * kTile);
     uint64_t* q_full = bars;
     uint64_t* kv_full = bars + 1;
     uint64_t* kv_empty = kv_full + kKVStages;
@@ -104,6 +103,7 @@ attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
     const uint32_t tmem_base = *tmem_ptr_smem;
     const uint32_t tmem_S = tmem_base;        // 2 x 128 columns
     const uint32_t tmem_O = tmem_base + 256;  // 2 x 64 columns
+    const uint32_t tmem_P = tmem_base + 384;  // 2 x 64 columns: P as packed fp16 pairs, the A operand of P V
 
     if (threadIdx.x == 0) {
         // ===================== TMA producer =====================
@@ -170,12 +170,10 @@ attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
                     tc_fence_after();
                     const uint32_t va = smem_u32(sKV + jp_stage[w] * 2 * kTile + kTile);
                     const uint64_t dv = umma_desc_sw128_mnmajor(va, kTile);
-                    const uint32_t pa = smem_u32(sP + w * kPBytes);
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) {
-                        const uint64_t dp = umma_desc_sw128_kmajor(pa + (kk >> 2) * kTile) + 2 * (kk & 3);
-                        umma_f16_ss(tmem_O + w * 64, dp, dv + 128 * kk, idesc_o, (jp[w] > 0) || (kk != 0));
-                    }
+                    for (int kk = 0; kk < 8; ++kk)  // 16 keys per step = 8 TMEM columns of packed P
+                        umma_f16_ts(tmem_O + w * 64, tmem_P + w * 64 + kk * 8, dv + 128 * kk, idesc_o,
+                                    (jp[w] > 0) || (kk != 0));
                     umma_commit(&o_full[w]);
                     ++jp[w];
                     if (++jp_stage[w] == kKVStages) jp_stage[w] = 0;
@@ -201,7 +199,7 @@ attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
         const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
         const uint32_t ts = tmem_S + lane_addr + w * 128 + half * kCols;
         const uint32_t to = tmem_O + lane_addr + w * 64 + half * kOc;
-        const uint32_t prow = smem_u32(sP + w * kPBytes + r * 128);
+        const uint32_t tp = tmem_P + lane_addr + w * 64 + half * (kCols / 2);
         const float sl2 = p.scale_log2;
         float m = -INFINITY, l = 0.f;
         const uint32_t fence_slot = smem_u32(fence_slots + threadIdx.x);
@@ -309,15 +307,10 @@ attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
                 }
             }
 #pragma unroll
-            for (int g = 0; g < kCols / 8; ++g) {
-                const int col0 = half * kCols + g * 8;
-                const uint32_t dst = prow + (col0 >> 6) * kTile + ((((col0 & 63) >> 3) ^ (r & 7)) << 4);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[4 * g]),
-                             "r"(packed[4 * g + 1]), "r"(packed[4 * g + 2]), "r"(packed[4 * g + 3])
-                             : "memory");
-            }
+            for (int c = 0; c < kCols / 64; ++c)
+                tmem_st_32x32(tp + c * 32, reinterpret_cast<const uint32_t(&)[32]>(packed[c * 32]));
+            tmem_st_wait();
             l += l_tile;
-            fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(&p_full[w]);
         }
@@ -395,7 +388,7 @@ extern "C" int mofa_attn_spatial(const void* qkv, void* out, int32_t frames, int
     p.heads = heads;
     p.n_kv = (L + 127) / 128;
     p.scale_log2 = scale * 1.4426950408889634f;
-    const size_t smem_bytes = 2 * v2::kTile + v2::kKVStages * 2 * v2::kTile + 2 * v2::kPBytes + 16 * 8 + 16 +
+    const size_t smem_bytes = 2 * v2::kTile + v2::kKVStages * 2 * v2::kTile + 16 * 8 + 16 +
                               (64 + 256 * 2) * 4 + 2 * 2 * 2 * 128 * 4 + 1024;
     // variants (environment, read once): MOFA_ATTN_SPLIT = 1 | 2 threads per query row, MOFA_ATTN_HANDOFF = 0 | 1
     // (kSplit 1 only), MOFA_ATTN_POLY = 0 | 2 | 4 (share of exponentials on the FMA pipe: none, 1/2, 1/4).
