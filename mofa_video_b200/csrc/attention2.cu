@@ -1,20 +1,29 @@
 // Spatial self-attention (head_dim 64), two 128-query tiles per CTA.
 //
-// With head_dim 64 the kernel is bound by the exponential (MUFU: 16 ex2 / clk / SM -> 2048 clk per 256 x 128 score
-// block) and by instruction issue of the softmax warps, not by the tensor core (1024 clk for the same block).  The
-// structure therefore keeps the MUFU busy and trims everything else:
-//   * one query row per thread, the 128 scores of a tile are read from TMEM ONCE into registers; the S buffer is
+// With head_dim 64 the kernel is bound by the exponential (MUFU.EX2: one warp instruction per 8 clk per SM
+// sub-partition, measured by tools/microbench/mufu_rate.cu -> 2048 clk per 256 x 128 score block) and by the latency
+// chain around it, not by the tensor core (1024 clk for the same block).  Structure:
+//   * one query row per thread; the 128 scores of a tile are read from TMEM ONCE into registers and the S buffer is
 //     released right after that read (s_free), so S_{j+1} = Q K_{j+1}^T is computed while the exponentials of tile j
 //     run -- the registers act as the second S buffer;
-//   * O accumulates in TMEM across KV tiles (tcgen05.mma accumulate), no per-tile read-back; the running maximum is
-//     lazy (moved only when it grows by more than 2^8, P <= 256 stays inside fp16), so the O rescale -- a TMEM
-//     load / scale / store by the owning warp -- happens on the first one or two tiles only;
+//   * P never touches shared memory: the packed fp16 probabilities are written back to tensor memory (tcgen05.st)
+//     and consumed as the A operand of the P V MMA (tcgen05.mma with A in TMEM); V is the MN-major B operand, read in
+//     place from the TMA tile.  Shared-memory traffic per 256 x 128 block drops from 256 KB to 128 KB;
+//   * O accumulates in TMEM across KV tiles, no per-tile read-back; the running maximum is lazy (moved only when it
+//     grows by more than 2^8, P <= 256 stays inside fp16), so the O rescale -- a TMEM load / scale / store by the
+//     owning warp -- happens on the first one or two tiles only;
 //   * the MMA-issuing thread multiplexes four barriers (s_free / p_full of both query tiles) with non-blocking probes
-//     and issues whatever is ready, so neither softmax warpgroup waits behind the other;
-//   * masking only on the ragged last tile, 3-input max, row sums of the unrounded probabilities.
+//     and issues whatever is ready;
+//   * the two softmax warps that share an SM sub-partition (one per query tile) hand the MUFU over explicitly
+//     (named barriers): their exp phases alternate instead of drifting into lockstep (+8 %);
+//   * masking only on the ragged last tile, 3-input max, four independent max / sum chains.
+// TMEM: S 2 x 128 | O 2 x 64 | P 2 x 64 columns = 512.
+// Tried and measured slower on B200 (profiles/r1_attention_experiments.md): exp2 on the FMA pipe for 1/4..1/2 of the
+// scores (issue-bound), two threads per row (16 softmax warps), row sums through 16 extra all-ones B columns,
+// softmax warpgroups issuing their own MMAs.
 //
-//   warp 0 (1 lane) : TMA producer   Q0,Q1 once; K/V tiles through a 3-stage ring
-//   warp 1 (1 lane) : MMA issuer     S_w = Q_w K^T (TMEM 2 x 128 cols), O_w += P_w V (TMEM 2 x 64 cols)
+//   warp 0 (1 lane) : TMA producer   Q0,Q1 once; K/V tiles through a 5-stage ring
+//   warp 1 (1 lane) : MMA issuer     S_w = Q_w K^T, O_w += P_w V
 //   warps 2..5      : softmax warpgroup 0 (query tile 0), one row per thread
 //   warps 6..9      : softmax warpgroup 1 (query tile 1)
 #include "../../include/mofa_b200.h"
