@@ -114,8 +114,12 @@ def _cpu_sample(steps, warmup, frames_per_half=2, budget_s=60.0):
     ids = torch.tensor([[6.0, 128.0, 0.02]] * 2)
     t = torch.tensor(1.6377)
     # (height, width, per-frame step FLOPs relative to 576x1024): from SURVEY.md App. B, conv+linear 173.8 TF
-    # scale with the token count, attention 43.4 TF with its square: (173.8/4 + 43.4/16)/217.2 = 0.212, etc.
-    shapes = [(H, W, 1.0), (H // 2, W // 2, 0.212), (H // 4, W // 4, 0.0505)]
+    # scale with the token count r, attention 43.4 TF with its square: (173.8 r + 43.4 r^2)/217.2.  Heights and widths
+    # must stay multiples of 64 (flow pyramid down to 1/64, FCN.py:302-315).
+    def rel_flops(hh, ww):
+        r = (hh * ww) / float(H * W)
+        return (173.8 * r + 43.4 * r * r) / 217.2
+    shapes = [(H, W, 1.0)] + [(hh, ww, rel_flops(hh, ww)) for hh, ww in ((320, 512), (128, 256)) if hh < H and ww < W]
 
     def make(hh, ww):
         sample = torch.randn(2, Tm, 8, hh // 8, ww // 8, generator=g)

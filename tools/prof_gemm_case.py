@@ -32,6 +32,12 @@ elif case == "proj320res":
     out = torch.empty(M, 320, dtype=torch.half, device=dev)
     fn = lambda: lib.linear(a, w, out, bias=b, res1=r)
     flops = 2.0 * M * 320 * 320
+elif case == "proj320rb":  # attention out-projection + collapsed cross-attention vector + residual (rb=1, res=1)
+    a, w, b, r = h(M, 320), h(320, 320), h(320), h(M, 320)
+    rb = h(2, 320)
+    out = torch.empty(M, 320, dtype=torch.half, device=dev)
+    fn = lambda: lib.linear(a, w, out, bias=b, res1=r, rowbias=rb, rows_per_group=M // 2)
+    flops = 2.0 * M * 320 * 320
 elif case == "ff2":
     a, w, b, r = h(M, 1280), h(320, 1280), h(320), h(M, 320)
     out = torch.empty(M, 320, dtype=torch.half, device=dev)
