@@ -30,163 +30,171 @@ __device__ __forceinline__ const __half* gn_src(const __half* x1, int C1, const 
     return x2 + (c - C1);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 groupnorm_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2,
-                       long long rows_per_stat, int rows_per_block, int groups, float* __restrict__ stats) {
+                       long long rows_per_stat, int rows_per_block, int slabs_per_stat, long long n_slabs, int groups,
+                       float* __restrict__ stats) {
+    constexpr int kU = 8;  // independent 16-byte loads in flight per thread
     const int C = C1 + C2;
     const int vecs = C >> 3;
     const int cpg = C / groups;
     const int VX = blockDim.x, VY = blockDim.y;
     const int tx = threadIdx.x, ty = threadIdx.y;
-    const long long s = blockIdx.y;
-    const long long r_begin = static_cast<long long>(blockIdx.x) * rows_per_block;
-    long long r_end = r_begin + rows_per_block;
-    if (r_end > rows_per_stat) r_end = rows_per_stat;
-    const long long row0 = s * rows_per_stat;
-
     __shared__ float s_sum[64], s_sq[64];
     const int tid = ty * VX + tx;
-    if (tid < 64) {
-        s_sum[tid] = 0.f;
-        s_sq[tid] = 0.f;
-    }
-    __syncthreads();
 
-    for (int vec = tx; vec < vecs; vec += VX) {
-        const int c = vec << 3;
-        long long ld;
-        const __half* base = gn_src(x1, C1, x2, C2, c, ld) + row0 * ld;
-        float sum[8], sq[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
-        long long r = r_begin + ty;
-        for (; r + static_cast<long long>(kGnUnroll - 1) * VY < r_end; r += static_cast<long long>(kGnUnroll) * VY) {
-            V8 v[kGnUnroll];
-#pragma unroll
-            for (int u = 0; u < kGnUnroll; ++u)
-                v[u].u = __ldg(reinterpret_cast<const uint4*>(base + (r + static_cast<long long>(u) * VY) * ld));
-#pragma unroll
-            for (int u = 0; u < kGnUnroll; ++u)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 f = __half22float2(v[u].h2[j]);
-                    sum[2 * j] += f.x;
-                    sq[2 * j] = fmaf(f.x, f.x, sq[2 * j]);
-                    sum[2 * j + 1] += f.y;
-                    sq[2 * j + 1] = fmaf(f.y, f.y, sq[2 * j + 1]);
-                }
+    // persistent: the grid is sized to the machine (no partial last wave), slabs are dealt round-robin
+    for (long long slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
+        const long long s = slab / slabs_per_stat;
+        const long long r_begin = (slab - s * slabs_per_stat) * rows_per_block;
+        long long r_end = r_begin + rows_per_block;
+        if (r_end > rows_per_stat) r_end = rows_per_stat;
+        const long long row0 = s * rows_per_stat;
+        if (tid < 64) {
+            s_sum[tid] = 0.f;
+            s_sq[tid] = 0.f;
         }
-        for (; r < r_end; r += VY) {
-            V8 v;
-            v.u = __ldg(reinterpret_cast<const uint4*>(base + r * ld));
+        __syncthreads();
+
+        for (int vec = tx; vec < vecs; vec += VX) {
+            const int c = vec << 3;
+            long long ld;
+            const __half* base = gn_src(x1, C1, x2, C2, c, ld) + row0 * ld;
+            float sum[8], sq[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
+            long long r = r_begin + ty;
+            for (; r + static_cast<long long>(kU - 1) * VY < r_end; r += static_cast<long long>(kU) * VY) {
+                V8 v[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u)
+                    v[u].u = __ldg(reinterpret_cast<const uint4*>(base + (r + static_cast<long long>(u) * VY) * ld));
+#pragma unroll
+                for (int u = 0; u < kU; ++u)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = __half22float2(v[u].h2[j]);
+                        sum[2 * j] += f.x;
+                        sq[2 * j] = fmaf(f.x, f.x, sq[2 * j]);
+                        sum[2 * j + 1] += f.y;
+                        sq[2 * j + 1] = fmaf(f.y, f.y, sq[2 * j + 1]);
+                    }
+            }
+            for (; r < r_end; r += VY) {
+                V8 v;
+                v.u = __ldg(reinterpret_cast<const uint4*>(base + r * ld));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float f = __half2float(v.h[j]);
+                    sum[j] += f;
+                    sq[j] = fmaf(f, f, sq[j]);
+                }
+            }
+            // flush: merge the channels of one group before touching shared memory (cpg >= 8: at most two groups)
+            int g_prev = c / cpg;
+            float a_sum = 0.f, a_sq = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float f = __half2float(v.h[j]);
-                sum[j] += f;
-                sq[j] = fmaf(f, f, sq[j]);
+                const int g = (c + j) / cpg;
+                if (g != g_prev) {
+                    atomicAdd(&s_sum[g_prev], a_sum);
+                    atomicAdd(&s_sq[g_prev], a_sq);
+                    a_sum = a_sq = 0.f;
+                    g_prev = g;
+                }
+                a_sum += sum[j];
+                a_sq += sq[j];
             }
+            atomicAdd(&s_sum[g_prev], a_sum);
+            atomicAdd(&s_sq[g_prev], a_sq);
         }
-        // flush: merge the channels of one group before touching shared memory (cpg >= 8: at most two groups)
-        int g_prev = c / cpg;
-        float a_sum = 0.f, a_sq = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int g = (c + j) / cpg;
-            if (g != g_prev) {
-                atomicAdd(&s_sum[g_prev], a_sum);
-                atomicAdd(&s_sq[g_prev], a_sq);
-                a_sum = a_sq = 0.f;
-                g_prev = g;
-            }
-            a_sum += sum[j];
-            a_sq += sq[j];
+        __syncthreads();
+        if (tid < groups) {
+            atomicAdd(&stats[(s * groups + tid) * 2 + 0], s_sum[tid]);
+            atomicAdd(&stats[(s * groups + tid) * 2 + 1], s_sq[tid]);
         }
-        atomicAdd(&s_sum[g_prev], a_sum);
-        atomicAdd(&s_sq[g_prev], a_sq);
-    }
-    __syncthreads();
-    if (tid < groups) {
-        atomicAdd(&stats[(s * groups + tid) * 2 + 0], s_sum[tid]);
-        atomicAdd(&stats[(s * groups + tid) * 2 + 1], s_sq[tid]);
+        __syncthreads();
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 groupnorm_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2,
                        const __half* __restrict__ gamma, const __half* __restrict__ beta, __half* __restrict__ out,
-                       long long rows_per_stat, int rows_per_block, int groups, float eps, int silu,
-                       const float* __restrict__ stats) {
+                       long long rows_per_stat, int rows_per_block, int slabs_per_stat, long long n_slabs, int groups,
+                       float eps, int silu, const float* __restrict__ stats) {
     const int C = C1 + C2;
     const int vecs = C >> 3;
     const int cpg = C / groups;
     const int VX = blockDim.x, VY = blockDim.y;
     const int tx = threadIdx.x, ty = threadIdx.y;
-    const long long s = blockIdx.y;
-    const long long r_begin = static_cast<long long>(blockIdx.x) * rows_per_block;
-    long long r_end = r_begin + rows_per_block;
-    if (r_end > rows_per_stat) r_end = rows_per_stat;
-    const long long row0 = s * rows_per_stat;
     const float inv_cnt = 1.0f / (static_cast<float>(cpg) * static_cast<float>(rows_per_stat));
 
-    for (int vec = tx; vec < vecs; vec += VX) {
-        const int c = vec << 3;
-        long long ld;
-        const __half* base = gn_src(x1, C1, x2, C2, c, ld) + row0 * ld;
-        __half* obase = out + row0 * C + c;
-        V8 gm, bt;
-        gm.u = __ldg(reinterpret_cast<const uint4*>(gamma + c));
-        bt.u = __ldg(reinterpret_cast<const uint4*>(beta + c));
-        float sc[8], sh[8];
-        int gi_prev = -1;
-        float mean = 0.f, rstd = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int gi = (c + j) / cpg;
-            if (gi != gi_prev) {
-                const float sm = stats[(s * groups + gi) * 2 + 0];
-                const float sq = stats[(s * groups + gi) * 2 + 1];
-                mean = sm * inv_cnt;
-                float var = sq * inv_cnt - mean * mean;
-                var = var < 0.f ? 0.f : var;
-                rstd = rsqrtf(var + eps);
-                gi_prev = gi;
-            }
-            sc[j] = rstd * __half2float(gm.h[j]);
-            sh[j] = __half2float(bt.h[j]) - mean * sc[j];
-        }
-        long long r = r_begin + ty;
-        for (; r + static_cast<long long>(kGnUnroll - 1) * VY < r_end; r += static_cast<long long>(kGnUnroll) * VY) {
-            V8 v[kGnUnroll];
-#pragma unroll
-            for (int u = 0; u < kGnUnroll; ++u)
-                v[u].u = __ldg(reinterpret_cast<const uint4*>(base + (r + static_cast<long long>(u) * VY) * ld));
-#pragma unroll
-            for (int u = 0; u < kGnUnroll; ++u) {
-                V8 o;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 f = __half22float2(v[u].h2[j]);
-                    float y0 = fmaf(f.x, sc[2 * j], sh[2 * j]);
-                    float y1 = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
-                    if (silu) {
-                        y0 = silu_f(y0);
-                        y1 = silu_f(y1);
-                    }
-                    o.h2[j] = __floats2half2_rn(y0, y1);
-                }
-                *reinterpret_cast<uint4*>(obase + (r + static_cast<long long>(u) * VY) * C) = o.u;
-            }
-        }
-        for (; r < r_end; r += VY) {
-            V8 v, o;
-            v.u = __ldg(reinterpret_cast<const uint4*>(base + r * ld));
+    for (long long slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
+        const long long s = slab / slabs_per_stat;
+        const long long r_begin = (slab - s * slabs_per_stat) * rows_per_block;
+        long long r_end = r_begin + rows_per_block;
+        if (r_end > rows_per_stat) r_end = rows_per_stat;
+        const long long row0 = s * rows_per_stat;
+        for (int vec = tx; vec < vecs; vec += VX) {
+            const int c = vec << 3;
+            long long ld;
+            const __half* base = gn_src(x1, C1, x2, C2, c, ld) + row0 * ld;
+            __half* obase = out + row0 * C + c;
+            V8 gm, bt;
+            gm.u = __ldg(reinterpret_cast<const uint4*>(gamma + c));
+            bt.u = __ldg(reinterpret_cast<const uint4*>(beta + c));
+            float sc[8], sh[8];
+            int gi_prev = -1;
+            float mean = 0.f, rstd = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                float y = fmaf(__half2float(v.h[j]), sc[j], sh[j]);
-                if (silu) y = silu_f(y);
-                o.h[j] = __float2half_rn(y);
+                const int gi = (c + j) / cpg;
+                if (gi != gi_prev) {
+                    const float sm = stats[(s * groups + gi) * 2 + 0];
+                    const float sq = stats[(s * groups + gi) * 2 + 1];
+                    mean = sm * inv_cnt;
+                    float var = sq * inv_cnt - mean * mean;
+                    var = var < 0.f ? 0.f : var;
+                    rstd = rsqrtf(var + eps);
+                    gi_prev = gi;
+                }
+                sc[j] = rstd * __half2float(gm.h[j]);
+                sh[j] = __half2float(bt.h[j]) - mean * sc[j];
             }
-            *reinterpret_cast<uint4*>(obase + r * C) = o.u;
+            long long r = r_begin + ty;
+            for (; r + static_cast<long long>(kGnUnroll - 1) * VY < r_end; r += static_cast<long long>(kGnUnroll) * VY) {
+                V8 v[kGnUnroll];
+#pragma unroll
+                for (int u = 0; u < kGnUnroll; ++u)
+                    v[u].u = __ldg(reinterpret_cast<const uint4*>(base + (r + static_cast<long long>(u) * VY) * ld));
+#pragma unroll
+                for (int u = 0; u < kGnUnroll; ++u) {
+                    V8 o;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = __half22float2(v[u].h2[j]);
+                        float y0 = fmaf(f.x, sc[2 * j], sh[2 * j]);
+                        float y1 = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
+                        if (silu) {
+                            y0 = silu_f(y0);
+                            y1 = silu_f(y1);
+                        }
+                        o.h2[j] = __floats2half2_rn(y0, y1);
+                    }
+                    *reinterpret_cast<uint4*>(obase + (r + static_cast<long long>(u) * VY) * C) = o.u;
+                }
+            }
+            for (; r < r_end; r += VY) {
+                V8 v, o;
+                v.u = __ldg(reinterpret_cast<const uint4*>(base + r * ld));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float y = fmaf(__half2float(v.h[j]), sc[j], sh[j]);
+                    if (silu) y = silu_f(y);
+                    o.h[j] = __float2half_rn(y);
+                }
+                *reinterpret_cast<uint4*>(obase + r * C) = o.u;
+            }
         }
     }
 }
@@ -529,26 +537,29 @@ extern "C" int mofa_groupnorm(const void* x1, int32_t C1, const void* x2, int32_
     int VY = 256 / VX;
     if (VY < 1) VY = 1;
     dim3 block(VX, VY);
-    auto launch_grid = [&](int rows_per_block) {
-        return dim3(static_cast<unsigned>((rows_per_stat + rows_per_block - 1) / rows_per_block),
-                    static_cast<unsigned>(nstat));
+    // slabs: a few unrolled iterations per thread; the grid is persistent (blocks-per-SM x 148) so there is no partial wave
+    auto plan = [&](int rows_per_thread, int blocks_per_sm, int& rpb, int& slabs_per_stat, long long& n_slabs, int& grid) {
+        long long want = static_cast<long long>(VY) * rows_per_thread;
+        if (want > rows_per_stat) want = rows_per_stat;
+        rpb = static_cast<int>(want < 1 ? 1 : want);
+        slabs_per_stat = static_cast<int>((rows_per_stat + rpb - 1) / rpb);
+        n_slabs = static_cast<long long>(slabs_per_stat) * nstat;
+        const long long cap = 148LL * blocks_per_sm;
+        grid = static_cast<int>(n_slabs < cap ? n_slabs : cap);
     };
-    // slabs sized so every thread streams >= 2 * kGnUnroll rows while the grid still covers the 148 SMs several times
-    auto pick_rows = [&](int want) {
-        long long rpb = want;
-        while (rpb > VY * kGnUnroll && ((rows_per_stat + rpb - 1) / rpb) * nstat < 148LL * 8) rpb >>= 1;
-        if (rpb > rows_per_stat) rpb = rows_per_stat;
-        return static_cast<int>(rpb < 1 ? 1 : rpb);
-    };
-    const int rpb_stats = pick_rows(VY * kGnUnroll * 8);
-    const int rpb_apply = pick_rows(VY * kGnUnroll * 4);
-    groupnorm_stats_kernel<<<launch_grid(rpb_stats), block, 0, stream>>>(
-        static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2, rows_per_stat, rpb_stats, groups, stats);
+    int rpb, sps, grid;
+    long long n_slabs;
+    plan(16, 3, rpb, sps, n_slabs, grid);
+    groupnorm_stats_kernel<<<grid, block, 0, stream>>>(static_cast<const __half*>(x1), C1,
+                                                       static_cast<const __half*>(x2), C2, rows_per_stat, rpb, sps,
+                                                       n_slabs, groups, stats);
     int rc = check_launch("mofa_groupnorm(stats)");
     if (rc) return rc;
-    groupnorm_apply_kernel<<<launch_grid(rpb_apply), block, 0, stream>>>(
+    plan(8, 3, rpb, sps, n_slabs, grid);
+    groupnorm_apply_kernel<<<grid, block, 0, stream>>>(
         static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2, static_cast<const __half*>(gamma),
-        static_cast<const __half*>(beta), static_cast<__half*>(out), rows_per_stat, rpb_apply, groups, eps, silu, stats);
+        static_cast<const __half*>(beta), static_cast<__half*>(out), rows_per_stat, rpb, sps, n_slabs, groups, eps, silu,
+        stats);
     return check_launch("mofa_groupnorm(apply)");
 }
 

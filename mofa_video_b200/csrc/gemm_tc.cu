@@ -100,7 +100,7 @@ union H8 {
 MOFA_DEVICE float apply_act(float v, int act) {
     if (act == 1) return silu_f(v);
     if (act == 3) return fmaxf(v, 0.f);
-    if (act == 4) return __fdividef(1.0f, 1.0f + __expf(-v));
+    if (act == 4) return sigmoid_f(v);
     return v;
 }
 
@@ -417,7 +417,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
                                 } else if (p.act == 4) {
 #pragma unroll
-                                    for (int j = 0; j < 32; ++j) v[j] = __fdividef(1.0f, 1.0f + __expf(-v[j]));
+                                    for (int j = 0; j < 32; ++j) v[j] = sigmoid_f(v[j]);
                                 }
                             }
                         }

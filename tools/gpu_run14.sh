@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for c in geglu320 proj320res proj320rb qkv320 ff2; do timeout 120 python tools/prof_gemm_case.py $c 5; done 2>&1 | tee gpurun_out/gemm_cases.log
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 2 -c 1 -o gpurun_out/prof_geglu320_v3 -f python tools/prof_gemm_case.py geglu320 1 > gpurun_out/ncu_geglu.log 2>&1; echo "ncu geglu exit $?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 2 -c 1 -o gpurun_out/prof_proj320rb_v3 -f python tools/prof_gemm_case.py proj320rb 1 > gpurun_out/ncu_proj.log 2>&1; echo "ncu proj exit $?"
+timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_kernels2_gpu.py tests/test_cmp_gpu.py -q -m gpu -p no:cacheprovider -x 2>&1 | tail -n 4
+for c in geglu320 proj320res qkv320; do timeout 120 python tools/prof_gemm_case.py $c 5; done 2>&1 | tee gpurun_out/gemm_cases.log
+timeout 300 python tools/profile_step.py --steps 2 --warmup 1 --detail > gpurun_out/step_detail.log 2>&1; grep -v "gemm_" gpurun_out/step_detail.log | head -24

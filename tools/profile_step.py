@@ -88,9 +88,10 @@ def main():
     for i in range(a.steps):
         step(a.warmup + i)
     e1.record()
+    enqueue = time.perf_counter() - t0
     torch.cuda.synchronize()
     host = time.perf_counter() - t0
-    print(f"steps={a.steps} device_ms_per_step={e0.elapsed_time(e1) / a.steps:.2f} host_s={host:.2f} "
+    print(f"steps={a.steps} device_ms_per_step={e0.elapsed_time(e1) / a.steps:.2f} host_s={host:.2f} enqueue_s={enqueue:.2f} "
           f"launches_per_step={lib.launch_count() / a.steps:.0f} finite={bool(torch.isfinite(lat.float()).all())}")
     if a.profile:
         rec = lib.profile_stop(detail=a.detail)
