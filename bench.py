@@ -91,7 +91,9 @@ def _cpu_sample(steps, warmup, frames_per_half=2, budget_s=60.0):
     Returns (frames_per_sec, seconds_per_sample, cores, description)."""
     from oracle import fixtures
     from oracle.models import FlowControlNet, UNetSpatioTemporalConditionControlNetModel
-    cores = os.cpu_count() or 1
+    # 32 threads: on the 128-core GPU box the fp32 oracle at these small spatial sizes got slower with more
+    # (160 s per sample with 128 threads, round-1 measurement); `cores` reports the threads actually used
+    cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
     cfg = dict(num_frames=frames_per_half)
     with torch.device("meta"):
