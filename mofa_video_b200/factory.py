@@ -32,13 +32,21 @@ def make_clip_vit_h(projection_dim=1024):
 
 
 def build_synthetic_pipeline(config=None, device="cuda", seed=0, tiny_encoders=False, vae_channels=None,
-                             native_vae=True):
+                             native_vae=True, variant="traj"):
+    """variant: 'traj' (T/pipeline/pipeline.py), 'keypoint' (K/pipeline/svdxt_pipeline_ctrlnet_loop.py, landmark
+    adapter) or 'hybrid' (H/pipeline/pipeline.py, landmark adapter inside the mask + trajectory adapter outside)."""
     cfg_u, sd_u = synthetic.unet_state_dict(config, seed=seed)
     cfg_a, sd_a = synthetic.adapter_state_dict(config, seed=seed + 1)
     unet = UNetSpatioTemporalConditionControlNetModel.from_state_dict(sd_u, cfg_u, device=device)
     del sd_u
-    controlnet = FlowControlNet.from_state_dict(sd_a, cfg_a, device=device)
+    controlnet = FlowControlNet.from_state_dict(sd_a, cfg_a, device=device) if variant != "keypoint" else None
     del sd_a
+    face = None
+    if variant in ("keypoint", "hybrid"):
+        from mofa_video_b200.models.ldmk_ctrlnet import FlowControlNet as LdmkFlowControlNet
+        cfg_l, sd_l = synthetic.ldmk_adapter_state_dict(config, seed=seed + 3)
+        face = LdmkFlowControlNet.from_state_dict(sd_l, cfg_l, device=device)
+        del sd_l
     torch.manual_seed(seed + 2)
     if tiny_encoders:
         vae = AutoencoderKLTemporalDecoder(block_out_channels=vae_channels or (64, 64, 128, 128))
@@ -51,6 +59,15 @@ def build_synthetic_pipeline(config=None, device="cuda", seed=0, tiny_encoders=F
     if native_vae:
         from mofa_video_b200.vae_engine import NativeTemporalDecoderVAE
         vae = NativeTemporalDecoderVAE(vae, device=device)  # decode on the sm_100a kernels; encode stays PyTorch
-    pipe = FlowControlNetPipeline(vae=vae, image_encoder=clip, unet=unet, controlnet=controlnet,
-                                  scheduler=EulerDiscreteScheduler())
+    if variant == "keypoint":
+        from mofa_video_b200.pipeline.svdxt_pipeline_ctrlnet_loop import FlowControlNetPipeline as KeypointPipeline
+        pipe = KeypointPipeline(vae=vae, image_encoder=clip, unet=unet, controlnet=face,
+                                scheduler=EulerDiscreteScheduler())
+    elif variant == "hybrid":
+        from mofa_video_b200.pipeline.pipeline_hybrid import FlowControlNetPipeline as HybridPipeline
+        pipe = HybridPipeline(vae=vae, image_encoder=clip, unet=unet, drag_controlnet=controlnet,
+                              face_controlnet=face, scheduler=EulerDiscreteScheduler())
+    else:
+        pipe = FlowControlNetPipeline(vae=vae, image_encoder=clip, unet=unet, controlnet=controlnet,
+                                      scheduler=EulerDiscreteScheduler())
     return pipe.to(device)

@@ -193,6 +193,35 @@ def adapter_state_dict(config=None, seed=1, dtype=torch.float16, zero_std=0.02):
     return cfg, g.sd
 
 
+def ldmk_adapter_state_dict(config=None, seed=3, dtype=torch.float16, zero_std=0.02):
+    """Keypoint (landmark) adapter: the trajectory adapter's trunk plus the landmark embedding, the per-scale occlusion
+    hourglasses and `zero_outs` (/root/reference/MOFA-Video-Keypoint/models/ldmk_ctrlnet.py:187-254,
+    models/occlusion/hourglass.py:227-246); its flow encoder has no zero-convs (:144-161, use_zeroconv=False)."""
+    cfg, sd = adapter_state_dict(config, seed=seed, dtype=dtype, zero_std=zero_std)
+    for k in [k for k in sd if k.startswith("flow_encoder.zeroconvs.")]:
+        del sd[k]
+    g = _Gen(seed + 100, dtype)
+    boc = tuple(cfg["block_out_channels"])
+    le, lch = "controlnet_ldmk_embedding", (16, 32, 64, 128)
+    g.conv(le + ".conv_in", lch[0], cfg["conditioning_channels"])
+    for b in range(len(lch) - 1):
+        g.conv(f"{le}.blocks.{2 * b}", lch[b], lch[b])
+        g.conv(f"{le}.blocks.{2 * b + 1}", lch[b + 1], lch[b])
+    g.conv(le + ".conv_out", boc[0], lch[-1], std=zero_std)
+    for s_, c in (("8", boc[0]), ("16", boc[0]), ("32", boc[1]), ("64", boc[2])):
+        g.conv(f"zero_outs.{s_}", c, c, k=1, std=zero_std)
+        pre = f"occlusions.{s_}"
+        enc = [2 * c + 2, 128, 256, 512]
+        for i in range(3):
+            g.conv(f"{pre}.hourglass.encoder.down_blocks.{i}.conv", enc[i + 1], enc[i])
+        for i, (cin, cout) in enumerate(((512, 256), (512, 128), (256, 64))):
+            g.conv(f"{pre}.hourglass.decoder.up_blocks.{i}.conv", cout, cin)
+        g.conv(f"{pre}.matting_mask", 1, 64, k=7)
+        g.conv(f"{pre}.matting", c, 64, k=7)
+    sd.update(g.sd)
+    return cfg, sd
+
+
 def cmp_state_dict(seed=2, dtype=torch.float32, prefix="module."):
     """Random-init CMP (ResNet-50-dilated + ShallowNet + MotionDecoderSkipLayer) in the reference checkpoint's
     key layout (`module.` prefix of FixModule, models/cmp/models/modules/others.py:3-10).  BN gamma < 1 keeps the

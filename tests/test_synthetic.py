@@ -28,3 +28,14 @@ def test_full_size_param_count():
     n_u = sum(p.numel() for p in ou.parameters())
     assert n_u == 1_524_623_082  # published SVD-XT UNet size
     assert abs(sum(p.numel() for p in oa.parameters()) - 694.3e6) < 0.1e6
+
+
+def test_ldmk_adapter_keys_match_oracle():
+    from oracle.keypoint import FlowControlNetLdmk
+    cfg = dict(fixtures.TINY_CONFIG)
+    _, sl = synthetic.ldmk_adapter_state_dict(cfg)
+    assert _shapes(sl) == _shapes(FlowControlNetLdmk(**cfg).state_dict())
+    with torch.device("meta"):
+        full = FlowControlNetLdmk()
+    _, sf = synthetic.ldmk_adapter_state_dict({"num_frames": 2}, dtype=torch.float16)
+    assert {k: tuple(v.shape) for k, v in sf.items()} == {k: tuple(v.shape) for k, v in full.state_dict().items()}
