@@ -221,6 +221,11 @@ int mofa_mask_blend(const void* a, const void* b, const void* mask, void* out, i
 /* nearest F.interpolate(scale_factor = 1/s) on channels-last data (landmark embedding pyramid, ldmk_ctrlnet.py:403-407) */
 int mofa_downsample_nearest(const void* x, void* out, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t s,
                             mofa_stream_t stream);
+/* Drag-flow post-processing (/root/reference/MOFA-Video-Traj/run_gradio.py:251-255 brush mask, :268-275 nearest resize
+ * 384^2 -> HxW with per-axis scaling, :330-333 in-mask / out-mask merge), fp16 NCHW [F, 2, ., .]; brush [Hs, Ws] and
+ * flow_out may be NULL */
+int mofa_flow_post(const void* flow_in, const void* brush, const void* flow_out, void* out, int32_t F, int32_t Hs,
+                   int32_t Ws, int32_t H, int32_t W, mofa_stream_t stream);
 
 #ifdef __cplusplus
 }

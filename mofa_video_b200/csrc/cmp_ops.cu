@@ -303,6 +303,72 @@ extern "C" int mofa_mask_blend(const void* a, const void* b, const void* mask, v
     return check_launch("mofa_mask_blend");
 }
 
+namespace mofa {
+// Drag-flow post-processing of T/run_gradio.py:251-277, 330-333 in one pass over the output [F, 2, H, W]:
+// (flow * brush) at 384^2 -> nearest resize -> x (W/Ws, H/Hs), fp16 roundings where the reference has them, then
+// where((flow_in != 0).all(channel), flow_in, flow_out).
+__global__ void __launch_bounds__(256)
+flow_post_kernel(const __half* __restrict__ fin, const __half* __restrict__ brush, const __half* __restrict__ fout,
+                 __half* __restrict__ out, int F, int Hs, int Ws, int H, int W) {
+    const long long total = static_cast<long long>(F) * H * W;
+    const float sx = static_cast<float>(W) / Ws, sy = static_cast<float>(H) / Hs;
+    const bool resize = (H != Hs) || (W != Ws);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(i % W);
+        const int y = static_cast<int>((i / W) % H);
+        const int f = static_cast<int>(i / (static_cast<long long>(W) * H));
+        int ys = static_cast<int>(floorf(y * (static_cast<float>(Hs) / H)));
+        int xs = static_cast<int>(floorf(x * (static_cast<float>(Ws) / W)));
+        ys = ys < Hs - 1 ? ys : Hs - 1;
+        xs = xs < Ws - 1 ? xs : Ws - 1;
+        const long long s0 = (static_cast<long long>(f) * 2 * Hs + ys) * Ws + xs;
+        const long long plane = static_cast<long long>(Hs) * Ws;
+        __half u = fin[s0], v = fin[s0 + plane];
+        if (brush) {
+            const __half b = brush[static_cast<long long>(ys) * Ws + xs];
+            u = __hmul(u, b);
+            v = __hmul(v, b);
+        }
+        if (resize) {
+            u = __float2half_rn(__half2float(u) * sx);
+            v = __float2half_rn(__half2float(v) * sy);
+        }
+        if (fout) {
+            const bool keep = (__half2float(u) != 0.f) && (__half2float(v) != 0.f);
+            if (!keep) {
+                __half uo = fout[s0], vo = fout[s0 + plane];
+                if (resize) {
+                    uo = __float2half_rn(__half2float(uo) * sx);
+                    vo = __float2half_rn(__half2float(vo) * sy);
+                }
+                u = uo;
+                v = vo;
+            }
+        }
+        const long long d0 = (static_cast<long long>(f) * 2 * H + y) * W + x;
+        out[d0] = u;
+        out[d0 + static_cast<long long>(H) * W] = v;
+    }
+}
+}  // namespace mofa
+
+extern "C" int mofa_flow_post(const void* flow_in, const void* brush, const void* flow_out, void* out, int32_t F,
+                              int32_t Hs, int32_t Ws, int32_t H, int32_t W, mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!flow_in || !out || F <= 0 || Hs <= 0 || Ws <= 0 || H <= 0 || W <= 0) {
+        mofa::set_last_error("mofa_flow_post: bad arguments");
+        return MOFA_ERR_ARG;
+    }
+    const long long total = static_cast<long long>(F) * H * W;
+    long long g = (total + 255) / 256;
+    if (g > 148LL * 16) g = 148LL * 16;
+    mofa::flow_post_kernel<<<static_cast<unsigned>(g), 256, 0, stream>>>(
+        static_cast<const __half*>(flow_in), static_cast<const __half*>(brush), static_cast<const __half*>(flow_out),
+        static_cast<__half*>(out), F, Hs, Ws, H, W);
+    return mofa::check_launch("mofa_flow_post");
+}
+
 extern "C" int mofa_downsample_nearest(const void* x, void* out, int32_t n_img, int32_t H, int32_t W, int32_t C,
                                        int32_t s, mofa_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);

@@ -22,7 +22,7 @@ EXPORTS = [
     "mofa_im2col3x3", "mofa_upsample2x", "mofa_nchw_to_nhwc", "mofa_nhwc_to_nchw", "mofa_linear_small",
     "mofa_timestep_embedding", "mofa_softsplat_avg", "mofa_cfg_euler_step", "mofa_softmax_rows",
     "mofa_vae_time_conv_out", "mofa_im2col", "mofa_pool2d", "mofa_resize_bilinear_ac", "mofa_cmp_fuser",
-    "mofa_copy_cols", "mofa_flow_pyramid", "mofa_mask_blend", "mofa_downsample_nearest",
+    "mofa_copy_cols", "mofa_flow_pyramid", "mofa_mask_blend", "mofa_downsample_nearest", "mofa_flow_post",
 ]
 
 
@@ -84,6 +84,7 @@ def load():
     lib.mofa_flow_pyramid.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.mofa_mask_blend.argtypes = [vp, vp, vp, vp, i64, i32, i64, vp]
     lib.mofa_downsample_nearest.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.mofa_flow_post.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     _lib = lib
     return lib
 
@@ -392,4 +393,12 @@ def mask_blend(a, b, mask, out, period_rows=None):
 def downsample_nearest(x, out, n_img, H, W, C, s):
     _chk_h(x, out)
     _check(load().mofa_downsample_nearest(_p(x), _p(out), n_img, H, W, C, s, _stream()), "mofa_downsample_nearest")
+    return out
+
+
+def flow_post(flow_in, out, F, Hs, Ws, H, W, brush=None, flow_out=None):
+    """Fused drag-flow post-processing (brush mask, nearest resize + rescale, in/out merge) on fp16 NCHW flows."""
+    _chk_h(flow_in, out, brush, flow_out)
+    _check(load().mofa_flow_post(_p(flow_in), _p(brush), _p(flow_out), _p(out), F, Hs, Ws, H, W, _stream()),
+           "mofa_flow_post")
     return out

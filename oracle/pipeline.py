@@ -118,3 +118,25 @@ def run_pipeline(vae, image_encoder, unet, controlnet, scheduler, image, control
     frames = torch.cat(frames, dim=0)
     frames = frames.reshape(-1, num_frames, *frames.shape[1:]).permute(0, 2, 1, 3, 4).float()
     return frames
+
+
+def drag_flow_post(flow_inmask, height, width, brush_mask=None, flow_outmask=None):
+    """T/run_gradio.py:251-255 (brush), :268-275 (nearest resize + rescale), :330-333 (merge), restated op for op on
+    [B, T-1, 2, hs, ws] tensors in their own dtype."""
+    def resize(fl):
+        fb, fl_, _, hs, ws = fl.shape
+        if (height, width) == (hs, ws):
+            return fl
+        r = F.interpolate(fl.flatten(0, 1), (height, width), mode="nearest").reshape(fb, fl_, 2, height, width).clone()
+        r[:, :, 0] *= width / ws
+        r[:, :, 1] *= height / hs
+        return r
+    a = flow_inmask
+    if brush_mask is not None:
+        a = a * brush_mask.to(a.dtype)[None, None, None]
+    a = resize(a)
+    if flow_outmask is None:
+        return a
+    b = resize(flow_outmask)
+    keep = (a != 0).all(dim=2).unsqueeze(2).expand_as(a)
+    return torch.where(keep, a, b)

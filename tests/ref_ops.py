@@ -317,3 +317,26 @@ def mask_blend(a, b, mask, out, period_rows=None):
 def downsample_nearest(x, out, n_img, H, W, C, s):
     out.view(n_img, H // s, W // s, C).copy_(x.view(n_img, H, W, C)[:, ::s, ::s])
     return out
+
+
+def flow_post(flow_in, out, F, Hs, Ws, H, W, brush=None, flow_out=None):
+    """T/run_gradio.py:251-255, 268-275, 330-333 in the reference's own op order and fp16 roundings."""
+    import torch.nn.functional as Fn
+
+    def resize(fl):
+        if (H, W) == (Hs, Ws):
+            return fl
+        r = Fn.interpolate(fl.float(), (H, W), mode="nearest").half()
+        r[:, 0] = (r[:, 0].float() * (W / Ws)).half()
+        r[:, 1] = (r[:, 1].float() * (H / Hs)).half()
+        return r
+    a = flow_in.view(F, 2, Hs, Ws)
+    if brush is not None:
+        a = a * brush.view(1, 1, Hs, Ws)
+    a = resize(a)
+    if flow_out is not None:
+        b = resize(flow_out.view(F, 2, Hs, Ws))
+        keep = (a != 0).all(dim=1, keepdim=True).expand_as(a)
+        a = torch.where(keep, a, b)
+    out.view(F, 2, H, W).copy_(a)
+    return out
