@@ -206,15 +206,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_ptr_smem;
     const uint32_t acc_stride = (static_cast<uint32_t>(p.bn) + 31u) & ~31u;
 
-    const int total_tiles = p.m_tiles * p.n_tiles;
+    // Tile order.  Default: tile = cta + i * grid with N fastest, so the CTAs that run concurrently share A tiles in L2.
+    // With several M tiles per CTA each CTA instead walks ALL N tiles of one M tile back to back: the A tile
+    // (K = 320: 80 KB) is re-read from L2 right after its first use instead of racing a neighbour CTA to DRAM
+    // (ncu: 838 MB read for 590 MB of algorithmic input on the 320x320 projection; +19 % on that GEMM).  The M tiles
+    // that do not fill a whole round of CTAs (m_tiles mod grid) are dealt out N-fastest again to keep the tail short.
+    const int grid_i = static_cast<int>(gridDim.x), cta_i = static_cast<int>(blockIdx.x);
+    const int full_groups = (p.n_tiles > 1 && p.m_tiles / grid_i >= 2) ? p.m_tiles / grid_i : 0;
+    const int grouped_tiles = full_groups * p.n_tiles;           // per CTA
+    const int tail_tiles = (p.m_tiles - full_groups * grid_i) * p.n_tiles;  // whole grid
+    auto tile_at = [&](int i, int& mt, int& nt) {  // i-th tile of this CTA; false past the end
+        if (i < grouped_tiles) {
+            const int g = i / p.n_tiles;
+            mt = cta_i + g * grid_i;
+            nt = i - g * p.n_tiles;
+            return true;
+        }
+        const int j = cta_i + (i - grouped_tiles) * grid_i;
+        mt = full_groups * grid_i + j / p.n_tiles;
+        nt = j % p.n_tiles;
+        return j < tail_tiles;
+    };
 
     if (threadIdx.x == 0) {
         // ===================== TMA producer =====================
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int mt = tile / p.n_tiles;
-            const int nt = tile - mt * p.n_tiles;
+        int mt, nt;
+        for (int ti = 0; tile_at(ti, mt, nt); ++ti) {
             const TileCoord tc = tile_coord(p, mt);
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -252,8 +271,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int stage = 0;
         uint32_t phase = 0;
         uint32_t iter = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-            const int nt = tile % p.n_tiles;
+        int mt, nt;
+        for (; tile_at(static_cast<int>(iter), mt, nt); ++iter) {
             int n_this = p.N - nt * p.bn;             // the last N tile of a row may be narrower
             n_this = n_this >= p.bn ? p.bn : ((n_this + 15) & ~15);
             const uint32_t idesc = umma_idesc_f16(static_cast<uint32_t>(n_this), false);
@@ -290,9 +309,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t* stg = staging + e * kStagingBytes;
         const int half_bn = p.bn >> 1;
         uint32_t iter = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-            const int mt = tile / p.n_tiles;
-            const int nt = tile - mt * p.n_tiles;
+        int mt, nt;
+        for (; tile_at(static_cast<int>(iter), mt, nt); ++iter) {
             const TileCoord tc = tile_coord(p, mt);
             const uint32_t as = iter & 1u;
             const uint32_t aphase = (iter >> 1) & 1u;
