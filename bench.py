@@ -310,8 +310,9 @@ def run_engine(args):
                           "step": "one clip through FlowControlNetPipeline.__call__", "clips_per_gpu_per_step": 1,
                           "parallelism": f"clip-parallel x{world}", "l2": "working set >> L2 (each level-0 "
                           "activation is 295 MB; weights 4.4 GB)",
-                          "vae_clip": "VAE decode native (tcgen05 convs + fused uint8 tail); VAE encode (1 frame, fp32) "
-                                      "and CLIP ViT-H are PyTorch eager (0.06 % of a clip's FLOPs)",
+                          "vae_clip": "VAE encode and decode native (tcgen05 convs, fused uint8 tail); the CLIP ViT-H "
+                                      "image encoder (a transformers module passed in by the caller, 0.33 TF once per "
+                                      "clip) is PyTorch eager",
                           "phase_ms_last_clip": {k: round(v, 1) for k, v in tim.items()}},
                "roofline": roof, "cpu_baseline": cpu,
                "e2e": {"value": round(fps_e2e, 4), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),

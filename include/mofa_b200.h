@@ -191,7 +191,8 @@ int mofa_vae_time_conv_out(const void* y, const float* w, const float* b, float*
  * utils/visualize_utils.py:6-19).  Convolutions (BatchNorm folded at pack time, ReLU epilogue, dilation 2/4) run on
  * mofa_gemm; these are the streaming pieces around them.  fp16 channels-last everywhere.
  * ---------------------------------------------------------------------------------------------- */
-/* general im2col: out[(n,oy,ox), (ky,kx,c)] zero padded to Kpad columns (7x7/s2 stem, 5x5/s2, strided 1x1 / 3x3) */
+/* general im2col: out[(n,oy,ox), (ky,kx,c)] zero padded to Kpad columns (7x7/s2 stem, 5x5/s2, strided 1x1 / 3x3);
+ * pad < 0 selects asymmetric padding (0 before, -pad after): the VAE encoder's F.pad(x,(0,1,0,1)) + stride-2 conv */
 int mofa_im2col(const void* x, void* out, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t ksize,
                 int32_t stride, int32_t pad, int32_t dilation, int32_t Kpad, mofa_stream_t stream);
 /* nn.MaxPool2d (mode 0) / nn.AvgPool2d (mode 1) with kernel ksize, stride, padding */

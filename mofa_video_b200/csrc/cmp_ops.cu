@@ -154,11 +154,14 @@ extern "C" int mofa_im2col(const void* x, void* out, int32_t n_img, int32_t H, i
         set_last_error("mofa_im2col: bad arguments");
         return MOFA_ERR_ARG;
     }
-    const int Ho = (H + 2 * pad - dilation * (ksize - 1) - 1) / stride + 1;
-    const int Wo = (W + 2 * pad - dilation * (ksize - 1) - 1) / stride + 1;
+    // pad < 0: asymmetric padding (0 before, -pad after) -- F.pad(x, (0, 1, 0, 1)) + stride-2 conv of the VAE encoder
+    const int pad_lo = pad < 0 ? 0 : pad;
+    const int pad_tot = pad < 0 ? -pad : 2 * pad;
+    const int Ho = (H + pad_tot - dilation * (ksize - 1) - 1) / stride + 1;
+    const int Wo = (W + pad_tot - dilation * (ksize - 1) - 1) / stride + 1;
     const long long total = static_cast<long long>(n_img) * Ho * Wo * Kpad;
     im2col_kernel<<<grid_for2(total), 256, 0, stream>>>(static_cast<const __half*>(x), static_cast<__half*>(out), n_img,
-                                                       H, W, C, ksize, stride, pad, dilation, Ho, Wo, Kpad);
+                                                       H, W, C, ksize, stride, pad_lo, dilation, Ho, Wo, Kpad);
     return check_launch("mofa_im2col");
 }
 

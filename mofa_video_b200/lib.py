@@ -340,7 +340,8 @@ def vae_time_conv_out(y, w, b, out_f32, out_u8, T, HW):
 
 
 def conv_out_size(n, k, stride, pad, dil=1):
-    return (n + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    """pad < 0 means asymmetric padding: 0 before, -pad after (mofa_im2col)."""
+    return (n + (-pad if pad < 0 else 2 * pad) - dil * (k - 1) - 1) // stride + 1
 
 
 def im2col(x, out, n_img, H, W, C, ksize, stride, pad, dilation, Kpad):

@@ -120,31 +120,150 @@ class VaeDecoderNet(engine.Net):
         ops.vae_time_conv_out(y, p["tconv_w"], p["tconv_b"], out_f32, out_u8, n, hw)
 
 
+class VaeEncoderNet(VaeDecoderNet):
+    """SD-style VAE encoder (diffusers 0.24 `Encoder` + `quant_conv`, called by
+    /root/reference/MOFA-Video-Traj/pipeline/pipeline.py:143-164 on ONE 576x1024 image per clip):
+    conv_in 3->128, four DownEncoderBlock2D (two plain ResnetBlock2D each, eps 1e-6; stride-2 conv after
+    F.pad(0,1,0,1) on the first three), mid (resnet, single-head attention d = 512, resnet), GroupNorm-SiLU-conv 512->8,
+    1x1 quant_conv; the latent is the mean half.  The reference upcasts this module to fp32 (:343-352); here it runs on
+    the fp16 tensor-core kernels with fp32 accumulation (difference bounded by tests/test_vae_cpu.py /
+    test_engine_gpu.py)."""
+
+    def __init__(self, state_dict, ops, device, block_out_channels=(128, 256, 512, 512), latent_channels=4):
+        self.kind, self.ops, self.device = "vae_encoder", ops, torch.device(device)
+        self.pk_bn = ops.pick_bn
+        self.temb = engine._TembBank()
+        self.xattn = []
+        self.B, self.T = 1, 1
+        pk = engine._Packer(state_dict, device)
+        boc = tuple(block_out_channels)
+        p = {"conv_in": self._pack_im2col_conv(pk, "encoder.conv_in", 1)}
+        blocks, cin = [], boc[0]
+        for i, cout in enumerate(boc):
+            pre = f"encoder.down_blocks.{i}"
+            blk = {"res": [self._res2d(pk, f"{pre}.resnets.{j}", cin if j == 0 else cout, cout) for j in range(2)],
+                   "down": None}
+            if i != len(boc) - 1:
+                w, b = pk.conv3(f"{pre}.downsamplers.0.conv")
+                blk["down"] = {"w": w, "b": b, "C": cout}
+            blocks.append(blk)
+            cin = cout
+        p["blocks"] = blocks
+        C = boc[-1]
+        p["mid_res"] = [self._res2d(pk, f"encoder.mid_block.resnets.{i}", C, C) for i in range(2)]
+        a = "encoder.mid_block.attentions.0"
+        p["attn"] = {"norm": pk.norm(a + ".group_norm"), "q": pk.lin(a + ".to_q"), "k": pk.lin(a + ".to_k"),
+                     "v": pk.lin(a + ".to_v"), "o": pk.lin(a + ".to_out.0"), "C": C}
+        p["norm_out"] = pk.norm("encoder.conv_norm_out")
+        p["conv_out"] = pk.conv3("encoder.conv_out")
+        # quant_conv (1x1, 8 -> 8): only the mean rows are needed; padded to 8 output columns for 16-byte rows
+        wq = state_dict["quant_conv.weight"].float().reshape(2 * latent_channels, 2 * latent_channels)
+        bq = state_dict["quant_conv.bias"].float()
+        wq8, bq8 = torch.zeros(8, 2 * latent_channels), torch.zeros(8)
+        wq8[:latent_channels], bq8[:latent_channels] = wq[:latent_channels], bq[:latent_channels]
+        p["quant"] = (wq8.to(device, torch.float16).contiguous(), bq8.to(device, torch.float16).contiguous())
+        self.latent_channels = latent_channels
+        self.p = p
+
+    def _res2d(self, pk, pre, cin, cout):
+        r = {"n1": pk.norm(pre + ".norm1"), "c1": pk.conv3(pre + ".conv1"), "n2": pk.norm(pre + ".norm2"),
+             "c2": pk.conv3(pre + ".conv2"), "cin": cin, "cout": cout}
+        r["sc"] = pk.conv1(pre + ".conv_shortcut") if (pre + ".conv_shortcut.weight") in pk.sd else None
+        return r
+
+    def res2d(self, r, x, n, H, W):
+        """ResnetBlock2D without time embedding: x + conv2(silu(gn(conv1(silu(gn(x)))))) (shortcut conv if cin != cout)."""
+        ops = self.ops
+        hw = H * W
+        stats = self.new(n * 64, dtype=torch.float32)
+        h = self.new(n * hw, r["cin"])
+        ops.groupnorm(x, r["n1"][0], r["n1"][1], h, hw, 1e-6, True, stats)
+        h1 = self.new(n * hw, r["cout"])
+        ops.gemm(ops.A_CONV3X3, h, r["c1"][0], h1, N=r["cout"], n_img=n, H=H, W=W, C=r["cin"], bias=r["c1"][1])
+        h2 = self.new(n * hw, r["cout"])
+        ops.groupnorm(h1, r["n2"][0], r["n2"][1], h2, hw, 1e-6, True, stats)
+        if r["sc"] is not None:
+            sc = self.new(n * hw, r["cout"])
+            ops.linear(x, r["sc"][0], sc, bias=r["sc"][1])
+        else:
+            sc = x
+        out = self.new(n * hw, r["cout"])
+        ops.gemm(ops.A_CONV3X3, h2, r["c2"][0], out, N=r["cout"], n_img=n, H=H, W=W, C=r["cout"], bias=r["c2"][1],
+                 res1=sc)
+        return out
+
+    def encode(self, x_cl, n, H, W):
+        """x_cl: fp16 channels-last image(s) [n*H*W, 3] in [-1, 1].  Returns the latent mean, fp16 [n*(H/8)*(W/8), 8]
+        (columns >= latent_channels are zero padding)."""
+        ops, p = self.ops, self.p
+        x, _, _ = self.conv_im2col(p["conv_in"], x_cl, n, H, W)
+        for blk in p["blocks"]:
+            for r in blk["res"]:
+                x = self.res2d(r, x, n, H, W)
+            if blk["down"] is not None:
+                d = blk["down"]
+                C = d["C"]
+                Ho, Wo = ops.conv_out_size(H, 3, 2, -1), ops.conv_out_size(W, 3, 2, -1)
+                cols = self.new(n * Ho * Wo, 9 * C)
+                ops.im2col(x, cols, n, H, W, C, 3, 2, -1, 1, 9 * C)   # F.pad(x, (0,1,0,1)) + 3x3 stride 2
+                del x
+                x = self.new(n * Ho * Wo, C)
+                ops.linear(cols, d["w"], x, bias=d["b"])
+                del cols
+                H, W = Ho, Wo
+        hw = H * W
+        x = self.res2d(p["mid_res"][0], x, n, H, W)
+        x = self.attention(x, hw)
+        x = self.res2d(p["mid_res"][1], x, n, H, W)
+        stats = self.new(n * 64, dtype=torch.float32)
+        hn = self.new(x.shape[0], x.shape[1])
+        ops.groupnorm(x, p["norm_out"][0], p["norm_out"][1], hn, hw, 1e-6, True, stats)
+        wgt, b = p["conv_out"]
+        mom = self.new(n * hw, wgt.shape[0])
+        ops.gemm(ops.A_CONV3X3, hn, wgt, mom, N=wgt.shape[0], n_img=n, H=H, W=W, C=x.shape[1], bias=b, bn=16)
+        lat = self.new(n * hw, 8)
+        ops.linear(mom, p["quant"][0], lat, bias=p["quant"][1], bn=16)
+        return lat, H, W
+
+
 class NativeTemporalDecoderVAE:
-    """`vae` object for FlowControlNetPipeline: encode() stays on the wrapped PyTorch module (fp32, one frame,
-    0.05 % of a clip), decode() runs the native decoder.  Same interface as AutoencoderKLTemporalDecoder."""
+    """`vae` object for FlowControlNetPipeline: encode() and decode() both run on the sm_100a kernels (the wrapped
+    PyTorch module only supplies the weights and the config).  Same interface as AutoencoderKLTemporalDecoder."""
 
     def __init__(self, torch_vae, ops=None, device="cuda"):
         from mofa_video_b200 import lib as _lib
         self.torch_vae = torch_vae
-        self.config = torch_vae.config
+        self.config = SimpleNamespace(**vars(torch_vae.config))
+        self.config.force_upcast = False  # nothing to upcast: encode() runs on the fp16 tensor-core kernels too
         self._ops = ops if ops is not None else _lib
         self._device = torch.device(device)
-        self.net = VaeDecoderNet(torch_vae.state_dict(), self._ops, self._device,
-                                 block_out_channels=self.config.block_out_channels,
+        sd = torch_vae.state_dict()
+        self.net = VaeDecoderNet(sd, self._ops, self._device, block_out_channels=self.config.block_out_channels,
                                  latent_channels=self.config.latent_channels,
                                  scaling_factor=self.config.scaling_factor)
+        self.enc = VaeEncoderNet(sd, self._ops, self._device, block_out_channels=self.config.block_out_channels,
+                                 latent_channels=self.config.latent_channels)
 
     @property
     def dtype(self):
-        return self.torch_vae.dtype
+        return torch.float16
 
     def to(self, *a, **k):
-        self.torch_vae.to(*a, **k)
-        return self
+        return self  # weights are packed once for the kernels; the wrapped module is not used at run time
 
     def encode(self, x):
-        return self.torch_vae.encode(x)
+        """x [n, 3, H, W] in [-1, 1] -> .latent_dist.mode() [n, 4, H/8, W/8] in x's dtype (pipeline.py:143-164)."""
+        n, c, H, W = x.shape
+        if H % 8 or W % 8 or c != 3:
+            raise ValueError("encode expects [n, 3, H, W] with H, W multiples of 8")
+        xc = torch.empty(n * H * W, 3, dtype=torch.float16, device=self._device)
+        self._ops.nchw_to_nhwc(x.to(device=self._device, dtype=torch.float16).contiguous(), xc, n, 3, H * W)
+        lat, h, w = self.enc.encode(xc, n, H, W)
+        L = self.config.latent_channels
+        full = torch.empty(n, 8, h, w, dtype=torch.float16, device=self._device)
+        self._ops.nhwc_to_nchw(lat, full, n, 8, h * w)
+        mean = full[:, :L].to(x.dtype)
+        return SimpleNamespace(latent_dist=SimpleNamespace(mode=lambda: mean, mean=mean))
 
     def _cl(self, z):
         n, c, h, w = z.shape

@@ -157,3 +157,23 @@ def test_native_vae_decoder_matches_torch_module():
     u8 = nat.decode_uint8(z.cuda(), num_frames=5).cpu()
     want = ((ref / 2 + 0.5).clamp(0, 1) * 255).round().permute(0, 2, 3, 1)
     assert (u8.float() - want).abs().max() <= 3
+
+
+def test_native_vae_encoder_matches_torch_module():
+    """SURVEY.md §8 row a9 on the GPU: conv_in (im2col), TMA implicit-GEMM resnets, asymmetric-pad stride-2 convs,
+    d = C attention as GEMMs, quant_conv -- vs the fp32 PyTorch module.  Real channel widths at a small image."""
+    from mofa_video_b200.models.autoencoder_kl_temporal_decoder import AutoencoderKLTemporalDecoder
+    from mofa_video_b200.vae_engine import NativeTemporalDecoderVAE
+    torch.manual_seed(4)
+    vae = AutoencoderKLTemporalDecoder().eval()
+    with torch.no_grad():
+        for n, p in vae.named_parameters():
+            p.copy_(p.half().float())
+    x = (torch.rand(1, 3, 128, 192, generator=torch.Generator().manual_seed(5)) * 2 - 1).half().float()
+    with torch.no_grad():
+        ref = vae.encode(x).latent_dist.mode()
+    nat = NativeTemporalDecoderVAE(vae)
+    out = nat.encode(x.cuda()).latent_dist.mode()
+    assert out.shape == ref.shape == (1, 4, 16, 24)
+    e = rel_err(out, ref)
+    assert e < 2e-2, f"vae encode rel err {e}"

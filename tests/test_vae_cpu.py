@@ -37,3 +37,17 @@ def test_native_decoder_matches_torch_module():
         ref1 = vae.decode(z[:1], num_frames=1).sample
     out1 = nat.decode(z[:1], num_frames=1).sample
     assert ((out1 - ref1).abs().max() / ref1.abs().max()).item() < 1e-2
+
+
+def test_native_encoder_matches_torch_module():
+    """Encoder + quant_conv -> latent mean, incl. the asymmetric-pad stride-2 convs."""
+    vae = make_vae(seed=2)
+    g = torch.Generator().manual_seed(3)
+    x = (torch.rand(1, 3, 64, 96, generator=g) * 2 - 1).half().float()
+    with torch.no_grad():
+        ref = vae.encode(x).latent_dist.mode()
+    nat = NativeTemporalDecoderVAE(vae, ops=ref_ops, device="cpu")
+    out = nat.encode(x).latent_dist.mode()
+    assert out.shape == ref.shape == (1, 4, 8, 12)
+    err = ((out - ref).abs().max() / ref.abs().max()).item()
+    assert err < 1e-2, err
