@@ -35,8 +35,6 @@ namespace mofa {
 
 int make_tmap_f16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box);
-int attn_spatial_v1(const void* qkv, void* out, int32_t frames, int32_t L, int32_t heads, float scale,
-                    mofa_stream_t stream_);
 
 namespace v2 {
 
@@ -372,12 +370,6 @@ using namespace mofa;
 
 extern "C" int mofa_attn_spatial(const void* qkv, void* out, int32_t frames, int32_t L, int32_t heads, float scale,
                                  mofa_stream_t stream_) {
-    static int use_v1 = -1;
-    if (use_v1 < 0) {
-        const char* e = getenv("MOFA_ATTN_V1");
-        use_v1 = (e && e[0] == '1') ? 1 : 0;
-    }
-    if (use_v1) return attn_spatial_v1(qkv, out, frames, L, heads, scale, stream_);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!qkv || !out || frames <= 0 || L <= 0 || heads <= 0) {
         set_last_error("mofa_attn_spatial: bad arguments");
