@@ -46,6 +46,7 @@ struct Params {
     __half* out;
     int L, C, heads, n_kv;
     float scale_log2;
+    int idle_ns;  // MMA issuer: nanosleep between barrier probes when nothing was ready (0 = spin)
 };
 
 MOFA_DEVICE float max3(float a, float b, float c) {
@@ -194,7 +195,7 @@ attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
                     progress = true;
                 }
             }
-            if (!progress) __nanosleep(20);
+            if (!progress && p.idle_ns > 0) __nanosleep(p.idle_ns);
         }
     } else if (warp >= 2) {
         // ===================== softmax warps =====================
@@ -264,6 +265,11 @@ attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
             l *= alpha;
             // exponentials first (registers only): they overlap P_{j-1} V_{j-1}, which still reads the P buffer
             float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+            // kPolyEvery < 0: row sums of the ROUNDED probabilities with packed-half adds (one HADD2 per two scores
+            // instead of two FADD); four accumulators of <= 16 values <= 256 each, widened to fp32 once per tile
+            __half2 hs[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hs[q] = __floats2half2_rn(0.f, 0.f);
             uint32_t packed[kCols / 2];
             // the reference maximum takes a round trip through shared memory across the barrier (and the row sum is
             // stored before the arrive below): ptxas keeps shared-memory accesses ordered around BAR, so the
@@ -281,15 +287,25 @@ attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
                 const bool poly = kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == 0;
                 const float p0 = poly ? poly_exp2(x0) : fast_exp2(x0);
                 const float p1 = poly ? poly_exp2(x1) : fast_exp2(x1);
-                if (i & 1) {
+                const __half2 h = __floats2half2_rn(p0, p1);
+                if (kPolyEvery < 0) {
+                    hs[i & 3] = __hadd2(hs[i & 3], h);
+                } else if (i & 1) {
                     sum2 += p0;
                     sum3 += p1;
                 } else {
                     sum0 += p0;
                     sum1 += p1;
                 }
-                const __half2 h = __floats2half2_rn(p0, p1);
                 packed[i] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            if (kPolyEvery < 0) {
+                const float2 a = __half22float2(hs[0]), b = __half22float2(hs[1]);
+                const float2 c = __half22float2(hs[2]), d = __half22float2(hs[3]);
+                sum0 = a.x + a.y;
+                sum1 = b.x + b.y;
+                sum2 = c.x + c.y;
+                sum3 = d.x + d.y;
             }
             const float l_tile = (sum0 + sum1) + (sum2 + sum3);
             if (kHandoff) {
@@ -389,10 +405,17 @@ extern "C" int mofa_attn_spatial(const void* qkv, void* out, int32_t frames, int
     p.heads = heads;
     p.n_kv = (L + 127) / 128;
     p.scale_log2 = scale * 1.4426950408889634f;
+    static int idle_ns = -1;
+    if (idle_ns < 0) {
+        const char* e = getenv("MOFA_ATTN_IDLE_NS");
+        idle_ns = e ? atoi(e) : 20;
+    }
+    p.idle_ns = idle_ns;
     const size_t smem_bytes = 2 * v2::kTile + v2::kKVStages * 2 * v2::kTile + 16 * 8 + 16 +
                               (64 + 256 * 2) * 4 + 2 * 2 * 2 * 128 * 4 + 1024;
     // variants (environment, read once): MOFA_ATTN_SPLIT = 1 | 2 threads per query row, MOFA_ATTN_HANDOFF = 0 | 1
-    // (kSplit 1 only), MOFA_ATTN_POLY = 0 | 2 | 4 (share of exponentials on the FMA pipe: none, 1/2, 1/4).
+    // (kSplit 1 only), MOFA_ATTN_POLY = -1 | 0 | 2 | 4 (-1: packed-half row sums; 0: fp32 row sums; 2 / 4: fp32 sums and
+    // 1/2 / 1/4 of the exponentials on the FMA pipe).
     // Defaults are the measured best on B200 (profiles/).
     using Kern = void (*)(const CUtensorMap, const v2::Params);
     static Kern kern = nullptr;
@@ -401,7 +424,7 @@ extern "C" int mofa_attn_spatial(const void* qkv, void* out, int32_t frames, int
         const char* ep = getenv("MOFA_ATTN_POLY");
         const char* eh = getenv("MOFA_ATTN_HANDOFF");
         const char* es = getenv("MOFA_ATTN_SPLIT");
-        const int poly = ep ? atoi(ep) : 0;
+        const int poly = ep ? atoi(ep) : -1;  // -1: packed-half row sums (+3.8 % over fp32 sums, same-box A/B)
         const int split = es ? atoi(es) : 1;
         const bool handoff = eh ? (eh[0] == '1') : true;
         Kern k;
@@ -410,9 +433,10 @@ extern "C" int mofa_attn_spatial(const void* qkv, void* out, int32_t frames, int
                 : poly == 4 ? v2::attn_spatial2_kernel<4, false, 2>
                             : v2::attn_spatial2_kernel<0, false, 2>;
         } else if (handoff) {
-            k = poly == 2   ? v2::attn_spatial2_kernel<2, true, 1>
-                : poly == 4 ? v2::attn_spatial2_kernel<4, true, 1>
-                            : v2::attn_spatial2_kernel<0, true, 1>;
+            k = poly == 2    ? v2::attn_spatial2_kernel<2, true, 1>
+                : poly == 4  ? v2::attn_spatial2_kernel<4, true, 1>
+                : poly == -1 ? v2::attn_spatial2_kernel<-1, true, 1>
+                             : v2::attn_spatial2_kernel<0, true, 1>;
         } else {
             k = poly == 2   ? v2::attn_spatial2_kernel<2, false, 1>
                 : poly == 4 ? v2::attn_spatial2_kernel<4, false, 1>
