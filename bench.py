@@ -192,6 +192,8 @@ def run_engine(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib.load()
+    torch.set_num_threads(min(8, os.cpu_count() or 1))  # host work of this arm is tiny; 128 OpenMP threads on a busy
+                                                        # host made it 10x slower (round-1 observation)
 
     # per-rank clip (independent clips, seeds 1234+rank / 1235+rank -- SURVEY.md §8d config 5)
     import numpy as np

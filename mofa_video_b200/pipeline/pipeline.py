@@ -149,7 +149,7 @@ class FlowControlNetPipeline:
     def _encode_image(self, image, device, num_videos_per_prompt, do_classifier_free_guidance):
         """pipeline.py:114-141 (Q3: [0,1] image, antialiased bicubic to 224, no CLIP mean/std)."""
         dtype = next(self.image_encoder.parameters()).dtype
-        img = _to_unit_tensor(image)
+        img = _to_unit_tensor(image).to(device)  # blur + bicubic run on the device, not on the host cores
         img = _resize_with_antialiasing(img, (224, 224)).to(device=device, dtype=dtype)
         emb = self.image_encoder(img).image_embeds.unsqueeze(1)
         emb = emb.repeat(1, num_videos_per_prompt, 1)
@@ -246,7 +246,7 @@ class FlowControlNetPipeline:
         fps = fps - 1
 
         # 4. VAE-encode the (noise-augmented) conditioning frame; CPU RNG like the reference (Q7)
-        img = _to_unit_tensor(image, height, width) * 2.0 - 1.0
+        img = _to_unit_tensor(image, height, width).to(device) * 2.0 - 1.0
         gen_cpu = generator if isinstance(generator, torch.Generator) and generator.device.type == "cpu" else None
         noise = torch.randn(img.shape, generator=gen_cpu, dtype=img.dtype)
         img = img + noise_aug_strength * noise.to(img.device)

@@ -82,7 +82,7 @@ class FlowControlNetPipeline(_TrajPipeline):
         device = self._device
         image_embeddings = self._encode_image(image, device, 1, True)
         emb_dtype = image_embeddings.dtype
-        img = _to_unit_tensor(image, height, width) * 2.0 - 1.0
+        img = _to_unit_tensor(image, height, width).to(device) * 2.0 - 1.0
         gen_cpu = generator if isinstance(generator, torch.Generator) and generator.device.type == "cpu" else None
         img = img + noise_aug_strength * torch.randn(img.shape, generator=gen_cpu, dtype=img.dtype).to(img.device)
         needs_upcasting = self.vae.dtype == torch.float16 and self.vae.config.force_upcast
