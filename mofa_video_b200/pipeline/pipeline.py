@@ -22,6 +22,11 @@ import torch.nn.functional as F
 from mofa_video_b200 import lib as _lib
 
 
+class _NoEvent:
+    def record(self):
+        pass
+
+
 @dataclass
 class FlowControlNetPipelineOutput:
     frames: Union[List[PIL.Image.Image], np.ndarray, torch.Tensor] = None
@@ -96,13 +101,18 @@ class FlowControlNetPipeline:
     model_cpu_offload_seq = "image_encoder->unet->vae"
     _callback_tensor_inputs = ["latents"]
 
-    def __init__(self, vae, image_encoder, unet, controlnet, scheduler, feature_extractor=None):
+    def __init__(self, vae, image_encoder, unet, controlnet, scheduler, feature_extractor=None, ops=None,
+                 device="cuda"):
+        """`ops` / `device` exist for the CPU host-logic tests only (tests/ref_ops.py states every C-ABI op in PyTorch);
+        a product user never passes them: the default binds the CUDA library and fails if it is missing."""
         self.vae, self.image_encoder, self.unet, self.controlnet = vae, image_encoder, unet, controlnet
         self.scheduler, self.feature_extractor = scheduler, feature_extractor
         self.vae_scale_factor = 2 ** (len(self.vae.config.block_out_channels) - 1)
-        self._device = torch.device("cuda")
+        self._device = torch.device(device)
         self.timings = {}
-        _lib.load()  # no fallback: fail here if the CUDA library is missing
+        self._ops = ops if ops is not None else _lib
+        if ops is None:
+            _lib.load()  # no fallback: fail here if the CUDA library is missing
 
     @classmethod
     def from_pretrained(cls, path, unet=None, controlnet=None, image_encoder=None, vae=None, scheduler=None,
@@ -223,7 +233,7 @@ class FlowControlNetPipeline:
                  callback_on_step_end: Optional[Callable[[int, int, Dict], None]] = None,
                  callback_on_step_end_tensor_inputs: List[str] = ["latents"], return_dict: bool = True,
                  controlnet_cond_scale=1.0, batch_size=1):
-        ops = _lib
+        ops = self._ops
         height = height or self.unet.config.sample_size * self.vae_scale_factor
         width = width or self.unet.config.sample_size * self.vae_scale_factor
         num_frames = num_frames if num_frames is not None else self.unet.config.num_frames
@@ -237,7 +247,8 @@ class FlowControlNetPipeline:
         if not do_cfg:
             raise ValueError("max_guidance_scale must be > 1: without CFG the reference substitutes the latents for "
                              "the condition image and flow (pipeline.py:393,396), which is not a usable mode")
-        ev = {k: torch.cuda.Event(enable_timing=True) for k in ("t0", "enc", "loop", "dec")}
+        ev = {k: (torch.cuda.Event(enable_timing=True) if device.type == "cuda" else _NoEvent())
+              for k in ("t0", "enc", "loop", "dec")}
         ev["t0"].record()
 
         # 3. CLIP image embedding

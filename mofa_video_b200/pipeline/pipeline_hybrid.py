@@ -46,8 +46,9 @@ def denoise_hybrid(ops, unet_net, face_net, drag_net, by_rows, lat, il, sig, tst
 
 
 class FlowControlNetPipeline(_TrajPipeline):
-    def __init__(self, vae, image_encoder, unet, drag_controlnet, face_controlnet, scheduler, feature_extractor=None):
-        super().__init__(vae, image_encoder, unet, drag_controlnet, scheduler, feature_extractor)
+    def __init__(self, vae, image_encoder, unet, drag_controlnet, face_controlnet, scheduler, feature_extractor=None,
+                 ops=None, device="cuda"):
+        super().__init__(vae, image_encoder, unet, drag_controlnet, scheduler, feature_extractor, ops=ops, device=device)
         self.drag_controlnet, self.face_controlnet = drag_controlnet, face_controlnet
 
     @classmethod
@@ -69,7 +70,7 @@ class FlowControlNetPipeline(_TrajPipeline):
                  callback_on_step_end: Optional[Callable[[int, int, Dict], None]] = None,
                  callback_on_step_end_tensor_inputs: List[str] = ["latents"], return_dict: bool = True,
                  ctrl_scale_traj=1.0, ctrl_scale_ldmk=1.0, batch_size=1):
-        ops = _lib
+        ops = self._ops
         num_frames = num_frames if num_frames is not None else self.unet.config.num_frames
         decode_chunk_size = decode_chunk_size if decode_chunk_size is not None else num_frames
         self.check_inputs(image, height, width)

@@ -77,7 +77,7 @@ class FlowControlNetPipeline(_TrajPipeline):
                  callback_on_step_end: Optional[Callable[[int, int, Dict], None]] = None,
                  callback_on_step_end_tensor_inputs: List[str] = ["latents"], return_dict: bool = True,
                  controlnet_cond_scale=1.0, batch_size=1, window_size=25, stride=12):
-        ops = _lib
+        ops = self._ops
         num_frames = num_frames if num_frames is not None else self.unet.config.num_frames
         decode_chunk_size = decode_chunk_size if decode_chunk_size is not None else num_frames
         self.check_inputs(image, height, width)

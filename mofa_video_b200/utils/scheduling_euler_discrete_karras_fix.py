@@ -70,7 +70,7 @@ class EulerDiscreteScheduler:
     # ------------------------------------------------------------------ ladder construction (host)
     def _train_sigmas(self):
         ac = self.alphas_cumprod
-        return np.array(((1 - ac) / ac) ** 0.5)
+        return (((1 - ac) / ac) ** 0.5).numpy()
 
     def _karras(self, in_sigmas, count):
         c = self.config

@@ -29,7 +29,7 @@ class EulerDiscreteScheduler:
         self.alphas = 1.0 - self.betas
         self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
         self.use_karras_sigmas = c["use_karras_sigmas"]
-        sigmas = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)[::-1].copy()
+        sigmas = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()[::-1].copy()
         if self.use_karras_sigmas:
             sigmas = self._convert_to_karras(sigmas, c["num_train_timesteps"])
         sigmas = torch.from_numpy(sigmas).to(dtype=torch.float32)
@@ -66,7 +66,7 @@ class EulerDiscreteScheduler:
         step_ratio = c.num_train_timesteps // num_inference_steps
         timesteps = (np.arange(0, num_inference_steps) * step_ratio).round()[::-1].copy().astype(np.float32)
         timesteps += c.steps_offset
-        sigmas = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sigmas = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
         sigmas = np.interp(timesteps, np.arange(0, len(sigmas)), sigmas)
         if self.use_karras_sigmas:
             sigmas = self._convert_to_karras(sigmas, num_inference_steps)

@@ -1,0 +1,82 @@
+"""-m "not gpu": the reference entry point FlowControlNetPipeline.__call__ end to end on CPU -- every C-ABI op replaced by
+its PyTorch statement (tests/ref_ops.py) -- against oracle.pipeline.run_pipeline (restatement of
+/root/reference/MOFA-Video-Traj/pipeline/pipeline.py:282-527).  Covers the host logic of row a1: input conversion, CLIP
+resize path, VAE encode + noise augmentation placement, added-time-id quirk (Q4), fused CFG/Euler stepping, callback,
+latent output, error behaviour."""
+import pytest
+import torch
+
+import ref_ops
+from mofa_video_b200.models.autoencoder_kl_temporal_decoder import AutoencoderKLTemporalDecoder
+from mofa_video_b200.models.svdxt_featureflow_forward_controlnet_s2d_fixcmp_norefine import FlowControlNet
+from mofa_video_b200.models.unet_spatio_temporal_condition_controlnet import UNetSpatioTemporalConditionControlNetModel
+from mofa_video_b200.pipeline.pipeline import FlowControlNetPipeline
+from mofa_video_b200.utils.scheduling_euler_discrete_karras_fix import EulerDiscreteScheduler
+from oracle import fixtures
+from oracle import pipeline as opipe
+from oracle import scheduler as osched
+
+
+class TinyClip(torch.nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.proj = torch.nn.Linear(3 * 8 * 8, dim)
+
+    def forward(self, x):
+        from types import SimpleNamespace
+        return SimpleNamespace(image_embeds=self.proj(torch.nn.functional.adaptive_avg_pool2d(x, 8).flatten(1)))
+
+
+def build():
+    cfg = dict(fixtures.TINY_CONFIG)
+    unet, adapter = fixtures.make_models(cfg, seed=0, adapter_gain=20.0)
+    e_unet = UNetSpatioTemporalConditionControlNetModel.from_state_dict(unet.state_dict(), unet.config.__dict__,
+                                                                        device="cpu", ops=ref_ops)
+    e_ad = FlowControlNet.from_state_dict(adapter.state_dict(), adapter.config.__dict__, device="cpu", ops=ref_ops)
+    torch.manual_seed(5)
+    vae = AutoencoderKLTemporalDecoder(block_out_channels=(32, 32, 64, 64)).eval()
+    clip = TinyClip(cfg["cross_attention_dim"]).eval()
+    pipe = FlowControlNetPipeline(vae=vae, image_encoder=clip, unet=e_unet, controlnet=e_ad,
+                                  scheduler=EulerDiscreteScheduler(), ops=ref_ops, device="cpu")
+    return cfg, unet, adapter, vae, clip, pipe
+
+
+def test_call_matches_oracle_on_cpu():
+    cfg, unet, adapter, vae, clip, pipe = build()
+    H, W, T = 128, 128, cfg["num_frames"]
+    image = fixtures.make_image(H, W)
+    flow = fixtures.make_flow(T, H, W)
+    lat0 = torch.randn(1, T, 4, H // 8, W // 8, generator=torch.Generator().manual_seed(9))
+    ref = opipe.run_pipeline(vae, clip, unet, adapter, osched.EulerDiscreteScheduler(), image, image, flow, height=H,
+                             width=W, num_inference_steps=2, latents=lat0.clone(),
+                             generator=torch.Generator().manual_seed(11), output_type="latent")
+    seen = []
+    out = pipe(image, image, flow, height=H, width=W, num_inference_steps=2, latents=lat0.clone(),
+               generator=torch.Generator().manual_seed(11), output_type="latent",
+               callback_on_step_end=lambda p, i, t, kw: seen.append((i, float(t), tuple(kw["latents"].shape))) or {})
+    lat = out.frames.float()
+    assert lat.shape == ref.shape
+    err = ((lat - ref).abs().max() / ref.abs().max()).item()
+    assert err < 1e-2, err
+    assert [s[0] for s in seen] == [0, 1] and seen[0][2] == (1, T, 4, H // 8, W // 8)
+    # frames through the (PyTorch) VAE passed in by the caller: shape / range contract of tensor2vid
+    frames = pipe(image, image, flow, height=H, width=W, num_inference_steps=1, latents=lat0.clone(),
+                  output_type="pt", decode_chunk_size=2).frames
+    assert len(frames) == 1 and frames[0].shape == (T, 3, H, W)
+    assert 0.0 <= float(frames[0].min()) and float(frames[0].max()) <= 1.0
+
+
+def test_call_errors_like_the_reference():
+    cfg, unet, adapter, vae, clip, pipe = build()
+    H, W, T = 128, 128, cfg["num_frames"]
+    image, flow = fixtures.make_image(H, W), fixtures.make_flow(T, H, W)
+    with pytest.raises(ValueError):
+        pipe(image, image, flow, height=H + 4, width=W)               # not divisible by 8
+    with pytest.raises(ValueError):
+        pipe(image, image, flow, height=H, width=W, max_guidance_scale=1.0)   # CFG is mandatory (Q5)
+    with pytest.raises(ValueError):
+        pipe(image, image, flow[:, :-1], height=H, width=W)           # wrong number of flow frames
+    with pytest.raises(ValueError):
+        pipe(3.0, image, flow, height=H, width=W)                     # unsupported image type
+    with pytest.raises(NotImplementedError):
+        pipe(image, image, flow, height=H, width=W, batch_size=2)
