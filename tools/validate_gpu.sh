@@ -1,5 +1,5 @@
 #!/bin/bash
-# full validation: all GPU tests, smoke, bench (both arms), step profile
+# full validation on a B200 box: all GPU tests, smoke, bench, step profiles (gpurun -- bash tools/validate_gpu.sh)
 mkdir -p gpurun_out
 rm -f gpurun_out/summary.txt
 timeout 1500 python -m pytest tests -q -m gpu -p no:cacheprovider -x > gpurun_out/t_all.log 2>&1
