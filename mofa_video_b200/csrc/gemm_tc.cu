@@ -357,7 +357,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         // (ncu on the first version: predicated-off activation/residual code still cost issue slots,
                         //  ~15 instructions per output element.)
                         const bool has1 = p.res1 != nullptr, has2 = p.res2 != nullptr;  // uniform
-                        uint4 r1[4], r2[4];
+                        uint4 r1[4], r2[4], rbv[4];
+                        if (!kGeglu && p.rowbias) {  // row-group bias: requested with the residuals, not after the
+#pragma unroll                                       // accumulator wait (its L2 latency sat on the critical path)
+                            for (int g = 0; g < 4; ++g) {
+                                const int nb = nt * p.bn + col0 + g * 8;
+                                rbv[g] = make_uint4(0, 0, 0, 0);
+                                if (nb < p.N_out)
+                                    rbv[g] = __ldg(reinterpret_cast<const uint4*>(p.rowbias + group * p.ld_rowbias + nb));
+                            }
+                        }
                         if (has1) {  // one batch of loads in flight, consumed after the TMEM load
 #pragma unroll
                             for (int g = 0; g < 4; ++g) {
@@ -421,7 +430,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                         const int nb = nt * p.bn + col0 + g * 8;
                                         if (nb < p.N_out) {
                                             H8 b;
-                                            b.u = __ldg(reinterpret_cast<const uint4*>(p.rowbias + group * p.ld_rowbias + nb));
+                                            b.u = rbv[g];
 #pragma unroll
                                             for (int j = 0; j < 8; ++j) v[g * 8 + j] += __half2float(b.h[j]);
                                         }

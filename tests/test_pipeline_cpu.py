@@ -80,3 +80,58 @@ def test_call_errors_like_the_reference():
         pipe(3.0, image, flow, height=H, width=W)                     # unsupported image type
     with pytest.raises(NotImplementedError):
         pipe(image, image, flow, height=H, width=W, batch_size=2)
+
+
+def test_keypoint_and_hybrid_calls_match_oracle_on_cpu():
+    """Rows a13-a15 through the reference entry points (Keypoint: windowed views of a 5-frame clip with T = 3;
+    Hybrid: two adapters + mask), CPU / ref_ops, vs the oracle prelude + loops."""
+    from mofa_video_b200.models.ldmk_ctrlnet import FlowControlNet as FaceNet
+    from mofa_video_b200.pipeline import pipeline_hybrid as hyb
+    from mofa_video_b200.pipeline import svdxt_pipeline_ctrlnet_loop as kpl
+    from oracle import keypoint as kp
+    from test_keypoint_cpu import make_ldmk_adapter
+    cfg, unet, drag, vae, clip, _ = build()
+    face = make_ldmk_adapter(cfg)
+    H, W, T, F_frames, stride = 128, 128, cfg["num_frames"], 5, 1
+    g = torch.Generator().manual_seed(3)
+    image = fixtures.make_image(H, W)
+    flow = fixtures.make_flow(F_frames, H, W)
+    ldmk = torch.rand(1, F_frames, 3, H, W, generator=g).half().float()
+    lat0 = torch.randn(1, F_frames, 4, H // 8, W // 8, generator=g)
+    mk = dict(device="cpu", ops=ref_ops)
+    e_unet = UNetSpatioTemporalConditionControlNetModel.from_state_dict(unet.state_dict(), unet.config.__dict__, **mk)
+    e_drag = FlowControlNet.from_state_dict(drag.state_dict(), drag.config.__dict__, **mk)
+    e_face = FaceNet.from_state_dict(face.state_dict(), face.config.__dict__, **mk)
+    cond = (2.0 * image - 1.0)[None].repeat(2, 1, 1, 1)
+
+    emb, il = opipe.prepare_inputs(vae, clip, image, F_frames, torch.Generator().manual_seed(11))
+    osch = osched.EulerDiscreteScheduler()
+    osch.set_timesteps(2)
+    ref = kp.keypoint_denoise(unet, face, osch, lat0 * osch.init_noise_sigma, il, emb, cond,
+                              flow.repeat(2, 1, 1, 1, 1), ldmk.repeat(2, 1, 1, 1, 1), 2, T, stride)
+    pipe = kpl.FlowControlNetPipeline(vae=vae, image_encoder=clip, unet=e_unet, controlnet=e_face,
+                                      scheduler=EulerDiscreteScheduler(), **mk)
+    out = pipe(image, image, flow, ldmk, height=H, width=W, num_frames=F_frames, num_inference_steps=2,
+               latents=lat0.clone(), generator=torch.Generator().manual_seed(11), output_type="latent",
+               window_size=T, stride=stride)
+    err = ((out.frames.float() - ref).abs().max() / ref.abs().max()).item()
+    assert out.frames.shape == ref.shape and err < 1.5e-2, err
+    with pytest.raises(ValueError):
+        pipe(image, image, flow, ldmk, height=H, width=W, num_frames=F_frames, window_size=T + 1)
+
+    emb, il = opipe.prepare_inputs(vae, clip, image, T, torch.Generator().manual_seed(11))
+    osch = osched.EulerDiscreteScheduler()
+    osch.set_timesteps(2)
+    drag_flow = (fixtures.make_flow(T, H, W, seed=99) * 0.5).half().float()
+    mask = torch.zeros(1, 1, H, W)
+    mask[..., 20:90, 30:100] = 1.0
+    ref = kp.hybrid_denoise(unet, face, drag, osch, lat0[:, :T] * osch.init_noise_sigma, il, emb, cond,
+                            flow[:, :T - 1].repeat(2, 1, 1, 1, 1), drag_flow.repeat(2, 1, 1, 1, 1),
+                            ldmk[:, :T].repeat(2, 1, 1, 1, 1), mask, 2, scale_ldmk=0.9, scale_traj=1.1)
+    pipe = hyb.FlowControlNetPipeline(vae=vae, image_encoder=clip, unet=e_unet, drag_controlnet=e_drag,
+                                      face_controlnet=e_face, scheduler=EulerDiscreteScheduler(), **mk)
+    out = pipe(image, image, flow[:, :T - 1], ldmk[:, :T], drag_flow, mask, height=H, width=W, num_inference_steps=2,
+               latents=lat0[:, :T].clone(), generator=torch.Generator().manual_seed(11), output_type="latent",
+               ctrl_scale_traj=1.1, ctrl_scale_ldmk=0.9)
+    err = ((out.frames.float() - ref).abs().max() / ref.abs().max()).item()
+    assert err < 1.5e-2, err
