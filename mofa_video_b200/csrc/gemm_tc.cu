@@ -409,19 +409,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     }
                                 }
                             } else {
+                                uint4 bvv[4];  // bias: requested while the TMEM load is in flight
+                                if (p.bias) {
+#pragma unroll
+                                    for (int g = 0; g < 4; ++g) {
+                                        const int nb = nt * p.bn + col0 + g * 8;
+                                        bvv[g] = make_uint4(0, 0, 0, 0);
+                                        if (nb < p.N_out) bvv[g] = __ldg(reinterpret_cast<const uint4*>(p.bias + nb));
+                                    }
+                                }
                                 tmem_ld_wait();
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
                                 if (p.bias) {
 #pragma unroll
                                     for (int g = 0; g < 4; ++g) {
-                                        const int nb = nt * p.bn + col0 + g * 8;
-                                        if (nb < p.N_out) {
-                                            H8 b;
-                                            b.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nb));
+                                        H8 b;
+                                        b.u = bvv[g];
 #pragma unroll
-                                            for (int j = 0; j < 8; ++j) v[g * 8 + j] += __half2float(b.h[j]);
-                                        }
+                                        for (int j = 0; j < 8; ++j) v[g * 8 + j] += __half2float(b.h[j]);
                                     }
                                 }
                                 if (p.rowbias) {
