@@ -227,6 +227,10 @@ int mofa_downsample_nearest(const void* x, void* out, int32_t n_img, int32_t H, 
  * flow_out may be NULL */
 int mofa_flow_post(const void* flow_in, const void* brush, const void* flow_out, void* out, int32_t F, int32_t Hs,
                    int32_t Ws, int32_t H, int32_t W, mofa_stream_t stream);
+/* CLIP-side resize (/root/reference/MOFA-Video-Traj/pipeline/pipeline.py:532-640 _resize_with_antialiasing, called at
+ * :123): Gaussian blur + bicubic(align_corners) in one pass, fp32 planes [planes, H, W] -> [planes, Ho, Wo] */
+int mofa_resize_antialias(const void* img, void* out, int32_t planes, int32_t H, int32_t W, int32_t Ho, int32_t Wo,
+                          mofa_stream_t stream);
 
 #ifdef __cplusplus
 }

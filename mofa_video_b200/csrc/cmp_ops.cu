@@ -307,6 +307,111 @@ extern "C" int mofa_mask_blend(const void* a, const void* b, const void* mask, v
 }
 
 namespace mofa {
+// CLIP-side resize of /root/reference/MOFA-Video-Traj/pipeline/pipeline.py:532-640 (_resize_with_antialiasing) fused
+// into one pass: separable Gaussian blur (sigma = max((factor-1)/2, 0.001) per axis, odd two-sigma kernel, reflect
+// padding) followed by bicubic interpolation (A = -0.75, align_corners = True, clamped taps), fp32 NCHW.
+__global__ void __launch_bounds__(256)
+resize_antialias_kernel(const float* __restrict__ img, float* __restrict__ out, int planes, int H, int W, int Ho, int Wo,
+                        float sig_y, float sig_x, int ks_y, int ks_x) {
+    __shared__ float gy[64], gx[64];
+    if (threadIdx.x < 64) {
+        for (int pass = 0; pass < 2; ++pass) {
+            const int ks = pass ? ks_x : ks_y;
+            const float sg = pass ? sig_x : sig_y;
+            float v = 0.f;
+            if (static_cast<int>(threadIdx.x) < ks) {
+                const float t = static_cast<float>(static_cast<int>(threadIdx.x) - ks / 2);
+                v = expf(-(t * t) / (2.0f * sg * sg));
+            }
+            (pass ? gx : gy)[threadIdx.x] = v;
+        }
+    }
+    __syncthreads();
+    float sy = 0.f, sx = 0.f;
+    for (int i = 0; i < ks_y; ++i) sy += gy[i];
+    for (int i = 0; i < ks_x; ++i) sx += gx[i];
+    const float ny = 1.0f / sy, nx = 1.0f / sx;
+    const float ry = Ho > 1 ? static_cast<float>(H - 1) / (Ho - 1) : 0.f;
+    const float rx = Wo > 1 ? static_cast<float>(W - 1) / (Wo - 1) : 0.f;
+    const int py = (ks_y - 1) / 2, px = (ks_x - 1) / 2;
+    const long long total = static_cast<long long>(planes) * Ho * Wo;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ox = static_cast<int>(idx % Wo);
+        const int oy = static_cast<int>((idx / Wo) % Ho);
+        const int pl = static_cast<int>(idx / (static_cast<long long>(Wo) * Ho));
+        const float* src = img + static_cast<long long>(pl) * H * W;
+        const float fy = oy * ry, fx = ox * rx;
+        const int y0 = static_cast<int>(floorf(fy)), x0 = static_cast<int>(floorf(fx));
+        const float ty = fy - y0, tx = fx - x0;
+        float wy[4], wx[4];
+        {
+            const float A = -0.75f;
+            auto c1 = [&](float x) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; };          // |x| <= 1
+            auto c2 = [&](float x) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; };    // 1 < |x| < 2
+            wy[0] = c2(ty + 1.f); wy[1] = c1(ty); wy[2] = c1(1.f - ty); wy[3] = c2(2.f - ty);
+            wx[0] = c2(tx + 1.f); wx[1] = c1(tx); wx[2] = c1(1.f - tx); wx[3] = c2(2.f - tx);
+        }
+        float acc = 0.f;
+        for (int a = 0; a < 4; ++a) {
+            int yy = y0 - 1 + a;
+            yy = yy < 0 ? 0 : (yy > H - 1 ? H - 1 : yy);     // bicubic taps are clamped to the (blurred) image
+            float row = 0.f;
+            for (int b = 0; b < 4; ++b) {
+                int xx = x0 - 1 + b;
+                xx = xx < 0 ? 0 : (xx > W - 1 ? W - 1 : xx);
+                float blur = 0.f;                             // blurred pixel (yy, xx): reflect padding
+                for (int i = 0; i < ks_y; ++i) {
+                    int sy_ = yy + i - py;
+                    sy_ = sy_ < 0 ? -sy_ : (sy_ > H - 1 ? 2 * (H - 1) - sy_ : sy_);
+                    float line = 0.f;
+                    for (int j = 0; j < ks_x; ++j) {
+                        int sx_ = xx + j - px;
+                        sx_ = sx_ < 0 ? -sx_ : (sx_ > W - 1 ? 2 * (W - 1) - sx_ : sx_);
+                        line = fmaf(gx[j] * nx, src[static_cast<long long>(sy_) * W + sx_], line);
+                    }
+                    blur = fmaf(gy[i] * ny, line, blur);
+                }
+                row = fmaf(wx[b], blur, row);
+            }
+            acc = fmaf(wy[a], row, acc);
+        }
+        out[idx] = acc;
+    }
+}
+}  // namespace mofa
+
+extern "C" int mofa_resize_antialias(const void* img, void* out, int32_t planes, int32_t H, int32_t W, int32_t Ho,
+                                     int32_t Wo, mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!img || !out || planes <= 0 || H <= 1 || W <= 1 || Ho <= 0 || Wo <= 0) {
+        mofa::set_last_error("mofa_resize_antialias: bad arguments");
+        return MOFA_ERR_ARG;
+    }
+    auto sigma = [](int in, int o) {
+        const float s = (static_cast<float>(in) / o - 1.0f) / 2.0f;
+        return s > 0.001f ? s : 0.001f;
+    };
+    auto ksize = [](float s) {
+        const float k = 4.0f * s > 3.0f ? 4.0f * s : 3.0f;
+        int ks = static_cast<int>(k);
+        return ks % 2 == 0 ? ks + 1 : ks;
+    };
+    const float sy = sigma(H, Ho), sx = sigma(W, Wo);
+    const int ky = ksize(sy), kx = ksize(sx);
+    if (ky > 63 || kx > 63 || ky / 2 >= H || kx / 2 >= W) {
+        mofa::set_last_error("mofa_resize_antialias: reduction factor too large for the 63-tap blur (%d x %d taps)", ky, kx);
+        return MOFA_ERR_ARG;
+    }
+    const long long total = static_cast<long long>(planes) * Ho * Wo;
+    long long g = (total + 255) / 256;
+    if (g > 148LL * 8) g = 148LL * 8;
+    mofa::resize_antialias_kernel<<<static_cast<unsigned>(g), 256, 0, stream>>>(
+        static_cast<const float*>(img), static_cast<float*>(out), planes, H, W, Ho, Wo, sy, sx, ky, kx);
+    return mofa::check_launch("mofa_resize_antialias");
+}
+
+namespace mofa {
 // Drag-flow post-processing of T/run_gradio.py:251-277, 330-333 in one pass over the output [F, 2, H, W]:
 // (flow * brush) at 384^2 -> nearest resize -> x (W/Ws, H/Hs), fp16 roundings where the reference has them, then
 // where((flow_in != 0).all(channel), flow_in, flow_out).

@@ -23,6 +23,7 @@ EXPORTS = [
     "mofa_timestep_embedding", "mofa_softsplat_avg", "mofa_cfg_euler_step", "mofa_softmax_rows",
     "mofa_vae_time_conv_out", "mofa_im2col", "mofa_pool2d", "mofa_resize_bilinear_ac", "mofa_cmp_fuser",
     "mofa_copy_cols", "mofa_flow_pyramid", "mofa_mask_blend", "mofa_downsample_nearest", "mofa_flow_post",
+    "mofa_resize_antialias",
 ]
 
 
@@ -85,6 +86,7 @@ def load():
     lib.mofa_mask_blend.argtypes = [vp, vp, vp, vp, i64, i32, i64, vp]
     lib.mofa_downsample_nearest.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     lib.mofa_flow_post.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.mofa_resize_antialias.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     _lib = lib
     return lib
 
@@ -402,4 +404,14 @@ def flow_post(flow_in, out, F, Hs, Ws, H, W, brush=None, flow_out=None):
     _chk_h(flow_in, out, brush, flow_out)
     _check(load().mofa_flow_post(_p(flow_in), _p(brush), _p(flow_out), _p(out), F, Hs, Ws, H, W, _stream()),
            "mofa_flow_post")
+    return out
+
+
+def resize_antialias(img, out):
+    """img fp32 [N, C, H, W] -> out fp32 [N, C, Ho, Wo]: Gaussian pre-blur + bicubic(align_corners=True) (CLIP input)."""
+    assert img.is_cuda and out.is_cuda and img.dtype == out.dtype == torch.float32
+    assert img.is_contiguous() and out.is_contiguous()
+    n, c, H, W = img.shape
+    _check(load().mofa_resize_antialias(_p(img), _p(out), n * c, H, W, out.shape[-2], out.shape[-1], _stream()),
+           "mofa_resize_antialias")
     return out

@@ -71,32 +71,6 @@ def _to_unit_tensor(image, height=None, width=None):
     raise ValueError(f"unsupported image type {type(image)}")
 
 
-def _gauss_kernel(size, sigma):
-    x = torch.arange(size, dtype=torch.float32) - size // 2
-    if size % 2 == 0:
-        x = x + 0.5
-    k = torch.exp(-x.pow(2) / (2 * sigma * sigma))
-    return k / k.sum()
-
-
-def _resize_with_antialiasing(img, size):
-    """Gaussian pre-blur (sigma = (factor-1)/2, two-sigma odd kernel, reflect padding) then bicubic with
-    align_corners=True -- the CLIP-side resize of pipeline.py:532-562."""
-    if img.ndim == 3:
-        img = img[None]
-    h, w = img.shape[-2:]
-    sig = (max((h / size[0] - 1.0) / 2.0, 0.001), max((w / size[1] - 1.0) / 2.0, 0.001))
-    ks = [int(max(4.0 * s, 3)) for s in sig]
-    ks = [k + 1 if k % 2 == 0 else k for k in ks]
-    c = img.shape[1]
-    kx = _gauss_kernel(ks[1], sig[1]).to(img).view(1, 1, 1, -1).expand(c, 1, 1, -1)
-    ky = _gauss_kernel(ks[0], sig[0]).to(img).view(1, 1, -1, 1).expand(c, 1, -1, 1)
-    px, py = (ks[1] - 1) // 2, (ks[0] - 1) // 2
-    out = F.conv2d(F.pad(img, (px, ks[1] - 1 - px, 0, 0), mode="reflect"), kx, groups=c)
-    out = F.conv2d(F.pad(out, (0, 0, py, ks[0] - 1 - py), mode="reflect"), ky, groups=c)
-    return F.interpolate(out, size=size, mode="bicubic", align_corners=True)
-
-
 class FlowControlNetPipeline:
     model_cpu_offload_seq = "image_encoder->unet->vae"
     _callback_tensor_inputs = ["latents"]
@@ -159,8 +133,10 @@ class FlowControlNetPipeline:
     def _encode_image(self, image, device, num_videos_per_prompt, do_classifier_free_guidance):
         """pipeline.py:114-141 (Q3: [0,1] image, antialiased bicubic to 224, no CLIP mean/std)."""
         dtype = next(self.image_encoder.parameters()).dtype
-        img = _to_unit_tensor(image).to(device)  # blur + bicubic run on the device, not on the host cores
-        img = _resize_with_antialiasing(img, (224, 224)).to(device=device, dtype=dtype)
+        img = _to_unit_tensor(image).to(device=device, dtype=torch.float32).contiguous()
+        small = torch.empty(img.shape[0], img.shape[1], 224, 224, dtype=torch.float32, device=device)
+        self._ops.resize_antialias(img, small)  # Gaussian pre-blur + bicubic(align_corners) fused (pipeline.py:532-640)
+        img = small.to(dtype)
         emb = self.image_encoder(img).image_embeds.unsqueeze(1)
         emb = emb.repeat(1, num_videos_per_prompt, 1)
         if do_classifier_free_guidance:

@@ -344,3 +344,10 @@ def flow_post(flow_in, out, F, Hs, Ws, H, W, brush=None, flow_out=None):
         a = torch.where(keep, a, b)
     out.view(F, 2, H, W).copy_(a)
     return out
+
+
+def resize_antialias(img, out):
+    """pipeline.py:532-640 as restated (two separable passes + F.interpolate) in oracle/pipeline.py."""
+    from oracle.pipeline import resize_with_antialiasing
+    out.copy_(resize_with_antialiasing(img.float().cpu(), tuple(out.shape[-2:])).to(out.device))
+    return out

@@ -35,3 +35,16 @@ def test_vae_time_conv_out():
     torch.cuda.synchronize()
     assert torch.allclose(o32, r32, atol=1e-4, rtol=1e-4)
     assert (ou8.int() - ru8.int()).abs().max().item() <= 1
+
+
+def test_resize_antialias_matches_reference_resize():
+    """CLIP-side resize (pipeline.py:532-640): fused blur + bicubic kernel vs the two-pass PyTorch restatement."""
+    from mofa_video_b200 import lib
+    g = torch.Generator().manual_seed(0)
+    for (H, W, Ho, Wo) in [(576, 1024, 224, 224), (128, 192, 224, 224), (384, 384, 224, 224), (300, 700, 64, 96)]:
+        img = torch.rand(1, 3, H, W, generator=g).cuda()
+        out = torch.empty(1, 3, Ho, Wo, dtype=torch.float32, device="cuda")
+        ref = torch.empty_like(out)
+        lib.resize_antialias(img, out)
+        R.resize_antialias(img, ref)
+        assert (out - ref).abs().max().item() < 2e-5, (H, W)
