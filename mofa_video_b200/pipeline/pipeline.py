@@ -198,6 +198,45 @@ class FlowControlNetPipeline:
                 raise ValueError(f"unknown output_type {output_type}")
         return outs
 
+    def _clip_inputs(self, image, controlnet_condition, height, width, num_frames, num_inference_steps, generator,
+                     latents, noise_aug_strength, fps, motion_bucket_id, max_guidance_scale, batch_size=1,
+                     num_videos_per_prompt=1):
+        """Steps 0-6 of the reference __call__ shared by the Traj / Keypoint / Hybrid pipelines (pipeline.py:324-441):
+        input checks, CLIP embedding (Q3), VAE latents of the noise-augmented frame (CPU RNG, Q7), added-time-id
+        constants (Q4), timesteps, initial latents x init_noise_sigma, the CFG-duplicated condition image in [-1, 1].
+        Returns (image_embeddings, image_latents, added_time_ids, latents, cond)."""
+        self.check_inputs(image, height, width)
+        if batch_size != 1 or num_videos_per_prompt != 1:
+            raise NotImplementedError("one clip per call (the reference's batch>1 path is unusable with one image, "
+                                      "pipeline.py:378-388,454); shard clips across processes/GPUs instead")
+        if max_guidance_scale <= 1.0:
+            raise ValueError("max_guidance_scale must be > 1: without CFG the reference substitutes the latents for "
+                             "the condition image and flow (pipeline.py:393,396), which is not a usable mode")
+        device = self._device
+        image_embeddings = self._encode_image(image, device, num_videos_per_prompt, True)
+        emb_dtype = image_embeddings.dtype
+        img = _to_unit_tensor(image, height, width).to(device) * 2.0 - 1.0
+        gen_cpu = generator if isinstance(generator, torch.Generator) and generator.device.type == "cpu" else None
+        noise = torch.randn(img.shape, generator=gen_cpu, dtype=img.dtype)
+        img = img + noise_aug_strength * noise.to(img.device)
+        needs_upcasting = self.vae.dtype == torch.float16 and self.vae.config.force_upcast
+        if needs_upcasting:
+            self.vae.to(dtype=torch.float32)
+        image_latents = self._encode_vae_image(img.to(self.vae.dtype), device, num_videos_per_prompt, True)
+        image_latents = image_latents.to(emb_dtype)
+        if needs_upcasting:
+            self.vae.to(dtype=torch.float16)
+        # added time ids: computed from the arguments, then overwritten by constants (Q4, pipeline.py:430-440)
+        _get_add_time_ids(noise_aug_strength, emb_dtype, batch_size, fps - 1, motion_bucket_id, unet=self.unet)
+        added_time_ids = torch.cat([_get_add_time_ids(0.02, emb_dtype, batch_size, 6, 128, unet=self.unet)] * 2)
+        added_time_ids = added_time_ids.to(device)
+        self.scheduler.set_timesteps(num_inference_steps, device=device)
+        latents = self.prepare_latents(batch_size, num_frames, self.unet.config.in_channels, height, width, emb_dtype,
+                                       device, generator, latents)
+        cond = _to_unit_tensor(controlnet_condition, height, width) * 2.0 - 1.0
+        cond = torch.cat([cond] * 2).to(device, latents.dtype)
+        return image_embeddings, image_latents, added_time_ids, latents, cond
+
     # ------------------------------------------------------------------ the call
     @torch.no_grad()
     def __call__(self, image, controlnet_condition=None, controlnet_flow=None, height: int = 576, width: int = 1024,
@@ -214,51 +253,14 @@ class FlowControlNetPipeline:
         width = width or self.unet.config.sample_size * self.vae_scale_factor
         num_frames = num_frames if num_frames is not None else self.unet.config.num_frames
         decode_chunk_size = decode_chunk_size if decode_chunk_size is not None else num_frames
-        self.check_inputs(image, height, width)
-        if batch_size != 1 or num_videos_per_prompt != 1:
-            raise NotImplementedError("one clip per call (the reference's batch>1 path is unusable with one image, "
-                                      "pipeline.py:378-388,454); shard clips across processes/GPUs instead")
         device = self._device
-        do_cfg = max_guidance_scale > 1.0
-        if not do_cfg:
-            raise ValueError("max_guidance_scale must be > 1: without CFG the reference substitutes the latents for "
-                             "the condition image and flow (pipeline.py:393,396), which is not a usable mode")
         ev = {k: (torch.cuda.Event(enable_timing=True) if device.type == "cuda" else _NoEvent())
               for k in ("t0", "enc", "loop", "dec")}
         ev["t0"].record()
-
-        # 3. CLIP image embedding
-        image_embeddings = self._encode_image(image, device, num_videos_per_prompt, do_cfg)
-        emb_dtype = image_embeddings.dtype
-        fps = fps - 1
-
-        # 4. VAE-encode the (noise-augmented) conditioning frame; CPU RNG like the reference (Q7)
-        img = _to_unit_tensor(image, height, width).to(device) * 2.0 - 1.0
-        gen_cpu = generator if isinstance(generator, torch.Generator) and generator.device.type == "cpu" else None
-        noise = torch.randn(img.shape, generator=gen_cpu, dtype=img.dtype)
-        img = img + noise_aug_strength * noise.to(img.device)
-        vae_dtype = self.vae.dtype
-        needs_upcasting = vae_dtype == torch.float16 and self.vae.config.force_upcast
-        if needs_upcasting:
-            self.vae.to(dtype=torch.float32)
-        image_latents = self._encode_vae_image(img.to(self.vae.dtype), device, num_videos_per_prompt, do_cfg)
-        image_latents = image_latents.to(emb_dtype)
-        if needs_upcasting:
-            self.vae.to(dtype=torch.float16)
-
-        # 5. added time ids: computed from the arguments, then overwritten by constants (Q4, pipeline.py:430-440)
-        _get_add_time_ids(noise_aug_strength, emb_dtype, batch_size, fps, motion_bucket_id, unet=self.unet)
-        added_time_ids = torch.cat([_get_add_time_ids(0.02, emb_dtype, batch_size, 6, 128, unet=self.unet)] * 2)
-        added_time_ids = added_time_ids.to(device)
-
-        self.scheduler.set_timesteps(num_inference_steps, device=device)
+        image_embeddings, image_latents, added_time_ids, latents, cond = self._clip_inputs(
+            image, controlnet_condition, height, width, num_frames, num_inference_steps, generator, latents,
+            noise_aug_strength, fps, motion_bucket_id, max_guidance_scale, batch_size, num_videos_per_prompt)
         timesteps = self.scheduler.timesteps
-        num_channels_latents = self.unet.config.in_channels
-        latents = self.prepare_latents(batch_size, num_frames, num_channels_latents, height, width, emb_dtype, device,
-                                       generator, latents)
-
-        cond = (_to_unit_tensor(controlnet_condition, height, width) * 2.0 - 1.0)
-        cond = torch.cat([cond] * 2).to(device, latents.dtype)
         if controlnet_flow is None or controlnet_flow.shape[1] != num_frames - 1:
             raise ValueError(f"controlnet_flow must be [1, {num_frames - 1}, 2, H, W]")
         controlnet_flow = torch.cat([controlnet_flow] * 2).to(device, latents.dtype)

@@ -11,8 +11,7 @@ import torch
 import torch.nn.functional as F
 
 from mofa_video_b200 import lib as _lib
-from mofa_video_b200.pipeline.pipeline import (FlowControlNetPipeline as _TrajPipeline, FlowControlNetPipelineOutput,
-                                               _get_add_time_ids, _to_unit_tensor)
+from mofa_video_b200.pipeline.pipeline import FlowControlNetPipeline as _TrajPipeline, FlowControlNetPipelineOutput
 
 
 def level_masks(mask, h, w, n_levels, T, device):
@@ -73,30 +72,12 @@ class FlowControlNetPipeline(_TrajPipeline):
         ops = self._ops
         num_frames = num_frames if num_frames is not None else self.unet.config.num_frames
         decode_chunk_size = decode_chunk_size if decode_chunk_size is not None else num_frames
-        self.check_inputs(image, height, width)
-        if batch_size != 1 or num_videos_per_prompt != 1:
-            raise NotImplementedError("one clip per call")
         if num_frames != self.unet.config.num_frames:
             raise ValueError(f"num_frames must equal the UNet's num_frames ({self.unet.config.num_frames})")
-        if max_guidance_scale <= 1.0:
-            raise ValueError("max_guidance_scale must be > 1 (classifier-free guidance is how the adapters are driven)")
         device = self._device
-        image_embeddings = self._encode_image(image, device, 1, True)
-        emb_dtype = image_embeddings.dtype
-        img = _to_unit_tensor(image, height, width).to(device) * 2.0 - 1.0
-        gen_cpu = generator if isinstance(generator, torch.Generator) and generator.device.type == "cpu" else None
-        img = img + noise_aug_strength * torch.randn(img.shape, generator=gen_cpu, dtype=img.dtype).to(img.device)
-        needs_upcasting = self.vae.dtype == torch.float16 and self.vae.config.force_upcast
-        if needs_upcasting:
-            self.vae.to(dtype=torch.float32)
-        image_latents = self._encode_vae_image(img.to(self.vae.dtype), device, 1, True).to(emb_dtype)
-        if needs_upcasting:
-            self.vae.to(dtype=torch.float16)
-        added_time_ids = torch.cat([_get_add_time_ids(0.02, emb_dtype, 1, 6, 128, unet=self.unet)] * 2).to(device)
-        self.scheduler.set_timesteps(num_inference_steps, device=device)
-        latents = self.prepare_latents(1, num_frames, self.unet.config.in_channels, height, width, emb_dtype, device,
-                                       generator, latents)
-        cond = torch.cat([_to_unit_tensor(controlnet_condition, height, width) * 2.0 - 1.0] * 2).to(device, torch.float16)
+        image_embeddings, image_latents, added_time_ids, latents, cond = self._clip_inputs(
+            image, controlnet_condition, height, width, num_frames, num_inference_steps, generator, latents,
+            noise_aug_strength, fps, motion_bucket_id, max_guidance_scale, batch_size, num_videos_per_prompt)
         flow = torch.cat([controlnet_flow] * 2).to(device, torch.float16)
         dflow = torch.cat([drag_flow] * 2).to(device, torch.float16)
         ldmk = torch.cat([landmarks] * 2).to(device, torch.float16)
