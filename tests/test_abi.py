@@ -49,3 +49,27 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     g = lib.GemmArgs()
     assert so.mofa_gemm(ctypes.byref(g), None) == -1
     assert b"null" in so.mofa_last_error()
+
+
+def test_header_is_plain_c_and_cxx(tmp_path):
+    """The boundary is a C ABI: include/mofa_b200.h must compile as C99 and as C++17 on its own (no torch / CUDA types),
+    and a C translation unit must be able to take the address of every declared entry point."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        import pytest
+        pytest.skip("no gcc")
+    hdr = os.path.join(ROOT, "include", "mofa_b200.h")
+    subprocess.run(["gcc", "-x", "c", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", hdr], check=True)
+    subprocess.run(["g++", "-x", "c++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", hdr], check=True)
+    names = _declared()
+    src = tmp_path / "use.c"
+    src.write_text('#include "mofa_b200.h"\nconst void* table[] = {' + ", ".join(f"(const void*){n}" for n in names) +
+                   "};\nint main(void) { return table[0] == 0; }\n")
+    so = os.path.join(ROOT, "mofa_video_b200", "libmofa_b200.so")
+    if not os.path.exists(so):
+        import pytest
+        pytest.skip("library not built")
+    # link against the built library: every declared symbol must resolve (unresolved ones fail the link)
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), so, "-o", str(tmp_path / "use"),
+                    "-Wl,--unresolved-symbols=ignore-in-shared-libs"], check=True)
