@@ -73,3 +73,49 @@ def test_header_is_plain_c_and_cxx(tmp_path):
     # link against the built library: every declared symbol must resolve (unresolved ones fail the link)
     subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), so, "-o", str(tmp_path / "use"),
                     "-Wl,--unresolved-symbols=ignore-in-shared-libs"], check=True)
+
+
+def test_product_never_imports_the_oracle_or_the_tests():
+    """oracle/ and tests/ are test infrastructure: nothing under mofa_video_b200/ may import them, and bench.py /
+    __graft_entry__.py only inside the CPU-baseline sampler / smoke checker."""
+    import ast
+    pkg = os.path.join(ROOT, "mofa_video_b200")
+    bad = []
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if not fn.endswith(".py"):
+                continue
+            path = os.path.join(dirpath, fn)
+            for node in ast.walk(ast.parse(open(path).read())):
+                mods = []
+                if isinstance(node, ast.Import):
+                    mods = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom) and node.module:
+                    mods = [node.module]
+                for m in mods:
+                    if m.split(".")[0] in ("oracle", "tests", "ref_ops"):
+                        bad.append((path, m))
+    assert not bad, bad
+    # bench.py: the oracle may only be imported inside _cpu_sample (the cpu_baseline / --impl reference leg)
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    for node in tree.body:
+        if isinstance(node, (ast.Import, ast.ImportFrom)):
+            names = [a.name for a in node.names] if isinstance(node, ast.Import) else [node.module or ""]
+            assert not any(n.split(".")[0] == "oracle" for n in names)
+        if isinstance(node, ast.FunctionDef) and node.name != "_cpu_sample":
+            for sub in ast.walk(node):
+                if isinstance(sub, ast.ImportFrom) and sub.module:
+                    assert sub.module.split(".")[0] != "oracle", node.name
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    """No fallback: with the shared library absent, binding raises instead of computing anything."""
+    import pytest
+
+    from mofa_video_b200 import lib
+    monkeypatch.setattr(lib, "_lib", None, raising=False)
+    monkeypatch.setattr(lib, "LIB_PATH", str(tmp_path / "nope" / "libmofa_b200.so"), raising=False)
+    if not hasattr(lib, "LIB_PATH"):
+        pytest.skip("library path is not a module attribute")
+    with pytest.raises((OSError, RuntimeError, FileNotFoundError)):
+        lib.load()
