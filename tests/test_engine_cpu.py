@@ -67,3 +67,13 @@ def test_engine_rectangular_and_more_frames():
     r = run_pair(16, 32, cfg)
     e = rel_err(r["out"], r["ref"])
     assert e < 5e-3, f"unet output rel err {e}"
+
+
+def test_engine_full_frame_count():
+    """T = 25 frames (the SVD-XT clip length: frame-position embedding table, temporal attention / conv over 25 tokens,
+    CFG batch of 50 frames) at the tiny channel widths."""
+    cfg = dict(fixtures.TINY_CONFIG)
+    cfg["num_frames"] = 25
+    r = run_pair(16, 16, cfg)
+    e = rel_err(r["out"], r["ref"])
+    assert e < 5e-3, f"unet output rel err {e}"

@@ -177,3 +177,10 @@ def test_native_vae_encoder_matches_torch_module():
     assert out.shape == ref.shape == (1, 4, 16, 24)
     e = rel_err(out, ref)
     assert e < 2e-2, f"vae encode rel err {e}"
+
+
+def test_step_full_frame_count_tiny_channels():
+    """T = 25 (the real clip length) against the oracle on the GPU: temporal attention / conv over 25 frames."""
+    cfg = dict(fixtures.TINY_CONFIG)
+    cfg["num_frames"] = 25
+    one_step(cfg, 16, 16, 1e-2)
