@@ -248,9 +248,106 @@ def make_hourglass():
     print("hourglass golden written:", tuple(out.shape), tuple(mask.shape))
 
 
+def make_networks():
+    """Execute the reference's OWN network definitions and forward graphs -- models/unet_spatio_temporal_condition_
+    controlnet.py (UNet: residual injection, Q1), models/controlnet_sdv.py (ControlNetSDVModel base class) and
+    models/svdxt_featureflow_forward_controlnet_s2d_fixcmp_norefine.py (FlowControlNet.forward, get_warped_frames, Q2)
+    -- on CPU.  The diffusers 0.24 *blocks* they instantiate are absent here, so the module names they import
+    (diffusers.models.unet_3d_blocks / embeddings) are bound to oracle/d24_blocks.py; models.softsplat (CuPy) is bound
+    to oracle/softsplat.py.  What this pins: the constructors' channel bookkeeping and state-dict layout (the oracle's
+    state dict must load strictly), and every line of the two forward graphs.  What stays unpinned: the arithmetic
+    inside the diffusers blocks."""
+    install_stubs()
+    import importlib.util
+
+    from oracle import d24_blocks as D
+    from oracle import fixtures
+    from oracle.softsplat import softsplat as oracle_softsplat
+
+    class ModelMixin(torch.nn.Module):
+        @property
+        def dtype(self):
+            return next(self.parameters()).dtype
+
+        @property
+        def device(self):
+            return next(self.parameters()).device
+
+    _mod("diffusers.models.modeling_utils", ModelMixin=ModelMixin)
+    _mod("diffusers.loaders", FromOriginalControlnetMixin=type("FromOriginalControlnetMixin", (), {}),
+         UNet2DConditionLoadersMixin=type("UNet2DConditionLoadersMixin", (), {}))
+    _mod("diffusers.models.embeddings", TimestepEmbedding=D.TimestepEmbedding, Timesteps=D.Timesteps,
+         TextImageProjection=None, TextImageTimeEmbedding=None, TextTimeEmbedding=None)
+    _mod("diffusers.models.unet_3d_blocks", get_down_block=D.get_down_block, get_up_block=D.get_up_block,
+         UNetMidBlockSpatioTemporal=D.UNetMidBlockSpatioTemporal,
+         CrossAttnDownBlockSpatioTemporal=D.CrossAttnDownBlockSpatioTemporal,
+         DownBlockSpatioTemporal=D.DownBlockSpatioTemporal)
+    _mod("diffusers.models", UNetSpatioTemporalConditionModel=ModelMixin)
+    sys.path.insert(0, REF)
+
+    def load(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[name] = m
+        spec.loader.exec_module(m)
+        return m
+
+    ref_unet = load("ref_unet", "models/unet_spatio_temporal_condition_controlnet.py")
+    ref_cn = load("models.controlnet_sdv", "models/controlnet_sdv.py")
+    _mod("models.softsplat", softsplat=oracle_softsplat)
+    _mod("models.cmp")
+    _mod("models.cmp.models")
+    _mod("models.cmp.utils")
+    ref_fcn = load("ref_fcn_full", "models/svdxt_featureflow_forward_controlnet_s2d_fixcmp_norefine.py")
+
+    cfg = dict(fixtures.TINY_CONFIG)
+    o_unet, o_ad = fixtures.make_models(cfg, seed=0, adapter_gain=20.0)
+    torch.manual_seed(0)
+    r_unet = ref_unet.UNetSpatioTemporalConditionControlNetModel(**cfg).eval()
+    # FlowControlNet.__init__ (FCN.py:183-221) calls super().__init__() and FlowControlNetFirstFrameEncoder() WITHOUT
+    # arguments, so the reference adapter only exists at the SVD-XT widths (1.4 GB).  For a fixture of test size the
+    # two constructors' *default sizes* are overridden here; no forward code is touched.
+    base_init = ref_cn.ControlNetSDVModel.__init__
+    enc_init = ref_fcn.FlowControlNetFirstFrameEncoder.__init__
+    boc = cfg["block_out_channels"]
+    ref_cn.ControlNetSDVModel.__init__ = lambda self, *a, **k: base_init(self, *a, **{**cfg, **k})
+    ref_fcn.FlowControlNetFirstFrameEncoder.__init__ = \
+        lambda self, *a, **k: enc_init(self, *a, **{"c_in": boc[0], "channels": list(boc[:3]), **k})
+    try:
+        r_ad = ref_fcn.FlowControlNet(**cfg).eval()
+    finally:
+        ref_cn.ControlNetSDVModel.__init__ = base_init
+        ref_fcn.FlowControlNetFirstFrameEncoder.__init__ = enc_init
+    r_unet.load_state_dict(o_unet.state_dict(), strict=True)
+    r_ad.load_state_dict(o_ad.state_dict(), strict=True)
+    inp = fixtures.make_step_inputs(cfg, 16, 16)
+    t = torch.tensor(1.6377)
+    with torch.no_grad():
+        dres, mid, _, _ = r_ad(inp["sample"], t, inp["encoder_hidden_states"], inp["added_time_ids"],
+                               controlnet_cond=inp["controlnet_cond"], controlnet_flow=inp["controlnet_flow"],
+                               conditioning_scale=0.8, return_dict=False)
+        out = r_unet(inp["sample"], t, inp["encoder_hidden_states"], down_block_additional_residuals=dres,
+                     mid_block_additional_residual=mid, added_time_ids=inp["added_time_ids"], return_dict=False)[0]
+
+    def digest(x):  # compact fingerprint of a tensor: moments + a strided sample
+        f = x.flatten()
+        return {"shape": tuple(x.shape), "mean": f.mean().item(), "abs_mean": f.abs().mean().item(),
+                "sample": f[:: max(1, f.numel() // 64)][:64].clone()}
+
+    g = {"config": cfg, "seed": 0, "adapter_gain": 20.0, "latent_hw": (16, 16), "timestep": float(t),
+         "conditioning_scale": 0.8, "unet_out": out.clone(),
+         "mid": mid.clone(), "down_digests": [digest(d) for d in dres],
+         "n_params": {"unet": sum(p.numel() for p in r_unet.parameters()),
+                      "adapter": sum(p.numel() for p in r_ad.parameters())}}
+    torch.save(g, os.path.join(OUT, "networks_tiny.pt"))
+    print("network golden written:", tuple(out.shape), float(out.abs().mean()), g["n_params"])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     make_scheduler()
+    if "--networks" in sys.argv or "--all" in sys.argv:
+        make_networks()
     if "--all" in sys.argv:
         make_adapter_encoders()
         make_cmp()

@@ -7,9 +7,12 @@
       FlowControlNetConditioningEmbeddingSVD :66-101, FlowControlNetFirstFrameEncoder :130-155,
       get_warped_frames :223-234, forward :236-383 (warp adds = quirk Q2)
 
-Blocks come from oracle/d24_blocks.py (parity unpinned, see there).  The two adapter-only encoders are
-PINNED against the reference's own classes (tests/golden/adapter_encoders.pt, oracle/make_goldens.py).
-State-dict key names equal the reference's, so reference-layout checkpoints load.
+PINNED (forward graphs, constructor bookkeeping, state-dict layout): tests/golden/networks_tiny.pt is produced by
+executing the reference's own three files above on CPU with this oracle's state dict loaded strictly
+(oracle/make_goldens.py:make_networks); tests/test_oracle.py requires this file's forward to reproduce it to 1e-6
+(measured: bit-exact).  The two adapter-only encoders are additionally pinned by tests/golden/adapter_encoders.pt.
+What remains unpinned is the arithmetic INSIDE the diffusers blocks, which come from oracle/d24_blocks.py on both
+sides of that comparison (see there).
 """
 import torch
 import torch.nn as nn

@@ -5,6 +5,7 @@ import os
 import pytest
 import torch
 
+from oracle import fixtures
 from oracle import scheduler as osched
 from oracle.softsplat import softsplat
 
@@ -102,3 +103,30 @@ def test_zero_convs_make_adapter_a_noop():
         dres, mid, _, _ = ad(inp["sample"], torch.tensor(1.0), inp["encoder_hidden_states"], inp["added_time_ids"],
                              controlnet_cond=inp["controlnet_cond"], controlnet_flow=inp["controlnet_flow"])
     assert all(d.abs().max() == 0 for d in dres) and mid.abs().max() == 0
+
+
+def test_network_forward_graphs_match_reference_fixture():
+    """tests/golden/networks_tiny.pt comes from EXECUTING the reference's own UNet / ControlNetSDVModel / FlowControlNet
+    definitions and forward code (oracle/make_goldens.py:make_networks; the absent diffusers block classes are bound to
+    oracle/d24_blocks.py).  The oracle's restated forward graphs must reproduce it exactly: residual injection with the
+    Q1 multiplicities, warp-add placement (Q2), conditioning scale, time-embedding plumbing, state-dict layout."""
+    g = _gold("networks_tiny.pt")
+    cfg = g["config"]
+    unet, ad = fixtures.make_models(cfg, seed=g["seed"], adapter_gain=g["adapter_gain"])
+    assert sum(p.numel() for p in unet.parameters()) == g["n_params"]["unet"]
+    assert sum(p.numel() for p in ad.parameters()) == g["n_params"]["adapter"]
+    inp = fixtures.make_step_inputs(cfg, *g["latent_hw"])
+    t = torch.tensor(g["timestep"])
+    with torch.no_grad():
+        dres, mid, _, _ = ad(inp["sample"], t, inp["encoder_hidden_states"], inp["added_time_ids"],
+                             controlnet_cond=inp["controlnet_cond"], controlnet_flow=inp["controlnet_flow"],
+                             conditioning_scale=g["conditioning_scale"])
+        out = unet(inp["sample"], t, inp["encoder_hidden_states"], dres, mid, added_time_ids=inp["added_time_ids"])[0]
+    assert (out - g["unet_out"]).abs().max().item() <= 1e-6 * g["unet_out"].abs().max().item()
+    assert (mid - g["mid"]).abs().max().item() <= 1e-6 * g["mid"].abs().max().item()
+    assert len(dres) == len(g["down_digests"]) == 12
+    for d, dg in zip(dres, g["down_digests"]):
+        f = d.flatten()
+        assert tuple(d.shape) == dg["shape"]
+        assert (f[:: max(1, f.numel() // 64)][:64] - dg["sample"]).abs().max().item() <= 1e-6
+        assert abs(f.abs().mean().item() - dg["abs_mean"]) <= 1e-6
