@@ -93,3 +93,27 @@ def make_step_inputs(config, H, W, seed=7, batch=2):
     flow = make_flow(T, 8 * H, 8 * W).half().float().repeat(batch, 1, 1, 1, 1)
     return dict(sample=sample, encoder_hidden_states=emb, added_time_ids=ids, controlnet_cond=cond,
                 controlnet_flow=flow)
+
+
+def make_ldmk_adapter(config, seed=3, gain=20.0):
+    """Keypoint (landmark) adapter oracle with every zero-initialised conv re-drawn so the occlusion branch and the
+    landmark embedding contribute; fp16-representable weights."""
+    from . import keypoint as kp
+    torch.manual_seed(seed)
+    ad = kp.FlowControlNetLdmk(**config)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        zero = list(ad.controlnet_down_blocks) + [ad.controlnet_mid_block, ad.controlnet_cond_embedding.conv_out,
+                                                  ad.controlnet_ldmk_embedding.conv_out] + list(ad.zero_outs.values())
+        for m in zero:
+            for p in m.parameters():
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+        for m in list(ad.controlnet_down_blocks) + [ad.controlnet_mid_block]:
+            m.weight.mul_(gain)
+        for m in list(ad.zero_outs.values()) + [ad.controlnet_ldmk_embedding.conv_out]:
+            m.weight.mul_(30.0)          # make the occlusion branch and the landmark embedding matter
+    _rescale(ad)
+    with torch.no_grad():
+        for p in ad.parameters():
+            p.copy_(p.half().float())
+    return ad.eval()

@@ -343,11 +343,106 @@ def make_networks():
     print("network golden written:", tuple(out.shape), float(out.abs().mean()), g["n_params"])
 
 
+def make_keypoint_network():
+    """Same as make_networks for the Keypoint adapter: executes /root/reference/MOFA-Video-Keypoint/models/ldmk_ctrlnet.py
+    (FlowControlNet.__init__ / get_warped_frames / forward with landmarks, :187-575), its controlnet_sdv.py and its
+    occlusion/hourglass.py.  The constructor hard-codes the SVD-XT widths (super().__init__() without arguments,
+    Conv2d(320, 320) ..., ForegroundMatting(1280)); the default sizes are overridden and the four zero_outs /
+    occlusions entries re-created from the reference's own classes at the test widths.  No forward code is touched."""
+    install_stubs()
+    import importlib.util
+
+    import torch.nn as nn
+
+    from oracle import d24_blocks as D
+    from oracle import fixtures
+    from oracle.softsplat import softsplat as oracle_softsplat
+    K = "/root/reference/MOFA-Video-Keypoint"
+
+    class ModelMixin(torch.nn.Module):
+        @property
+        def dtype(self):
+            return next(self.parameters()).dtype
+
+    _mod("diffusers.models.modeling_utils", ModelMixin=ModelMixin)
+    _mod("diffusers.loaders", FromOriginalControlnetMixin=type("FromOriginalControlnetMixin", (), {}),
+         UNet2DConditionLoadersMixin=type("UNet2DConditionLoadersMixin", (), {}))
+    _mod("diffusers.models.embeddings", TimestepEmbedding=D.TimestepEmbedding, Timesteps=D.Timesteps,
+         TextImageProjection=None, TextImageTimeEmbedding=None, TextTimeEmbedding=None)
+    _mod("diffusers.models.unet_3d_blocks", get_down_block=D.get_down_block, get_up_block=D.get_up_block,
+         UNetMidBlockSpatioTemporal=D.UNetMidBlockSpatioTemporal,
+         CrossAttnDownBlockSpatioTemporal=D.CrossAttnDownBlockSpatioTemporal,
+         DownBlockSpatioTemporal=D.DownBlockSpatioTemporal)
+    _mod("diffusers.models", UNetSpatioTemporalConditionModel=ModelMixin)
+
+    def load(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(K, rel))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[name] = m
+        spec.loader.exec_module(m)
+        return m
+
+    _mod("models")
+    ref_cn = load("models.controlnet_sdv", "models/controlnet_sdv.py")
+    _mod("models.softsplat", softsplat=oracle_softsplat)
+    _mod("models.cmp")
+    _mod("models.cmp.models")
+    _mod("models.cmp.utils")
+    _mod("models.occlusion")
+    ref_hg = load("models.occlusion.hourglass", "models/occlusion/hourglass.py")
+    ref_ldmk = load("ref_ldmk", "models/ldmk_ctrlnet.py")
+
+    # forward() adds the landmark embedding where `sample.shape[1] == 320` (a literal, :501): the first level keeps the
+    # SVD-XT width so that branch is exercised; the deeper levels are shrunk
+    cfg = dict(fixtures.TINY_CONFIG)
+    cfg.update(block_out_channels=(320, 128, 256, 256), num_attention_heads=(5, 2, 4, 4))
+    boc = cfg["block_out_channels"]
+    o_ad = fixtures.make_ldmk_adapter(cfg)
+    base_init = ref_cn.ControlNetSDVModel.__init__
+    enc_init = ref_ldmk.FlowControlNetFirstFrameEncoder.__init__
+    ref_cn.ControlNetSDVModel.__init__ = lambda self, *a, **k: base_init(self, *a, **{**cfg, **k})
+    ref_ldmk.FlowControlNetFirstFrameEncoder.__init__ = \
+        lambda self, *a, **k: enc_init(self, *a, **{"c_in": boc[0], "channels": list(boc[:3]), **k})
+    try:
+        r_ad = ref_ldmk.FlowControlNet(**cfg)
+    finally:
+        ref_cn.ControlNetSDVModel.__init__ = base_init
+        ref_ldmk.FlowControlNetFirstFrameEncoder.__init__ = enc_init
+    chans = {"8": boc[0], "16": boc[0], "32": boc[1], "64": boc[2]}
+    r_ad.zero_outs = nn.ModuleDict({k: nn.Conv2d(c, c, kernel_size=1) for k, c in chans.items()})
+    r_ad.occlusions = nn.ModuleDict({k: ref_hg.ForegroundMatting(c) for k, c in chans.items()})
+    r_ad.load_state_dict(o_ad.state_dict(), strict=True)
+    r_ad.eval()
+    H = W = 16
+    T = cfg["num_frames"]
+    inp = fixtures.make_step_inputs(cfg, H, W)
+    landmarks = torch.rand(1, T, 3, 8 * H, 8 * W, generator=torch.Generator().manual_seed(11)).half().float()
+    landmarks = landmarks.repeat(2, 1, 1, 1, 1)
+    t = torch.tensor(1.6377)
+    with torch.no_grad():
+        dres, mid, _, occ = r_ad(inp["sample"], t, inp["encoder_hidden_states"], inp["added_time_ids"],
+                                 controlnet_cond=inp["controlnet_cond"], controlnet_flow=inp["controlnet_flow"],
+                                 landmarks=landmarks, conditioning_scale=0.9, return_dict=False)
+
+    def digest(x):
+        f = x.flatten()
+        return {"shape": tuple(x.shape), "mean": f.mean().item(), "abs_mean": f.abs().mean().item(),
+                "sample": f[:: max(1, f.numel() // 64)][:64].clone()}
+
+    g = {"config": cfg, "latent_hw": (H, W), "timestep": float(t), "conditioning_scale": 0.9, "landmark_seed": 11,
+         "mid": mid.clone(), "down_digests": [digest(d) for d in dres], "occ_digests": [digest(m) for m in occ],
+         "n_params": sum(p.numel() for p in r_ad.parameters())}
+    torch.save(g, os.path.join(OUT, "keypoint_network_tiny.pt"))
+    print("keypoint network golden written:", tuple(mid.shape), float(mid.abs().mean()), g["n_params"])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     make_scheduler()
     if "--networks" in sys.argv or "--all" in sys.argv:
         make_networks()
+    if "--keypoint" in sys.argv:
+        make_keypoint_network()   # separate process from --networks: both bind sys.modules["models.*"]
     if "--all" in sys.argv:
         make_adapter_encoders()
         make_cmp()

@@ -10,25 +10,7 @@ from oracle import fixtures
 from oracle import keypoint as kp
 
 
-def make_ldmk_adapter(cfg, seed=3, gain=20.0):
-    torch.manual_seed(seed)
-    ad = kp.FlowControlNetLdmk(**cfg)
-    g = torch.Generator().manual_seed(seed + 1)
-    with torch.no_grad():
-        zero = list(ad.controlnet_down_blocks) + [ad.controlnet_mid_block, ad.controlnet_cond_embedding.conv_out,
-                                                  ad.controlnet_ldmk_embedding.conv_out] + list(ad.zero_outs.values())
-        for m in zero:
-            for p in m.parameters():
-                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
-        for m in list(ad.controlnet_down_blocks) + [ad.controlnet_mid_block]:
-            m.weight.mul_(gain)
-        for m in list(ad.zero_outs.values()) + [ad.controlnet_ldmk_embedding.conv_out]:
-            m.weight.mul_(30.0)          # make the occlusion branch and the landmark embedding matter
-    fixtures._rescale(ad)
-    with torch.no_grad():
-        for p in ad.parameters():
-            p.copy_(p.half().float())
-    return ad.eval()
+make_ldmk_adapter = fixtures.make_ldmk_adapter
 
 
 def to_cl(x):
