@@ -117,3 +117,24 @@ def make_ldmk_adapter(config, seed=3, gain=20.0):
         for p in ad.parameters():
             p.copy_(p.half().float())
     return ad.eval()
+
+
+def make_vae_and_clip(dim, seed=5):
+    """The two third-party constructor arguments of the pipeline, as small seeded PyTorch modules (the same objects
+    are handed to the reference pipeline here and to the oracle / engine in the tests)."""
+    from types import SimpleNamespace
+
+    from mofa_video_b200.models.autoencoder_kl_temporal_decoder import AutoencoderKLTemporalDecoder
+
+    class TinyClip(torch.nn.Module):
+        def __init__(self, d):
+            super().__init__()
+            self.proj = torch.nn.Linear(3 * 8 * 8, d)
+
+        def forward(self, x):
+            return SimpleNamespace(image_embeds=self.proj(torch.nn.functional.adaptive_avg_pool2d(x, 8).flatten(1)))
+
+    torch.manual_seed(seed)
+    vae = AutoencoderKLTemporalDecoder(block_out_channels=(32, 32, 64, 64)).eval()
+    clip = TinyClip(dim).eval()
+    return vae, clip

@@ -343,6 +343,146 @@ def make_networks():
     print("network golden written:", tuple(out.shape), float(out.abs().mean()), g["n_params"])
 
 
+def make_pipeline():
+    """Execute the reference's FlowControlNetPipeline.__call__ (/root/reference/MOFA-Video-Traj/pipeline/pipeline.py:
+    282-527, with _encode_image, _encode_vae_image, _get_add_time_ids, prepare_latents, _resize_with_antialiasing ...)
+    on CPU for 2 steps at 128x128x3 frames with the reference UNet / FlowControlNet (see make_networks), the
+    reference scheduler, and small seeded VAE / CLIP stand-ins.  Absent base classes are stubbed minimally:
+    DiffusionPipeline (register_modules, _execution_device, progress_bar, maybe_free_model_hooks) and
+    VaeImageProcessor (pil_to_numpy / numpy_to_pt / preprocess: PIL -> [0,1] -> NCHW -> 2x-1, diffusers 0.24 behaviour)."""
+    install_stubs()
+    import contextlib
+    import importlib.util
+
+    import numpy as np
+    import PIL.Image
+
+    from oracle import d24_blocks as D
+    from oracle import fixtures
+    from oracle.softsplat import softsplat as oracle_softsplat
+
+    class ModelMixin(torch.nn.Module):
+        @property
+        def dtype(self):
+            return next(self.parameters()).dtype
+
+    class DiffusionPipeline:
+        def __init__(self):
+            pass
+
+        def register_modules(self, **kw):
+            for k, v in kw.items():
+                setattr(self, k, v)
+
+        @property
+        def _execution_device(self):
+            return torch.device("cpu")
+
+        @contextlib.contextmanager
+        def progress_bar(self, total=None):
+            class _Bar:
+                def update(self, *a):
+                    pass
+            yield _Bar()
+
+        def maybe_free_model_hooks(self):
+            pass
+
+    class VaeImageProcessor:
+        def __init__(self, vae_scale_factor=8, do_resize=True, do_normalize=True):
+            self.vae_scale_factor = vae_scale_factor
+
+        @staticmethod
+        def pil_to_numpy(images):
+            if not isinstance(images, list):
+                images = [images]
+            return np.stack([np.array(im).astype(np.float32) / 255.0 for im in images], axis=0)
+
+        @staticmethod
+        def numpy_to_pt(images):
+            if images.ndim == 3:
+                images = images[..., None]
+            return torch.from_numpy(images.transpose(0, 3, 1, 2))
+
+        def preprocess(self, image, height=None, width=None):
+            if isinstance(image, PIL.Image.Image):
+                image = [image]
+            image = [im.resize((width, height), resample=PIL.Image.LANCZOS) if im.size != (width, height) else im
+                     for im in image]
+            return 2.0 * self.numpy_to_pt(self.pil_to_numpy(image)) - 1.0
+
+    _mod("diffusers.models.modeling_utils", ModelMixin=ModelMixin)
+    _mod("diffusers.loaders", FromOriginalControlnetMixin=type("FromOriginalControlnetMixin", (), {}),
+         UNet2DConditionLoadersMixin=type("UNet2DConditionLoadersMixin", (), {}))
+    _mod("diffusers.models.embeddings", TimestepEmbedding=D.TimestepEmbedding, Timesteps=D.Timesteps,
+         TextImageProjection=None, TextImageTimeEmbedding=None, TextTimeEmbedding=None)
+    _mod("diffusers.models.unet_3d_blocks", get_down_block=D.get_down_block, get_up_block=D.get_up_block,
+         UNetMidBlockSpatioTemporal=D.UNetMidBlockSpatioTemporal,
+         CrossAttnDownBlockSpatioTemporal=D.CrossAttnDownBlockSpatioTemporal,
+         DownBlockSpatioTemporal=D.DownBlockSpatioTemporal)
+    _mod("diffusers.models", UNetSpatioTemporalConditionModel=ModelMixin, AutoencoderKLTemporalDecoder=ModelMixin)
+    _mod("diffusers.image_processor", VaeImageProcessor=VaeImageProcessor)
+    _mod("diffusers.pipelines")
+    _mod("diffusers.pipelines.pipeline_utils", DiffusionPipeline=DiffusionPipeline)
+
+    def load(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[name] = m
+        spec.loader.exec_module(m)
+        return m
+
+    _mod("models")
+    ref_unet = load("models.unet_spatio_temporal_condition_controlnet",
+                    "models/unet_spatio_temporal_condition_controlnet.py")
+    ref_cn = load("models.controlnet_sdv", "models/controlnet_sdv.py")
+    _mod("models.softsplat", softsplat=oracle_softsplat)
+    _mod("models.cmp")
+    _mod("models.cmp.models")
+    _mod("models.cmp.utils")
+    ref_fcn = load("models.svdxt_featureflow_forward_controlnet_s2d_fixcmp_norefine",
+                   "models/svdxt_featureflow_forward_controlnet_s2d_fixcmp_norefine.py")
+    _mod("utils")
+    ref_sched = load("utils.scheduling_euler_discrete_karras_fix", "utils/scheduling_euler_discrete_karras_fix.py")
+    ref_pipe = load("ref_pipeline", "pipeline/pipeline.py")
+
+    cfg = dict(fixtures.TINY_CONFIG)
+    boc = cfg["block_out_channels"]
+    o_unet, o_ad = fixtures.make_models(cfg, seed=0, adapter_gain=20.0)
+    r_unet = ref_unet.UNetSpatioTemporalConditionControlNetModel(**cfg).eval()
+    base_init = ref_cn.ControlNetSDVModel.__init__
+    enc_init = ref_fcn.FlowControlNetFirstFrameEncoder.__init__
+    ref_cn.ControlNetSDVModel.__init__ = lambda self, *a, **k: base_init(self, *a, **{**cfg, **k})
+    ref_fcn.FlowControlNetFirstFrameEncoder.__init__ = \
+        lambda self, *a, **k: enc_init(self, *a, **{"c_in": boc[0], "channels": list(boc[:3]), **k})
+    try:
+        r_ad = ref_fcn.FlowControlNet(**cfg).eval()
+    finally:
+        ref_cn.ControlNetSDVModel.__init__ = base_init
+        ref_fcn.FlowControlNetFirstFrameEncoder.__init__ = enc_init
+    r_unet.load_state_dict(o_unet.state_dict(), strict=True)
+    r_ad.load_state_dict(o_ad.state_dict(), strict=True)
+    from oracle.scheduler import SVD_XT_SCHEDULER_CONFIG
+    sched = ref_sched.EulerDiscreteScheduler(**SVD_XT_SCHEDULER_CONFIG)
+    vae, clip = fixtures.make_vae_and_clip(cfg["cross_attention_dim"])
+    pipe = ref_pipe.FlowControlNetPipeline(vae=vae, image_encoder=clip, unet=r_unet, controlnet=r_ad, scheduler=sched,
+                                           feature_extractor=None)
+    H = W = 128
+    T = cfg["num_frames"]
+    img = fixtures.make_image(H, W)
+    pil = PIL.Image.fromarray((img.permute(1, 2, 0) * 255).round().to(torch.uint8).numpy())
+    flow = fixtures.make_flow(T, H, W)
+    lat0 = torch.randn(1, T, 4, H // 8, W // 8, generator=torch.Generator().manual_seed(9))
+    seen = []
+    out = pipe(pil, pil, flow, height=H, width=W, num_frames=T, num_inference_steps=2, latents=lat0.clone(),
+               generator=torch.Generator().manual_seed(11), output_type="latent", controlnet_cond_scale=0.8,
+               callback_on_step_end=lambda p_, i, t, kw: seen.append(float(t)) or {})
+    g = {"config": cfg, "hw": (H, W), "steps": 2, "latent_seed": 9, "generator_seed": 11, "cond_scale": 0.8,
+         "image_u8": torch.from_numpy(np.array(pil)), "latents": out.frames.clone(), "timesteps_seen": seen}
+    torch.save(g, os.path.join(OUT, "pipeline_tiny.pt"))
+    print("pipeline golden written:", tuple(out.frames.shape), float(out.frames.abs().mean()), seen)
+
+
 def make_keypoint_network():
     """Same as make_networks for the Keypoint adapter: executes /root/reference/MOFA-Video-Keypoint/models/ldmk_ctrlnet.py
     (FlowControlNet.__init__ / get_warped_frames / forward with landmarks, :187-575), its controlnet_sdv.py and its
@@ -441,6 +581,8 @@ if __name__ == "__main__":
     make_scheduler()
     if "--networks" in sys.argv or "--all" in sys.argv:
         make_networks()
+    if "--pipeline" in sys.argv:
+        make_pipeline()           # separate process as well
     if "--keypoint" in sys.argv:
         make_keypoint_network()   # separate process from --networks: both bind sys.modules["models.*"]
     if "--all" in sys.argv:

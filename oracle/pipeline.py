@@ -2,7 +2,9 @@
 /root/reference/MOFA-Video-Traj/pipeline/pipeline.py:282-527, runnable on CPU in fp32 with the oracle
 networks (oracle/models.py) and scheduler (oracle/scheduler.py).  `vae` and `image_encoder` are the
 third-party objects the reference receives in its constructor (:90-108); any module with the same
-interface works.  Parity unpinned (no reference run is possible here).
+interface works.  PINNED: tests/golden/pipeline_tiny.pt is produced by executing the reference's own __call__ (oracle/make_goldens.py:
+make_pipeline; DiffusionPipeline / VaeImageProcessor base classes stubbed, diffusers blocks from oracle/d24_blocks.py);
+run_pipeline reproduces its 2-step latents bit-exactly (tests/test_oracle.py).
 """
 import numpy as np
 import PIL.Image

@@ -130,3 +130,29 @@ def test_network_forward_graphs_match_reference_fixture():
         assert tuple(d.shape) == dg["shape"]
         assert (f[:: max(1, f.numel() // 64)][:64] - dg["sample"]).abs().max().item() <= 1e-6
         assert abs(f.abs().mean().item() - dg["abs_mean"]) <= 1e-6
+
+
+def test_pipeline_call_matches_reference_fixture():
+    """tests/golden/pipeline_tiny.pt comes from EXECUTING the reference's FlowControlNetPipeline.__call__ (with its own
+    UNet / FlowControlNet / scheduler files; DiffusionPipeline and VaeImageProcessor stubbed, oracle/make_goldens.py:
+    make_pipeline).  oracle.pipeline.run_pipeline -- the oracle every engine pipeline test compares against -- must
+    reproduce the 2-step latents: PIL conversion, CLIP resize path (Q3), VAE encode of the noise-augmented frame (Q7),
+    added-time-id constants (Q4), CFG with the per-frame scale, Karras-sigma Euler steps."""
+    import PIL.Image
+
+    from oracle import pipeline as opipe
+    g = _gold("pipeline_tiny.pt")
+    cfg = g["config"]
+    H, W = g["hw"]
+    T = cfg["num_frames"]
+    unet, ad = fixtures.make_models(cfg, seed=0, adapter_gain=20.0)
+    vae, clip = fixtures.make_vae_and_clip(cfg["cross_attention_dim"])
+    pil = PIL.Image.fromarray(g["image_u8"].numpy())
+    flow = fixtures.make_flow(T, H, W)
+    lat0 = torch.randn(1, T, 4, H // 8, W // 8, generator=torch.Generator().manual_seed(g["latent_seed"]))
+    out = opipe.run_pipeline(vae, clip, unet, ad, osched.EulerDiscreteScheduler(), pil, pil, flow, height=H, width=W,
+                             num_inference_steps=g["steps"], latents=lat0.clone(),
+                             generator=torch.Generator().manual_seed(g["generator_seed"]), output_type="latent",
+                             controlnet_cond_scale=g["cond_scale"])
+    assert out.shape == g["latents"].shape
+    assert (out - g["latents"]).abs().max().item() <= 1e-5 * g["latents"].abs().max().item()
