@@ -483,6 +483,219 @@ def make_pipeline():
     print("pipeline golden written:", tuple(out.frames.shape), float(out.frames.abs().mean()), seen)
 
 
+def _reference_tree(root):
+    """Install the stubs and return a loader for files of one reference sub-project (Traj / Keypoint / Hybrid): the
+    diffusers block / embedding modules are bound to oracle/d24_blocks.py, models.softsplat to oracle/softsplat.py,
+    DiffusionPipeline / VaeImageProcessor to minimal stand-ins (see make_pipeline)."""
+    install_stubs()
+    import contextlib
+    import importlib.util
+
+    import numpy as np
+    import PIL.Image
+
+    from oracle import d24_blocks as D
+    from oracle.softsplat import softsplat as oracle_softsplat
+
+    class ModelMixin(torch.nn.Module):
+        @property
+        def dtype(self):
+            return next(self.parameters()).dtype
+
+    class DiffusionPipeline:
+        def __init__(self):
+            pass
+
+        def register_modules(self, **kw):
+            for k, v in kw.items():
+                setattr(self, k, v)
+
+        @property
+        def _execution_device(self):
+            return torch.device("cpu")
+
+        @contextlib.contextmanager
+        def progress_bar(self, total=None):
+            class _Bar:
+                def update(self, *a):
+                    pass
+            yield _Bar()
+
+        def maybe_free_model_hooks(self):
+            pass
+
+    class VaeImageProcessor:
+        def __init__(self, vae_scale_factor=8, do_resize=True, do_normalize=True):
+            self.vae_scale_factor = vae_scale_factor
+
+        @staticmethod
+        def pil_to_numpy(images):
+            if not isinstance(images, list):
+                images = [images]
+            return np.stack([np.array(im).astype(np.float32) / 255.0 for im in images], axis=0)
+
+        @staticmethod
+        def numpy_to_pt(images):
+            if images.ndim == 3:
+                images = images[..., None]
+            return torch.from_numpy(images.transpose(0, 3, 1, 2))
+
+        def preprocess(self, image, height=None, width=None):
+            if isinstance(image, PIL.Image.Image):
+                image = [image]
+            image = [im.resize((width, height), resample=PIL.Image.LANCZOS) if im.size != (width, height) else im
+                     for im in image]
+            return 2.0 * self.numpy_to_pt(self.pil_to_numpy(image)) - 1.0
+
+    _mod("diffusers.models.modeling_utils", ModelMixin=ModelMixin)
+    _mod("diffusers.loaders", FromOriginalControlnetMixin=type("FromOriginalControlnetMixin", (), {}),
+         UNet2DConditionLoadersMixin=type("UNet2DConditionLoadersMixin", (), {}))
+    _mod("diffusers.models.embeddings", TimestepEmbedding=D.TimestepEmbedding, Timesteps=D.Timesteps,
+         TextImageProjection=None, TextImageTimeEmbedding=None, TextTimeEmbedding=None)
+    _mod("diffusers.models.unet_3d_blocks", get_down_block=D.get_down_block, get_up_block=D.get_up_block,
+         UNetMidBlockSpatioTemporal=D.UNetMidBlockSpatioTemporal,
+         CrossAttnDownBlockSpatioTemporal=D.CrossAttnDownBlockSpatioTemporal,
+         DownBlockSpatioTemporal=D.DownBlockSpatioTemporal)
+    _mod("diffusers.models", UNetSpatioTemporalConditionModel=ModelMixin, AutoencoderKLTemporalDecoder=ModelMixin)
+    _mod("diffusers.image_processor", VaeImageProcessor=VaeImageProcessor)
+    _mod("diffusers.pipelines")
+    _mod("diffusers.pipelines.pipeline_utils", DiffusionPipeline=DiffusionPipeline)
+    _mod("models")
+    _mod("models.softsplat", softsplat=oracle_softsplat)
+    _mod("models.cmp")
+    _mod("models.cmp.models")
+    _mod("models.cmp.utils")
+    _mod("models.occlusion")
+    _mod("utils")
+
+    def load(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(root, rel))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[name] = m
+        spec.loader.exec_module(m)
+        return m
+    return load
+
+
+def _build_reference_adapter(ref_cn, mod, cfg, state_dict, hourglass=None):
+    """Instantiate a reference FlowControlNet at the test widths (its constructor hard-codes the SVD-XT sizes: default
+    sizes overridden, zero_outs / occlusions re-created from the reference's own classes) and load the oracle weights."""
+    import torch.nn as nn
+    boc = cfg["block_out_channels"]
+    base_init = ref_cn.ControlNetSDVModel.__init__
+    enc_init = mod.FlowControlNetFirstFrameEncoder.__init__
+    ref_cn.ControlNetSDVModel.__init__ = lambda self, *a, **k: base_init(self, *a, **{**cfg, **k})
+    mod.FlowControlNetFirstFrameEncoder.__init__ = \
+        lambda self, *a, **k: enc_init(self, *a, **{"c_in": boc[0], "channels": list(boc[:3]), **k})
+    try:
+        net = mod.FlowControlNet(**cfg)
+    finally:
+        ref_cn.ControlNetSDVModel.__init__ = base_init
+        mod.FlowControlNetFirstFrameEncoder.__init__ = enc_init
+    if hourglass is not None:
+        chans = {"8": boc[0], "16": boc[0], "32": boc[1], "64": boc[2]}
+        net.zero_outs = nn.ModuleDict({k: nn.Conv2d(c, c, kernel_size=1) for k, c in chans.items()})
+        net.occlusions = nn.ModuleDict({k: hourglass.ForegroundMatting(c) for k, c in chans.items()})
+    net.load_state_dict(state_dict, strict=True)
+    return net.eval()
+
+
+KP_CONFIG_UPDATE = dict(block_out_channels=(320, 128, 256, 256), num_attention_heads=(5, 2, 4, 4))
+
+
+def _kp_inputs(cfg, H, W, F_frames):
+    import numpy as np
+    import PIL.Image
+
+    from oracle import fixtures
+    g = torch.Generator().manual_seed(3)
+    img = fixtures.make_image(H, W)
+    pil = PIL.Image.fromarray((img.permute(1, 2, 0) * 255).round().to(torch.uint8).numpy())
+    flow = fixtures.make_flow(F_frames, H, W)
+    ldmk = torch.rand(1, F_frames, 3, H, W, generator=g).half().float()
+    lat0 = torch.randn(1, F_frames, 4, H // 8, W // 8, generator=g)
+    return pil, torch.from_numpy(np.array(pil)), flow, ldmk, lat0
+
+
+def make_keypoint_pipeline():
+    """Execute /root/reference/MOFA-Video-Keypoint/pipeline/svdxt_pipeline_ctrlnet_loop.py FlowControlNetPipeline.__call__
+    (windowed views, per-view denoise, _step_index rewind, value / count averaging, :287-664) for a 5-frame clip with
+    window_size 3, stride 1, 2 steps, with the Keypoint tree's own UNet / ldmk_ctrlnet / hourglass / scheduler files."""
+    K = "/root/reference/MOFA-Video-Keypoint"
+    load = _reference_tree(K)
+    from oracle import fixtures
+    from oracle.scheduler import SVD_XT_SCHEDULER_CONFIG
+    ref_unet = load("models.unet_spatio_temporal_condition_controlnet", "models/unet_spatio_temporal_condition_controlnet.py")
+    ref_cn = load("models.controlnet_sdv", "models/controlnet_sdv.py")
+    ref_hg = load("models.occlusion.hourglass", "models/occlusion/hourglass.py")
+    ref_ldmk = load("models.ldmk_ctrlnet", "models/ldmk_ctrlnet.py")
+    ref_sched = load("utils.scheduling_euler_discrete_karras_fix", "utils/scheduling_euler_discrete_karras_fix.py")
+    ref_pipe = load("ref_kp_pipeline", "pipeline/svdxt_pipeline_ctrlnet_loop.py")
+    cfg = dict(fixtures.TINY_CONFIG)
+    cfg.update(KP_CONFIG_UPDATE)
+    o_unet, _ = fixtures.make_models(cfg, seed=0, adapter_gain=20.0)
+    o_face = fixtures.make_ldmk_adapter(cfg)
+    r_unet = ref_unet.UNetSpatioTemporalConditionControlNetModel(**cfg).eval()
+    r_unet.load_state_dict(o_unet.state_dict(), strict=True)
+    r_face = _build_reference_adapter(ref_cn, ref_ldmk, cfg, o_face.state_dict(), hourglass=ref_hg)
+    vae, clip = fixtures.make_vae_and_clip(cfg["cross_attention_dim"])
+    pipe = ref_pipe.FlowControlNetPipeline(vae=vae, image_encoder=clip, unet=r_unet, controlnet=r_face,
+                                           scheduler=ref_sched.EulerDiscreteScheduler(**SVD_XT_SCHEDULER_CONFIG),
+                                           feature_extractor=None)
+    H = W = 128
+    T, F_frames, stride = cfg["num_frames"], 5, 1
+    pil, u8, flow, ldmk, lat0 = _kp_inputs(cfg, H, W, F_frames)
+    out = pipe(pil, pil, flow, ldmk, height=H, width=W, num_frames=F_frames, num_inference_steps=2,
+               latents=lat0.clone(), generator=torch.Generator().manual_seed(11), output_type="latent",
+               window_size=T, stride=stride)
+    g = {"config": cfg, "hw": (H, W), "frames": F_frames, "stride": stride, "steps": 2, "generator_seed": 11,
+         "image_u8": u8, "latents": out.frames.clone()}
+    torch.save(g, os.path.join(OUT, "keypoint_pipeline_tiny.pt"))
+    print("keypoint pipeline golden written:", tuple(out.frames.shape), float(out.frames.abs().mean()))
+
+
+def make_hybrid_pipeline():
+    """Execute /root/reference/MOFA-Video-Hybrid/pipeline/pipeline.py FlowControlNetPipeline.__call__ (face adapter
+    inside the mask, drag adapter outside, nearest-resized mask per level, :291-520) with the Hybrid tree's own files."""
+    Hy = "/root/reference/MOFA-Video-Hybrid"
+    load = _reference_tree(Hy)
+    from oracle import fixtures
+    from oracle.scheduler import SVD_XT_SCHEDULER_CONFIG
+    ref_unet = load("models.unet_spatio_temporal_condition_controlnet", "models/unet_spatio_temporal_condition_controlnet.py")
+    ref_cn = load("models.controlnet_sdv", "models/controlnet_sdv.py")
+    ref_hg = load("models.occlusion.hourglass", "models/occlusion/hourglass.py")
+    ref_traj = load("models.traj_ctrlnet", "models/traj_ctrlnet.py")
+    ref_ldmk = load("models.ldmk_ctrlnet", "models/ldmk_ctrlnet.py")
+    ref_sched = load("utils.scheduling_euler_discrete_karras_fix", "utils/scheduling_euler_discrete_karras_fix.py")
+    ref_pipe = load("ref_hybrid_pipeline", "pipeline/pipeline.py")
+    cfg = dict(fixtures.TINY_CONFIG)
+    cfg.update(KP_CONFIG_UPDATE)
+    o_unet, o_drag = fixtures.make_models(cfg, seed=0, adapter_gain=20.0)
+    o_face = fixtures.make_ldmk_adapter(cfg)
+    r_unet = ref_unet.UNetSpatioTemporalConditionControlNetModel(**cfg).eval()
+    r_unet.load_state_dict(o_unet.state_dict(), strict=True)
+    r_drag = _build_reference_adapter(ref_cn, ref_traj, cfg, o_drag.state_dict())
+    r_face = _build_reference_adapter(ref_cn, ref_ldmk, cfg, o_face.state_dict(), hourglass=ref_hg)
+    vae, clip = fixtures.make_vae_and_clip(cfg["cross_attention_dim"])
+    pipe = ref_pipe.FlowControlNetPipeline(vae=vae, image_encoder=clip, unet=r_unet, drag_controlnet=r_drag,
+                                           face_controlnet=r_face,
+                                           scheduler=ref_sched.EulerDiscreteScheduler(**SVD_XT_SCHEDULER_CONFIG),
+                                           feature_extractor=None)
+    H = W = 128
+    T = cfg["num_frames"]
+    pil, u8, flow, ldmk, lat0 = _kp_inputs(cfg, H, W, T)
+    drag_flow = (fixtures.make_flow(T, H, W, seed=99) * 0.5).half().float()
+    mask = torch.zeros(1, 1, H, W)
+    mask[..., 20:90, 30:100] = 1.0
+    out = pipe(pil, pil, flow, ldmk, drag_flow, mask, height=H, width=W, num_frames=T, num_inference_steps=2,
+               latents=lat0.clone(), generator=torch.Generator().manual_seed(11), output_type="latent",
+               ctrl_scale_traj=1.1, ctrl_scale_ldmk=0.9)
+    g = {"config": cfg, "hw": (H, W), "steps": 2, "generator_seed": 11, "image_u8": u8, "latents": out.frames.clone(),
+         "scale_traj": 1.1, "scale_ldmk": 0.9}
+    torch.save(g, os.path.join(OUT, "hybrid_pipeline_tiny.pt"))
+    print("hybrid pipeline golden written:", tuple(out.frames.shape), float(out.frames.abs().mean()))
+
+
 def make_keypoint_network():
     """Same as make_networks for the Keypoint adapter: executes /root/reference/MOFA-Video-Keypoint/models/ldmk_ctrlnet.py
     (FlowControlNet.__init__ / get_warped_frames / forward with landmarks, :187-575), its controlnet_sdv.py and its
@@ -583,6 +796,10 @@ if __name__ == "__main__":
         make_networks()
     if "--pipeline" in sys.argv:
         make_pipeline()           # separate process as well
+    if "--keypoint-pipeline" in sys.argv:
+        make_keypoint_pipeline()
+    if "--hybrid-pipeline" in sys.argv:
+        make_hybrid_pipeline()
     if "--keypoint" in sys.argv:
         make_keypoint_network()   # separate process from --networks: both bind sys.modules["models.*"]
     if "--all" in sys.argv:
