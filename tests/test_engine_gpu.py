@@ -184,3 +184,77 @@ def test_step_full_frame_count_tiny_channels():
     cfg = dict(fixtures.TINY_CONFIG)
     cfg["num_frames"] = 25
     one_step(cfg, 16, 16, 1e-2)
+
+
+def test_entry_points_against_reference_pipeline_latents():
+    """The three engine entry points on the B200 (real kernels) DIRECTLY against latents produced by executing the
+    reference's own Traj / Keypoint / Hybrid pipelines on CPU in fp32 (tests/golden/README.md)."""
+    import os
+
+    import PIL.Image
+
+    from mofa_video_b200.models.ldmk_ctrlnet import FlowControlNet as FaceNet
+    from mofa_video_b200.models.svdxt_featureflow_forward_controlnet_s2d_fixcmp_norefine import FlowControlNet
+    from mofa_video_b200.models.unet_spatio_temporal_condition_controlnet import \
+        UNetSpatioTemporalConditionControlNetModel as UNet
+    from mofa_video_b200.pipeline import pipeline_hybrid as hyb
+    from mofa_video_b200.pipeline import svdxt_pipeline_ctrlnet_loop as kpl
+    from mofa_video_b200.pipeline.pipeline import FlowControlNetPipeline
+    from mofa_video_b200.utils.scheduling_euler_discrete_karras_fix import EulerDiscreteScheduler
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+
+    def rel(a, b):
+        return ((a.float().cpu() - b).abs().max() / b.abs().max()).item()
+
+    g = torch.load(os.path.join(gold, "pipeline_tiny.pt"))
+    cfg = g["config"]
+    H, W = g["hw"]
+    T = cfg["num_frames"]
+    unet, drag = fixtures.make_models(cfg, seed=0, adapter_gain=20.0)
+    vae, clip = fixtures.make_vae_and_clip(cfg["cross_attention_dim"])
+    pil = PIL.Image.fromarray(g["image_u8"].numpy())
+    pipe = FlowControlNetPipeline(vae=vae.cuda().half(), image_encoder=clip.cuda().half(),
+                                  unet=UNet.from_state_dict(unet.state_dict(), unet.config.__dict__),
+                                  controlnet=FlowControlNet.from_state_dict(drag.state_dict(), drag.config.__dict__),
+                                  scheduler=EulerDiscreteScheduler())
+    lat0 = torch.randn(1, T, 4, H // 8, W // 8, generator=torch.Generator().manual_seed(g["latent_seed"]))
+    out = pipe(pil, pil, fixtures.make_flow(T, H, W), height=H, width=W, num_inference_steps=g["steps"],
+               latents=lat0.clone().half(), generator=torch.Generator().manual_seed(g["generator_seed"]),
+               output_type="latent", controlnet_cond_scale=g["cond_scale"]).frames
+    assert rel(out, g["latents"]) < 2e-2
+
+    g = torch.load(os.path.join(gold, "keypoint_pipeline_tiny.pt"))
+    cfg = g["config"]
+    F_frames = g["frames"]
+    unet, drag = fixtures.make_models(cfg, seed=0, adapter_gain=20.0)
+    face = fixtures.make_ldmk_adapter(cfg)
+    e_unet = UNet.from_state_dict(unet.state_dict(), unet.config.__dict__)
+    e_drag = FlowControlNet.from_state_dict(drag.state_dict(), drag.config.__dict__)
+    e_face = FaceNet.from_state_dict(face.state_dict(), face.config.__dict__)
+    vae, clip = fixtures.make_vae_and_clip(cfg["cross_attention_dim"])
+    vae, clip = vae.cuda().half(), clip.cuda().half()
+    gen = torch.Generator().manual_seed(3)
+    flow = fixtures.make_flow(F_frames, H, W)
+    ldmk = torch.rand(1, F_frames, 3, H, W, generator=gen).half().float()
+    lat0 = torch.randn(1, F_frames, 4, H // 8, W // 8, generator=gen)
+    pipe = kpl.FlowControlNetPipeline(vae=vae, image_encoder=clip, unet=e_unet, controlnet=e_face,
+                                      scheduler=EulerDiscreteScheduler())
+    out = pipe(pil, pil, flow, ldmk, height=H, width=W, num_frames=F_frames, num_inference_steps=g["steps"],
+               latents=lat0.clone().half(), generator=torch.Generator().manual_seed(g["generator_seed"]),
+               output_type="latent", window_size=T, stride=g["stride"]).frames
+    assert rel(out, g["latents"]) < 3e-2
+
+    g = torch.load(os.path.join(gold, "hybrid_pipeline_tiny.pt"))
+    gen = torch.Generator().manual_seed(3)
+    flow = fixtures.make_flow(T, H, W)
+    ldmk = torch.rand(1, T, 3, H, W, generator=gen).half().float()
+    lat0 = torch.randn(1, T, 4, H // 8, W // 8, generator=gen)
+    drag_flow = (fixtures.make_flow(T, H, W, seed=99) * 0.5).half().float()
+    mask = torch.zeros(1, 1, H, W)
+    mask[..., 20:90, 30:100] = 1.0
+    pipe = hyb.FlowControlNetPipeline(vae=vae, image_encoder=clip, unet=e_unet, drag_controlnet=e_drag,
+                                      face_controlnet=e_face, scheduler=EulerDiscreteScheduler())
+    out = pipe(pil, pil, flow, ldmk, drag_flow, mask, height=H, width=W, num_inference_steps=g["steps"],
+               latents=lat0.clone().half(), generator=torch.Generator().manual_seed(g["generator_seed"]),
+               output_type="latent", ctrl_scale_traj=g["scale_traj"], ctrl_scale_ldmk=g["scale_ldmk"]).frames
+    assert rel(out, g["latents"]) < 3e-2

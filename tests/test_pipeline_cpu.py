@@ -135,3 +135,87 @@ def test_keypoint_and_hybrid_calls_match_oracle_on_cpu():
                ctrl_scale_traj=1.1, ctrl_scale_ldmk=0.9)
     err = ((out.frames.float() - ref).abs().max() / ref.abs().max()).item()
     assert err < 1.5e-2, err
+
+
+# ------------------------------------------------------------------------------------------------
+# engine entry points (kernels replaced by their PyTorch statements) DIRECTLY against latents produced by executing
+# the reference's own pipelines (tests/golden/README.md) -- no oracle in between
+# ------------------------------------------------------------------------------------------------
+def _gold(name):
+    import os
+    fn = os.path.join(os.path.dirname(__file__), "golden", name)
+    if not os.path.exists(fn):
+        pytest.skip(f"{name} not generated")
+    return torch.load(fn)
+
+
+def _engine_models(cfg, with_face, with_drag=True):
+    from mofa_video_b200.models.ldmk_ctrlnet import FlowControlNet as FaceNet
+    mk = dict(device="cpu", ops=ref_ops)
+    unet, drag = fixtures.make_models(cfg, seed=0, adapter_gain=20.0)
+    e_unet = UNetSpatioTemporalConditionControlNetModel.from_state_dict(unet.state_dict(), unet.config.__dict__, **mk)
+    e_drag = FlowControlNet.from_state_dict(drag.state_dict(), drag.config.__dict__, **mk) if with_drag else None
+    e_face = None
+    if with_face:
+        face = fixtures.make_ldmk_adapter(cfg)
+        e_face = FaceNet.from_state_dict(face.state_dict(), face.config.__dict__, **mk)
+    vae, clip = fixtures.make_vae_and_clip(cfg["cross_attention_dim"])
+    return e_unet, e_drag, e_face, vae, clip, mk
+
+
+def test_traj_entry_point_against_reference_pipeline_latents():
+    import PIL.Image
+    g = _gold("pipeline_tiny.pt")
+    cfg = g["config"]
+    H, W = g["hw"]
+    T = cfg["num_frames"]
+    e_unet, e_drag, _, vae, clip, mk = _engine_models(cfg, with_face=False)
+    pipe = FlowControlNetPipeline(vae=vae, image_encoder=clip, unet=e_unet, controlnet=e_drag,
+                                  scheduler=EulerDiscreteScheduler(), **mk)
+    pil = PIL.Image.fromarray(g["image_u8"].numpy())
+    lat0 = torch.randn(1, T, 4, H // 8, W // 8, generator=torch.Generator().manual_seed(g["latent_seed"]))
+    out = pipe(pil, pil, fixtures.make_flow(T, H, W), height=H, width=W, num_inference_steps=g["steps"],
+               latents=lat0.clone(), generator=torch.Generator().manual_seed(g["generator_seed"]), output_type="latent",
+               controlnet_cond_scale=g["cond_scale"]).frames.float()
+    err = ((out - g["latents"]).abs().max() / g["latents"].abs().max()).item()
+    assert err < 1e-2, err          # fp16 activations / weights-as-fp16 vs the reference's fp32 run
+
+
+def test_keypoint_and_hybrid_entry_points_against_reference_pipeline_latents():
+    import PIL.Image
+
+    from mofa_video_b200.pipeline import pipeline_hybrid as hyb
+    from mofa_video_b200.pipeline import svdxt_pipeline_ctrlnet_loop as kpl
+    g = _gold("keypoint_pipeline_tiny.pt")
+    cfg = g["config"]
+    H, W = g["hw"]
+    T, F_frames = cfg["num_frames"], g["frames"]
+    e_unet, e_drag, e_face, vae, clip, mk = _engine_models(cfg, with_face=True)
+    gen = torch.Generator().manual_seed(3)                      # same draws as oracle/make_goldens.py:_kp_inputs
+    flow = fixtures.make_flow(F_frames, H, W)
+    ldmk = torch.rand(1, F_frames, 3, H, W, generator=gen).half().float()
+    lat0 = torch.randn(1, F_frames, 4, H // 8, W // 8, generator=gen)
+    pil = PIL.Image.fromarray(g["image_u8"].numpy())
+    pipe = kpl.FlowControlNetPipeline(vae=vae, image_encoder=clip, unet=e_unet, controlnet=e_face,
+                                      scheduler=EulerDiscreteScheduler(), **mk)
+    out = pipe(pil, pil, flow, ldmk, height=H, width=W, num_frames=F_frames, num_inference_steps=g["steps"],
+               latents=lat0.clone(), generator=torch.Generator().manual_seed(g["generator_seed"]), output_type="latent",
+               window_size=T, stride=g["stride"]).frames.float()
+    err = ((out - g["latents"]).abs().max() / g["latents"].abs().max()).item()
+    assert err < 1.5e-2, err
+
+    g = _gold("hybrid_pipeline_tiny.pt")
+    gen = torch.Generator().manual_seed(3)
+    flow = fixtures.make_flow(T, H, W)
+    ldmk = torch.rand(1, T, 3, H, W, generator=gen).half().float()
+    lat0 = torch.randn(1, T, 4, H // 8, W // 8, generator=gen)
+    drag_flow = (fixtures.make_flow(T, H, W, seed=99) * 0.5).half().float()
+    mask = torch.zeros(1, 1, H, W)
+    mask[..., 20:90, 30:100] = 1.0
+    pipe = hyb.FlowControlNetPipeline(vae=vae, image_encoder=clip, unet=e_unet, drag_controlnet=e_drag,
+                                      face_controlnet=e_face, scheduler=EulerDiscreteScheduler(), **mk)
+    out = pipe(pil, pil, flow, ldmk, drag_flow, mask, height=H, width=W, num_inference_steps=g["steps"],
+               latents=lat0.clone(), generator=torch.Generator().manual_seed(g["generator_seed"]), output_type="latent",
+               ctrl_scale_traj=g["scale_traj"], ctrl_scale_ldmk=g["scale_ldmk"]).frames.float()
+    err = ((out - g["latents"]).abs().max() / g["latents"].abs().max()).item()
+    assert err < 1.5e-2, err
