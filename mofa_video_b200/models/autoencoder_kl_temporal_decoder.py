@@ -1,9 +1,12 @@
 """AutoencoderKLTemporalDecoder stand-in (the reference takes this object from diffusers 0.24,
 /root/reference/MOFA-Video-Traj/run_gradio.py:101-102, pipeline.py:143-164, 194-220).
 
-INTERIM, NOT the native path: SURVEY.md §8(f) row 1 schedules the VAE for native kernels after the denoise
-loop; until then encode/decode run as plain PyTorch modules on the GPU (cuDNN/cuBLAS eager).  bench.py reports
-the time spent here separately.  Topology restates diffusers 0.24 `Encoder` / `TemporalDecoder`
+This PyTorch module is the weight container / parameter-name contract of the VAE (a real `vae` checkpoint loads into
+it) and the fp32 statement the native path is tested against; at run time `vae_engine.NativeTemporalDecoderVAE` wraps it
+and executes both encode and decode on the sm_100a kernels.  A caller may still pass this
+module (or diffusers' own) to the pipeline directly -- the pipeline only uses `.encode(x).latent_dist.mode()`,
+`.decode(z, num_frames=n).sample`, `.config`, `.dtype`.
+Topology restates diffusers 0.24 `Encoder` / `TemporalDecoder`
 (SURVEY.md App. A.2): encoder (128,256,512,512) x2 ResnetBlock2D + mid res-attn(d=512)-res -> 8ch ->
 quant_conv, mode() = mean; decoder conv_in 4->512, mid res-attn-res, 4 up blocks of 3
 SpatioTemporalResBlock(merge 'learned', switch_spatial_to_temporal_mix) + nearest-2x conv, GN-SiLU-conv 128->3,
