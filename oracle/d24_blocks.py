@@ -15,7 +15,10 @@ anchored on the reference's call sites
 (/root/reference/MOFA-Video-Traj/models/unet_spatio_temporal_condition_controlnet.py:137-143, 169-233;
  /root/reference/MOFA-Video-Traj/models/controlnet_sdv.py:227-309) and on the one known answer the
 topology must reproduce: the SVD-XT UNet has 1,524,623,082 parameters (tests/test_oracle.py).
-Module/parameter names follow diffusers so reference-layout state dicts load unchanged.
+Module/parameter names follow diffusers so reference-layout state dicts load unchanged; the NAME SET is pinned: the
+adapter built from these blocks has exactly the 683 parameter names of /root/reference/Training/rec_para_train.txt
+(the reference's own `named_parameters()` dump from the real diffusers blocks, train_stage1.py:846-856;
+tests/test_oracle.py compares a digest).  What stays unpinned is the arithmetic inside each block.
 """
 import math
 

@@ -156,3 +156,22 @@ def test_pipeline_call_matches_reference_fixture():
                              controlnet_cond_scale=g["cond_scale"])
     assert out.shape == g["latents"].shape
     assert (out - g["latents"]).abs().max().item() <= 1e-5 * g["latents"].abs().max().item()
+
+
+def test_adapter_parameter_names_match_the_reference_training_dump():
+    """/root/reference/Training/rec_para_train.txt is the reference's own dump of `controlnet.named_parameters()` names
+    (train_stage1.py:846-856) -- 683 names produced by the REAL diffusers 0.24 blocks.  The oracle adapter (hence
+    oracle/d24_blocks.py's module structure: resnets / attentions / transformer_blocks / temporal blocks / mixers) must
+    have exactly that name set.  Compared through a digest so no reference file is copied:
+    sha256 of the sorted names joined by newlines (regenerate: see the two lines below with the reference mounted)."""
+    import hashlib
+    from oracle.models import FlowControlNet
+    with torch.device("meta"):
+        names = sorted(n for n, _ in FlowControlNet().named_parameters())
+    assert len(names) == 683
+    digest = hashlib.sha256("\n".join(names).encode()).hexdigest()
+    assert digest == "dde7b69aad4901bc3ef3bcd4f1301973a7749dd83d6f843e466b3b599d358dd5"
+    ref_file = "/root/reference/Training/rec_para_train.txt"
+    if os.path.exists(ref_file):  # builder container only: check the digest against the file itself
+        ref = sorted(line.strip() for line in open(ref_file) if line.strip())
+        assert hashlib.sha256("\n".join(ref).encode()).hexdigest() == digest
