@@ -343,7 +343,7 @@ def make_networks():
     print("network golden written:", tuple(out.shape), float(out.abs().mean()), g["n_params"])
 
 
-def make_pipeline():
+def make_pipeline(H=128, W=128, steps=2, cond_scale=0.8, name="pipeline_tiny.pt"):
     """Execute the reference's FlowControlNetPipeline.__call__ (/root/reference/MOFA-Video-Traj/pipeline/pipeline.py:
     282-527, with _encode_image, _encode_vae_image, _get_add_time_ids, prepare_latents, _resize_with_antialiasing ...)
     on CPU for 2 steps at 128x128x3 frames with the reference UNet / FlowControlNet (see make_networks), the
@@ -467,19 +467,18 @@ def make_pipeline():
     vae, clip = fixtures.make_vae_and_clip(cfg["cross_attention_dim"])
     pipe = ref_pipe.FlowControlNetPipeline(vae=vae, image_encoder=clip, unet=r_unet, controlnet=r_ad, scheduler=sched,
                                            feature_extractor=None)
-    H = W = 128
     T = cfg["num_frames"]
     img = fixtures.make_image(H, W)
     pil = PIL.Image.fromarray((img.permute(1, 2, 0) * 255).round().to(torch.uint8).numpy())
     flow = fixtures.make_flow(T, H, W)
     lat0 = torch.randn(1, T, 4, H // 8, W // 8, generator=torch.Generator().manual_seed(9))
     seen = []
-    out = pipe(pil, pil, flow, height=H, width=W, num_frames=T, num_inference_steps=2, latents=lat0.clone(),
-               generator=torch.Generator().manual_seed(11), output_type="latent", controlnet_cond_scale=0.8,
+    out = pipe(pil, pil, flow, height=H, width=W, num_frames=T, num_inference_steps=steps, latents=lat0.clone(),
+               generator=torch.Generator().manual_seed(11), output_type="latent", controlnet_cond_scale=cond_scale,
                callback_on_step_end=lambda p_, i, t, kw: seen.append(float(t)) or {})
-    g = {"config": cfg, "hw": (H, W), "steps": 2, "latent_seed": 9, "generator_seed": 11, "cond_scale": 0.8,
+    g = {"config": cfg, "hw": (H, W), "steps": steps, "latent_seed": 9, "generator_seed": 11, "cond_scale": cond_scale,
          "image_u8": torch.from_numpy(np.array(pil)), "latents": out.frames.clone(), "timesteps_seen": seen}
-    torch.save(g, os.path.join(OUT, "pipeline_tiny.pt"))
+    torch.save(g, os.path.join(OUT, name))
     print("pipeline golden written:", tuple(out.frames.shape), float(out.frames.abs().mean()), seen)
 
 
@@ -796,6 +795,8 @@ if __name__ == "__main__":
         make_networks()
     if "--pipeline" in sys.argv:
         make_pipeline()           # separate process as well
+    if "--pipeline-rect" in sys.argv:
+        make_pipeline(H=128, W=192, steps=3, cond_scale=1.0, name="pipeline_tiny_rect.pt")
     if "--keypoint-pipeline" in sys.argv:
         make_keypoint_pipeline()
     if "--hybrid-pipeline" in sys.argv:

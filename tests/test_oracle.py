@@ -132,7 +132,8 @@ def test_network_forward_graphs_match_reference_fixture():
         assert abs(f.abs().mean().item() - dg["abs_mean"]) <= 1e-6
 
 
-def test_pipeline_call_matches_reference_fixture():
+@pytest.mark.parametrize("fixture", ["pipeline_tiny.pt", "pipeline_tiny_rect.pt"])
+def test_pipeline_call_matches_reference_fixture(fixture):
     """tests/golden/pipeline_tiny.pt comes from EXECUTING the reference's FlowControlNetPipeline.__call__ (with its own
     UNet / FlowControlNet / scheduler files; DiffusionPipeline and VaeImageProcessor stubbed, oracle/make_goldens.py:
     make_pipeline).  oracle.pipeline.run_pipeline -- the oracle every engine pipeline test compares against -- must
@@ -141,7 +142,7 @@ def test_pipeline_call_matches_reference_fixture():
     import PIL.Image
 
     from oracle import pipeline as opipe
-    g = _gold("pipeline_tiny.pt")
+    g = _gold(fixture)          # square 128x128 / 2 steps / scale 0.8, and rectangular 128x192 / 3 steps / scale 1.0
     cfg = g["config"]
     H, W = g["hw"]
     T = cfg["num_frames"]

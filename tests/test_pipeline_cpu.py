@@ -163,9 +163,10 @@ def _engine_models(cfg, with_face, with_drag=True):
     return e_unet, e_drag, e_face, vae, clip, mk
 
 
-def test_traj_entry_point_against_reference_pipeline_latents():
+@pytest.mark.parametrize("fixture", ["pipeline_tiny.pt", "pipeline_tiny_rect.pt"])
+def test_traj_entry_point_against_reference_pipeline_latents(fixture):
     import PIL.Image
-    g = _gold("pipeline_tiny.pt")
+    g = _gold(fixture)
     cfg = g["config"]
     H, W = g["hw"]
     T = cfg["num_frames"]
