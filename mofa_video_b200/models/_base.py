@@ -108,9 +108,10 @@ class EngineModel:
 
     # -- helpers --------------------------------------------------------------------------------
     def _prepare(self, encoder_hidden_states, added_time_ids):
-        key = (encoder_hidden_states.data_ptr(), encoder_hidden_states._version, added_time_ids.data_ptr(),
-               added_time_ids._version, tuple(encoder_hidden_states.shape))
-        if key != self._clip_key:
+        # identity, not address: the key holds the tensors, so a new embedding on a recycled address never matches
+        key = ((encoder_hidden_states, added_time_ids), (encoder_hidden_states._version, added_time_ids._version))
+        old = self._clip_key
+        if (old is None or old[0][0] is not key[0][0] or old[0][1] is not key[0][1] or old[1] != key[1]):
             self.net.prepare_clip(encoder_hidden_states.to(self._device), added_time_ids.to(self._device))
             self._clip_key = key
 

@@ -9,6 +9,7 @@ import torch
 
 from mofa_video_b200.keypoint_engine import LdmkAdapterNet
 from mofa_video_b200.models._base import EngineModel
+from mofa_video_b200.models.svdxt_featureflow_forward_controlnet_s2d_fixcmp_norefine import _identity_key, _same_key
 
 
 @dataclass
@@ -30,11 +31,11 @@ class FlowControlNet(EngineModel):
     def _make_net(self, state_dict, cfg):
         return LdmkAdapterNet(state_dict, cfg, self._ops, self._device)
 
-    def prepare_condition(self, controlnet_cond, controlnet_flow, landmarks):
-        """controlnet_cond [B,3,H,W] in [-1,1]; controlnet_flow [B,T-1,2,H,W]; landmarks [B,T,3,H,W] (B = CFG copies)."""
-        key = (controlnet_cond.data_ptr(), controlnet_cond._version, controlnet_flow.data_ptr(), controlnet_flow._version,
-               landmarks.data_ptr(), landmarks._version, tuple(controlnet_flow.shape))
-        if key == self._cond_key:
+    def prepare_condition(self, controlnet_cond, controlnet_flow, landmarks, force=False):
+        """controlnet_cond [B,3,H,W] in [-1,1]; controlnet_flow [B,T-1,2,H,W]; landmarks [B,T,3,H,W] (B = CFG copies).
+        Cached on tensor identity only (see svdxt_..._norefine._identity_key); the pipelines pass force=True."""
+        key = _identity_key(controlnet_cond, controlnet_flow, landmarks)
+        if not force and _same_key(key, self._cond_key):
             return self._masks
         _, _, H, W = controlnet_cond.shape
         if H % 64 or W % 64:

@@ -46,6 +46,29 @@ def _get_add_time_ids(noise_aug_strength, dtype, batch_size, fps=4, motion_bucke
     return torch.tensor([add_time_ids], dtype=dtype)
 
 
+def _randn_tensor(shape, generator=None, device=None, dtype=None):
+    """diffusers.utils.torch_utils.randn_tensor as the reference calls it (pipeline.py:262, :340): a CPU generator
+    draws on the CPU and the result is moved; a CUDA generator cannot fill a CPU tensor (ValueError); a list of
+    generators draws one batch item each."""
+    device = torch.device(device) if device is not None else torch.device("cpu")
+    rand_device = device
+    if generator is not None:
+        gtype = (generator[0] if isinstance(generator, list) else generator).device.type
+        if gtype != device.type and gtype == "cpu":
+            rand_device = torch.device("cpu")
+        elif gtype != device.type and gtype == "cuda":
+            raise ValueError(f"Cannot generate a {device} tensor from a generator of type {gtype}.")
+    if isinstance(generator, list) and len(generator) == 1:
+        generator = generator[0]
+    if isinstance(generator, list):
+        one = (1,) + tuple(shape[1:])
+        out = torch.cat([torch.randn(one, generator=generator[i], device=rand_device, dtype=dtype)
+                         for i in range(shape[0])], dim=0)
+    else:
+        out = torch.randn(tuple(shape), generator=generator, device=rand_device, dtype=dtype)
+    return out.to(device)
+
+
 # ------------------------------------------------------------------------------------------------
 # image pre/post-processing (diffusers VaeImageProcessor behaviour used by the reference, Q21)
 # ------------------------------------------------------------------------------------------------
@@ -158,9 +181,7 @@ class FlowControlNetPipeline:
             raise ValueError(f"You have passed a list of generators of length {len(generator)}, but requested an "
                              f"effective batch size of {batch_size}.")
         if latents is None:
-            gdev = generator.device if isinstance(generator, torch.Generator) else device
-            latents = torch.randn(shape, generator=generator if isinstance(generator, torch.Generator) else None,
-                                  device=gdev, dtype=dtype).to(device)
+            latents = _randn_tensor(shape, generator=generator, device=device, dtype=dtype)
         else:
             latents = latents.to(device)
         return latents * self.scheduler.init_noise_sigma
@@ -215,9 +236,11 @@ class FlowControlNetPipeline:
         device = self._device
         image_embeddings = self._encode_image(image, device, num_videos_per_prompt, True)
         emb_dtype = image_embeddings.dtype
-        img = _to_unit_tensor(image, height, width).to(device) * 2.0 - 1.0
-        gen_cpu = generator if isinstance(generator, torch.Generator) and generator.device.type == "cpu" else None
-        noise = torch.randn(img.shape, generator=gen_cpu, dtype=img.dtype)
+        img = _to_unit_tensor(image, height, width)
+        # the noise is drawn where the preprocessed image lives (pipeline.py:339-341): the CPU for PIL / ndarray inputs
+        # (a CUDA generator raises there, as in the reference), the tensor's own device for tensor inputs
+        noise = _randn_tensor(img.shape, generator=generator, device=img.device, dtype=img.dtype)
+        img = img.to(device) * 2.0 - 1.0
         img = img + noise_aug_strength * noise.to(img.device)
         needs_upcasting = self.vae.dtype == torch.float16 and self.vae.config.force_upcast
         if needs_upcasting:
@@ -275,7 +298,7 @@ class FlowControlNetPipeline:
         unet_net, ad_net = self.unet.net, self.controlnet.net
         unet_net.prepare_clip(image_embeddings, added_time_ids)
         ad_net.prepare_clip(image_embeddings, added_time_ids)
-        self.controlnet.prepare_condition(cond, controlnet_flow)
+        self.controlnet.prepare_condition(cond, controlnet_flow, force=True)
         lat_h = latents[0].to(torch.float16).reshape(T, 4, hw).contiguous()
         img_lat = image_latents.to(torch.float16).reshape(2, 4, hw).contiguous()
         next_in = torch.empty(2 * T * hw, 8, dtype=torch.float16, device=device)
@@ -297,10 +320,13 @@ class FlowControlNetPipeline:
                 kw = {k: cur for k in callback_on_step_end_tensor_inputs if k == "latents"}
                 outs = callback_on_step_end(self, i, timesteps[i], kw) or {}
                 new = outs.pop("latents", None)
+                # whatever the callback left in / returned as `latents` drives the next step, as in the reference
+                # (pipeline.py:502-509; an in-place edit of the tensor it was handed counts too): rebuild the fused
+                # model input from it
                 if new is not None and new is not cur:
                     lat_h.copy_(new.reshape(T, 4, hw))
-                    ops.cfg_euler_step(None, lat_h, img_lat, next_in, T, hw, min_guidance_scale,
-                                       max_guidance_scale, 0.0, sig[i + 1])
+                ops.cfg_euler_step(None, lat_h, img_lat, next_in, T, hw, min_guidance_scale, max_guidance_scale,
+                                   0.0, sig[i + 1])
         latents = lat_h.reshape(1, T, 4, h, w)
         ev["loop"].record()
 

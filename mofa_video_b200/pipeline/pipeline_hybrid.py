@@ -87,8 +87,8 @@ class FlowControlNetPipeline(_TrajPipeline):
         unet_net, face, drag = self.unet.net, self.face_controlnet, self.drag_controlnet
         for n in (unet_net, face.net, drag.net):
             n.prepare_clip(image_embeddings, added_time_ids)
-        face.prepare_condition(cond, flow, ldmk)
-        drag.prepare_condition(cond, dflow)
+        face.prepare_condition(cond, flow, ldmk, force=True)
+        drag.prepare_condition(cond, dflow, force=True)
         by_rows = level_masks(mask, h, w, len(self.unet.config.block_out_channels), T, device)
         lat = latents[0].to(torch.float16).reshape(T, 4, hw).contiguous()
         il = image_latents.to(torch.float16).reshape(2, 4, hw).contiguous()
@@ -103,10 +103,9 @@ class FlowControlNetPipeline(_TrajPipeline):
             cur = cur_lat.reshape(1, T, 4, h, w)
             outs = callback_on_step_end(self, i, self.scheduler.timesteps[i], {"latents": cur}) or {}
             new = outs.pop("latents", None)
-            if new is None or new is cur:
-                return False
-            cur_lat.copy_(new.reshape(T, 4, hw))
-            return True
+            if new is not None and new is not cur:
+                cur_lat.copy_(new.reshape(T, 4, hw))
+            return True             # an in-place edit of `cur` counts too (H/pipeline/pipeline.py loop end)
 
         denoise_hybrid(ops, unet_net, face.net, drag.net, by_rows, lat, il, sig, tsteps, h, w, min_guidance_scale,
                        max_guidance_scale, ctrl_scale_ldmk, ctrl_scale_traj, on_step)

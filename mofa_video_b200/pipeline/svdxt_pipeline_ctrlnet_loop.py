@@ -100,8 +100,7 @@ class FlowControlNetPipeline(_TrajPipeline):
             # loop-invariant conditioning of every distinct view
             fl = flow[:, (ts - 1):(te - 1)]
             lm = torch.cat([ldmk[:, 0:1], ldmk[:, ts:te]], dim=1)
-            ad._cond_key = None
-            ad.prepare_condition(cond, torch.cat([fl] * 2), torch.cat([lm] * 2))
+            ad.prepare_condition(cond, torch.cat([fl] * 2), torch.cat([lm] * 2), force=True)
             states.append(((ts, te), mult, (ad.net.warped, ad.net.ldmk)))
         lat = latents[0].to(torch.float16).reshape(num_frames, 4, hw).contiguous()
         il = image_latents.to(torch.float16).reshape(2, 4, hw).contiguous()
