@@ -56,18 +56,18 @@ def build_synthetic_pipeline(config=None, device="cuda", seed=0, tiny_encoders=F
         clip = make_clip_vit_h(cfg_u["cross_attention_dim"])
     vae = vae.to(device=device, dtype=torch.float16).eval()
     clip = clip.to(device=device, dtype=torch.float16).eval()
-    if native_vae:
-        from mofa_video_b200.vae_engine import NativeTemporalDecoderVAE
-        vae = NativeTemporalDecoderVAE(vae, device=device)  # decode on the sm_100a kernels; encode stays PyTorch
+    # the pipelines re-host an AutoencoderKLTemporalDecoder-layout VAE on the sm_100a kernels themselves
+    # (FlowControlNetPipeline._adopt_vae) -- the same path T/run_gradio.py:init_models takes
+    nv = None if native_vae else False
     if variant == "keypoint":
         from mofa_video_b200.pipeline.svdxt_pipeline_ctrlnet_loop import FlowControlNetPipeline as KeypointPipeline
         pipe = KeypointPipeline(vae=vae, image_encoder=clip, unet=unet, controlnet=face,
-                                scheduler=EulerDiscreteScheduler())
+                                scheduler=EulerDiscreteScheduler(), native_vae=nv)
     elif variant == "hybrid":
         from mofa_video_b200.pipeline.pipeline_hybrid import FlowControlNetPipeline as HybridPipeline
         pipe = HybridPipeline(vae=vae, image_encoder=clip, unet=unet, drag_controlnet=controlnet,
-                              face_controlnet=face, scheduler=EulerDiscreteScheduler())
+                              face_controlnet=face, scheduler=EulerDiscreteScheduler(), native_vae=nv)
     else:
         pipe = FlowControlNetPipeline(vae=vae, image_encoder=clip, unet=unet, controlnet=controlnet,
-                                      scheduler=EulerDiscreteScheduler())
+                                      scheduler=EulerDiscreteScheduler(), native_vae=nv)
     return pipe.to(device)

@@ -25,6 +25,41 @@ DEFAULT_CONFIG = dict(
 )
 
 
+# Where engine objects are built when the caller does not say: the CUDA library on "cuda".  The CPU host-logic tests
+# (no GPU in the builder container) switch both through `default_backend(...)` so that UNMODIFIED reference code --
+# e.g. T/run_gradio.py:init_models, which never passes ops= / device= -- can be executed against these classes.
+_BACKEND = {"ops": None, "device": "cuda"}
+
+
+class default_backend:
+    """Context manager (tests only): `with default_backend(ref_ops, "cpu"): ...`."""
+
+    def __init__(self, ops, device):
+        self.new = {"ops": ops, "device": device}
+
+    def __enter__(self):
+        self.old = dict(_BACKEND)
+        _BACKEND.update(self.new)
+        return self
+
+    def __exit__(self, *exc):
+        _BACKEND.update(self.old)
+        return False
+
+
+def resolve_backend(ops=None, device=None):
+    """(ops, device, is_product): the caller's choice, else the process default (the CUDA library; load() raises if it
+    has not been built -- there is no CPU or PyTorch fallback)."""
+    if ops is None:
+        ops = _BACKEND["ops"]
+    if device is None:
+        device = _BACKEND["device"]
+    if ops is None:
+        _lib.load()
+        return _lib, torch.device(device), True
+    return ops, torch.device(device), False
+
+
 def read_checkpoint(path, subfolder=None, variant=None):
     d = os.path.join(path, subfolder) if subfolder else path
     with open(os.path.join(d, "config.json")) as f:
@@ -41,20 +76,32 @@ def read_checkpoint(path, subfolder=None, variant=None):
     raise FileNotFoundError(f"no diffusion_pytorch_model*.safetensors under {d}")
 
 
+class _Config(SimpleNamespace):
+    """Attribute bag that also answers `"key" in config` / config["key"] like diffusers' FrozenDict (the reference's
+    from_unet tests membership, controlnet_sdv.py:592-600)."""
+
+    def __contains__(self, key):
+        return key in self.__dict__
+
+    def __getitem__(self, key):
+        return self.__dict__[key]
+
+    def get(self, key, default=None):
+        return self.__dict__.get(key, default)
+
+
 class EngineModel:
     """Base of UNetSpatioTemporalConditionControlNetModel / FlowControlNet."""
 
     kind = None
 
-    def __init__(self, state_dict, config=None, device="cuda", ops=None):
+    def __init__(self, state_dict, config=None, device=None, ops=None):
         cfg = dict(DEFAULT_CONFIG)
         cfg.update(config or {})
-        self.config = SimpleNamespace(**cfg)
+        self.config = _Config(**cfg)
         self._cfg = cfg
-        self._device = torch.device(device)
-        self._ops = ops if ops is not None else _lib
-        if ops is None:
-            _lib.load()  # fail loudly right here when the CUDA library is missing
+        self._ops, self._device, _ = resolve_backend(ops, device)  # fails loudly when the CUDA library is missing
+        self._sd = state_dict  # kept by reference (host memory): state_dict() / from_unet() hand these tensors on
         self.net = self._make_net(state_dict, cfg)
         self.add_embedding = SimpleNamespace(linear_1=SimpleNamespace(
             in_features=int(state_dict["add_embedding.linear_1.weight"].shape[1])))
@@ -66,13 +113,17 @@ class EngineModel:
     # -- construction --------------------------------------------------------------------------
     @classmethod
     def from_pretrained(cls, path, subfolder=None, variant=None, low_cpu_mem_usage=True, torch_dtype=None,
-                        device="cuda", **_ignored):
+                        device=None, **_ignored):
         cfg, sd = read_checkpoint(path, subfolder, variant)
         return cls(sd, cfg, device=device)
 
     @classmethod
-    def from_state_dict(cls, state_dict, config=None, device="cuda", ops=None):
+    def from_state_dict(cls, state_dict, config=None, device=None, ops=None):
         return cls(state_dict, config, device=device, ops=ops)
+
+    def state_dict(self):
+        """The reference-layout tensors this model was built from (not copies)."""
+        return self._sd
 
     # -- nn.Module look-alikes the reference scripts call ---------------------------------------
     @property

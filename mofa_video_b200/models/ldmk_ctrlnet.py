@@ -9,6 +9,8 @@ import torch
 
 from mofa_video_b200.keypoint_engine import LdmkAdapterNet
 from mofa_video_b200.models._base import EngineModel
+from mofa_video_b200.models.svdxt_featureflow_forward_controlnet_s2d_fixcmp_norefine import \
+    FlowControlNet as _TrajFlowControlNet
 from mofa_video_b200.models.svdxt_featureflow_forward_controlnet_s2d_fixcmp_norefine import _identity_key, _same_key
 
 
@@ -30,6 +32,15 @@ class FlowControlNet(EngineModel):
 
     def _make_net(self, state_dict, cfg):
         return LdmkAdapterNet(state_dict, cfg, self._ops, self._device)
+
+    @staticmethod
+    def _fresh_state_dict(cfg):
+        """from_unet (K/models/controlnet_sdv.py:572-628): landmark embedding / occlusion nets fresh, zero_module convs zero."""
+        from mofa_video_b200 import synthetic
+        return synthetic.ldmk_adapter_state_dict(cfg, seed=3, zero_std=0.0)
+
+    from_unet = classmethod(_TrajFlowControlNet.from_unet.__func__)
+    _UNET_PREFIXES = _TrajFlowControlNet._UNET_PREFIXES
 
     def prepare_condition(self, controlnet_cond, controlnet_flow, landmarks, force=False):
         """controlnet_cond [B,3,H,W] in [-1,1]; controlnet_flow [B,T-1,2,H,W]; landmarks [B,T,3,H,W] (B = CFG copies).

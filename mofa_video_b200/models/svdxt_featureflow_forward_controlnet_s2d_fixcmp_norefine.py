@@ -37,6 +37,46 @@ class FlowControlNet(EngineModel):
         super().__init__(*args, **kwargs)
         self._cond_key = None
 
+    # -- ControlNetSDVModel.from_unet (models/controlnet_sdv.py:572-628; Training/train_stage2.py:823) ------------
+    _UNET_PREFIXES = ("conv_in.", "time_embedding.", "down_blocks.", "mid_block.")   # :617-626 (time_proj has no weights)
+
+    @staticmethod
+    def _fresh_state_dict(cfg):
+        """Everything from_unet does NOT copy: add_embedding, cond embedding, first-frame encoder (fresh init) and the
+        zero_module convs -- exactly zero, weights and biases (controlnet_sdv.py:259-300, FCN.py:86-88,145)."""
+        from mofa_video_b200 import synthetic
+        return synthetic.adapter_state_dict(cfg, seed=1, zero_std=0.0)
+
+    @classmethod
+    def from_unet(cls, unet, controlnet_conditioning_channel_order="rgb",
+                  conditioning_embedding_out_channels=(16, 32, 96, 256), load_weights_from_unet=True,
+                  conditioning_channels=3, device=None, ops=None):
+        """Adapter with the UNet's configuration; conv_in / time_embedding / down_blocks / mid_block take the UNet's
+        weights (by reference, no copy) when load_weights_from_unet.  `unet` is any object with .config and
+        .state_dict() in the reference layout (this package's UNet, the oracle's, diffusers')."""
+        uc = unet.config
+        get = (lambda k: uc.get(k)) if isinstance(uc, dict) else (lambda k: getattr(uc, k, None))
+        cfg = {k: get(k) for k in ("in_channels", "down_block_types", "block_out_channels", "addition_time_embed_dim",
+                                   "transformer_layers_per_block", "cross_attention_dim", "num_attention_heads",
+                                   "num_frames", "sample_size", "layers_per_block",
+                                   "projection_class_embeddings_input_dim")}
+        cfg = {k: v for k, v in cfg.items() if v is not None}
+        cfg["conditioning_channels"] = conditioning_channels
+        cfg["conditioning_embedding_out_channels"] = tuple(conditioning_embedding_out_channels)
+        cfg_full, sd = cls._fresh_state_dict(cfg)
+        if load_weights_from_unet:
+            usd = unet.state_dict()
+            for k in list(sd):
+                if k.startswith(cls._UNET_PREFIXES):
+                    if tuple(usd[k].shape) != tuple(sd[k].shape):
+                        raise ValueError(f"from_unet: {k} has shape {tuple(usd[k].shape)} in the UNet, "
+                                         f"{tuple(sd[k].shape)} expected")
+                    sd[k] = usd[k]
+        if ops is None and device is None and isinstance(unet, EngineModel):
+            ops, device = unet._ops, unet._device
+        return cls(sd, {k: v for k, v in cfg_full.items() if k not in ("out_channels", "up_block_types")},
+                   device=device, ops=ops)
+
     def prepare_condition(self, controlnet_cond, controlnet_flow, force=False):
         """controlnet_cond [B, 3, H, W] in [-1, 1], controlnet_flow [B, T-1, 2, H, W] (B = CFG copies).
         The branch is skipped only when the SAME tensor objects (held by reference, unchanged `_version`) come back,
@@ -100,12 +140,12 @@ class CMP_demo:
     'state_dict', names prefixed 'module.'); like the reference (models/cmp/utils/common_utils.py:115-116) a missing
     checkpoint is a warning and the network keeps its random initialisation."""
 
-    def __init__(self, configfn=None, load_iter=None, state_dict=None, device="cuda", ops=None):
+    def __init__(self, configfn=None, load_iter=None, state_dict=None, device=None, ops=None):
         import os
         import warnings
 
-        from mofa_video_b200 import lib as _lib
         from mofa_video_b200.cmp_engine import CmpNet
+        from mofa_video_b200.models._base import resolve_backend
         nbins, fmax = 99, 50.0
         if configfn is not None:
             import yaml
@@ -124,9 +164,7 @@ class CMP_demo:
         if state_dict is None:
             from mofa_video_b200 import synthetic
             state_dict = synthetic.cmp_state_dict()
-        self._ops = ops if ops is not None else _lib
-        if ops is None:
-            _lib.load()
+        self._ops, device, _ = resolve_backend(ops, device)
         self.net = CmpNet(state_dict, self._ops, device, nbins=nbins, fmax=fmax)
 
     def to(self, *a, **k):

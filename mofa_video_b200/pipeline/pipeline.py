@@ -99,17 +99,42 @@ class FlowControlNetPipeline:
     _callback_tensor_inputs = ["latents"]
 
     def __init__(self, vae, image_encoder, unet, controlnet, scheduler, feature_extractor=None, ops=None,
-                 device="cuda"):
-        """`ops` / `device` exist for the CPU host-logic tests only (tests/ref_ops.py states every C-ABI op in PyTorch);
-        a product user never passes them: the default binds the CUDA library and fails if it is missing."""
-        self.vae, self.image_encoder, self.unet, self.controlnet = vae, image_encoder, unet, controlnet
+                 device=None, native_vae=None):
+        """`ops` / `device` / `native_vae` exist for the CPU host-logic tests only (tests/ref_ops.py states every C-ABI
+        op in PyTorch); a product user never passes them: the default binds the CUDA library and fails if it is
+        missing, and re-hosts the VAE on the kernels."""
+        from mofa_video_b200.models._base import resolve_backend
+        self._ops, self._device, _ = resolve_backend(ops, device)  # no fallback: raises if the library is missing
+        if native_vae is None:
+            native_vae = True
+        self.image_encoder, self.unet, self.controlnet = image_encoder, unet, controlnet
+        self.vae = self._adopt_vae(vae) if native_vae else vae
         self.scheduler, self.feature_extractor = scheduler, feature_extractor
         self.vae_scale_factor = 2 ** (len(self.vae.config.block_out_channels) - 1)
-        self._device = torch.device(device)
         self.timings = {}
-        self._ops = ops if ops is not None else _lib
-        if ops is None:
-            _lib.load()  # no fallback: fail here if the CUDA library is missing
+
+    _VAE_KEYS = ("encoder.conv_in.weight", "quant_conv.weight", "decoder.conv_in.weight",
+                 "decoder.mid_block.attentions.0.to_q.weight", "decoder.time_conv_out.weight")
+
+    def _adopt_vae(self, vae):
+        """What the reference's scripts hand over is diffusers' AutoencoderKLTemporalDecoder (T/run_gradio.py:101-102).
+        Any module with that parameter layout is re-hosted on the sm_100a kernels (vae_engine.NativeTemporalDecoderVAE:
+        encode, decode and the fused uint8 tail); only a VAE of some other architecture is left to run as the caller
+        built it."""
+        if hasattr(vae, "decode_uint8") or not hasattr(vae, "state_dict"):
+            return vae
+        sd = vae.state_dict()
+        if not all(k in sd for k in self._VAE_KEYS):
+            return vae
+        cfg = vae.config
+        boc = cfg["block_out_channels"] if isinstance(cfg, dict) else cfg.block_out_channels
+        if any(c % 64 for c in boc):
+            import warnings
+            warnings.warn(f"VAE widths {tuple(boc)} are not multiples of 64 (the SVD VAE is 128/256/512/512): the implicit-"
+                          "GEMM kernels cannot host it, it runs as the module the caller built")
+            return vae
+        from mofa_video_b200.vae_engine import NativeTemporalDecoderVAE
+        return NativeTemporalDecoderVAE(vae, ops=self._ops, device=self._device)
 
     @classmethod
     def from_pretrained(cls, path, unet=None, controlnet=None, image_encoder=None, vae=None, scheduler=None,
@@ -197,6 +222,24 @@ class FlowControlNetPipeline:
         frames = torch.cat(frames, dim=0)
         frames = frames.reshape(-1, num_frames, *frames.shape[1:]).permute(0, 2, 1, 3, 4)
         return frames.float()
+
+    def _decode_output(self, latents, num_frames, decode_chunk_size, output_type):
+        """Step 9 of the reference __call__ (pipeline.py:513-522): latents [1, T, 4, h, w] -> `frames` of the output."""
+        if output_type == "latent":
+            return latents
+        if output_type in ("pil", "uint8", "uint8_pt") and hasattr(self.vae, "decode_uint8"):
+            # native decoder: time_conv_out + (x/2+0.5).clamp*255 -> uint8 fused in the decoder's tail kernel
+            lat = latents.to(torch.float16).flatten(0, 1) * (1 / self.vae.config.scaling_factor)
+            u8 = torch.cat([self.vae.decode_uint8(lat[i:i + decode_chunk_size],
+                                                  num_frames=lat[i:i + decode_chunk_size].shape[0])
+                            for i in range(0, lat.shape[0], decode_chunk_size)], dim=0)  # [T, H, W, 3]
+            if output_type == "uint8_pt":
+                return [u8]
+            if output_type == "uint8":
+                return [u8.cpu().numpy()]
+            return [[PIL.Image.fromarray(f) for f in u8.cpu().numpy()]]
+        frames = self.decode_latents(latents.to(self.vae.dtype), num_frames, decode_chunk_size)
+        return self._postprocess(frames, "uint8" if output_type == "uint8_pt" else output_type)
 
     @staticmethod
     def _postprocess(frames, output_type):
@@ -330,23 +373,7 @@ class FlowControlNetPipeline:
         latents = lat_h.reshape(1, T, 4, h, w)
         ev["loop"].record()
 
-        if output_type == "latent":
-            frames = latents
-        elif output_type in ("pil", "uint8", "uint8_pt") and hasattr(self.vae, "decode_uint8"):
-            # native decoder: time_conv_out + (x/2+0.5).clamp*255 -> uint8 fused in the decoder's tail kernel
-            lat = latents.to(torch.float16).flatten(0, 1) * (1 / self.vae.config.scaling_factor)
-            u8 = torch.cat([self.vae.decode_uint8(lat[i:i + decode_chunk_size],
-                                                  num_frames=lat[i:i + decode_chunk_size].shape[0])
-                            for i in range(0, lat.shape[0], decode_chunk_size)], dim=0)  # [T, H, W, 3]
-            if output_type == "uint8_pt":
-                frames = [u8]
-            elif output_type == "uint8":
-                frames = [u8.cpu().numpy()]
-            else:
-                frames = [[PIL.Image.fromarray(f) for f in u8.cpu().numpy()]]
-        else:
-            frames = self.decode_latents(latents.to(self.vae.dtype), num_frames, decode_chunk_size)
-            frames = self._postprocess(frames, "uint8" if output_type == "uint8_pt" else output_type)
+        frames = self._decode_output(latents, num_frames, decode_chunk_size, output_type)
         ev["dec"].record()
         self._events = ev
         controlnet_flow_out = controlnet_flow

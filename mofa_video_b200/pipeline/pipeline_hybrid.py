@@ -46,8 +46,9 @@ def denoise_hybrid(ops, unet_net, face_net, drag_net, by_rows, lat, il, sig, tst
 
 class FlowControlNetPipeline(_TrajPipeline):
     def __init__(self, vae, image_encoder, unet, drag_controlnet, face_controlnet, scheduler, feature_extractor=None,
-                 ops=None, device="cuda"):
-        super().__init__(vae, image_encoder, unet, drag_controlnet, scheduler, feature_extractor, ops=ops, device=device)
+                 ops=None, device=None, native_vae=None):
+        super().__init__(vae, image_encoder, unet, drag_controlnet, scheduler, feature_extractor, ops=ops, device=device,
+                         native_vae=native_vae)
         self.drag_controlnet, self.face_controlnet = drag_controlnet, face_controlnet
 
     @classmethod
@@ -110,11 +111,7 @@ class FlowControlNetPipeline(_TrajPipeline):
         denoise_hybrid(ops, unet_net, face.net, drag.net, by_rows, lat, il, sig, tsteps, h, w, min_guidance_scale,
                        max_guidance_scale, ctrl_scale_ldmk, ctrl_scale_traj, on_step)
         latents = lat.reshape(1, T, 4, h, w)
-        if output_type == "latent":
-            frames = latents
-        else:
-            frames = self.decode_latents(latents.to(self.vae.dtype), num_frames, decode_chunk_size)
-            frames = self._postprocess(frames, output_type)
+        frames = self._decode_output(latents, num_frames, decode_chunk_size, output_type)
         if not return_dict:
             return frames, controlnet_flow
         return FlowControlNetPipelineOutput(frames=frames, controlnet_flow=controlnet_flow)

@@ -119,11 +119,7 @@ class FlowControlNetPipeline(_TrajPipeline):
         lat = denoise_windowed(ops, unet_net, ad.net, states, lat, il, sig, tsteps, h, w, T, min_guidance_scale,
                                max_guidance_scale, controlnet_cond_scale, on_step)
         latents = lat.reshape(1, num_frames, 4, h, w)
-        if output_type == "latent":
-            frames = latents
-        else:
-            frames = self.decode_latents(latents.to(self.vae.dtype), num_frames, decode_chunk_size)
-            frames = self._postprocess(frames, output_type)
+        frames = self._decode_output(latents, num_frames, decode_chunk_size, output_type)
         if not return_dict:
             return frames, controlnet_flow
         return FlowControlNetPipelineOutput(frames=frames, controlnet_flow=controlnet_flow)

@@ -230,13 +230,14 @@ class NativeTemporalDecoderVAE:
     """`vae` object for FlowControlNetPipeline: encode() and decode() both run on the sm_100a kernels (the wrapped
     PyTorch module only supplies the weights and the config).  Same interface as AutoencoderKLTemporalDecoder."""
 
-    def __init__(self, torch_vae, ops=None, device="cuda"):
-        from mofa_video_b200 import lib as _lib
+    def __init__(self, torch_vae, ops=None, device=None):
+        from mofa_video_b200.models._base import resolve_backend
+        ops, device, _ = resolve_backend(ops, device)
         self.torch_vae = torch_vae
-        self.config = SimpleNamespace(**vars(torch_vae.config))
+        cfg = torch_vae.config          # our stand-in keeps a namespace, diffusers a FrozenDict
+        self.config = SimpleNamespace(**(dict(cfg) if isinstance(cfg, dict) else vars(cfg)))
         self.config.force_upcast = False  # nothing to upcast: encode() runs on the fp16 tensor-core kernels too
-        self._ops = ops if ops is not None else _lib
-        self._device = torch.device(device)
+        self._ops, self._device = ops, device
         sd = torch_vae.state_dict()
         self.net = VaeDecoderNet(sd, self._ops, self._device, block_out_channels=self.config.block_out_channels,
                                  latent_channels=self.config.latent_channels,
