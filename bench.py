@@ -81,96 +81,117 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm (oracle): bounded sample of the same workload
+# CPU arm (oracle): bounded sample of the same workload, ALWAYS at 576x1024
 # ------------------------------------------------------------------------------------------------
-def _cpu_sample(steps, warmup, frames_per_half=2, budget_s=60.0):
-    """One denoise step (adapter trunk + cond branch + UNet, fp32) at 576x1024 on 2*frames_per_half of the 50
-    CFG-batched frames, on all host cores; clip time is extrapolated x(50/frames) x25 steps (VAE/CLIP excluded).
-    If `steps` such samples would not fit `budget_s` (judged from the first evaluation) the spatial size is halved
-    (and the extrapolation multiplied by the FLOP ratio of the two shapes) -- said in `sample`.
-    Returns (frames_per_sec, seconds_per_sample, cores, description)."""
-    from oracle import fixtures
-    from oracle.models import FlowControlNet, UNetSpatioTemporalConditionControlNetModel
-    # 32 threads: on the 128-core GPU box the fp32 oracle at these small spatial sizes got slower with more
-    # (160 s per sample with 128 threads, round-1 measurement); `cores` reports the threads actually used
-    cores = min(os.cpu_count() or 1, 32)
-    torch.set_num_threads(cores)
-    cfg = dict(num_frames=frames_per_half)
-    with torch.device("meta"):
-        unet = UNetSpatioTemporalConditionControlNetModel(**cfg)
-        adapter = FlowControlNet(**cfg)
-    for m in (unet, adapter):
-        m.to_empty(device="cpu")
-        with torch.no_grad():
-            for n_, p in m.named_parameters():
-                if p.ndim > 1:
-                    p.normal_(0.0, 0.02)
-                elif n_.endswith("weight"):
-                    p.fill_(1.0)
-                else:
-                    p.zero_()
-        m.eval()
-    g = torch.Generator().manual_seed(0)
-    Tm = frames_per_half
-    emb = torch.randn(2, 1, 1024, generator=g)
-    ids = torch.tensor([[6.0, 128.0, 0.02]] * 2)
-    t = torch.tensor(1.6377)
-    # (height, width, per-frame step FLOPs relative to 576x1024): from SURVEY.md App. B, conv+linear 173.8 TF
-    # scale with the token count r, attention 43.4 TF with its square: (173.8 r + 43.4 r^2)/217.2.  Heights and widths
-    # must stay multiples of 64 (flow pyramid down to 1/64, FCN.py:302-315).
-    def rel_flops(hh, ww):
-        r = (hh * ww) / float(H * W)
-        return (173.8 * r + 43.4 * r * r) / 217.2
-    shapes = [(H, W, 1.0)] + [(hh, ww, rel_flops(hh, ww)) for hh, ww in ((320, 512), (128, 256)) if hh < H and ww < W]
+WORKLOAD = "configs[1]: Traj adapter 576x1024, 25 frames, 25 steps, fp16 on 1xB200 (CFG 1->3)"
 
-    def make(hh, ww):
-        sample = torch.randn(2, Tm, 8, hh // 8, ww // 8, generator=g)
-        cond = torch.rand(2, 3, hh, ww, generator=g) * 2 - 1
-        flow = torch.randn(2, Tm - 1, 2, hh, ww, generator=g)
 
-        def one():
+def shared_config(world):
+    """The `config` object of BOTH arms (the driver compares them): what is measured, not how."""
+    return {"workload": WORKLOAD, "step": "one clip through FlowControlNetPipeline.__call__",
+            "height": H, "width": W, "num_frames": T, "num_inference_steps": STEPS, "clips_per_gpu_per_step": 1,
+            "parallelism": f"clip-parallel x{world}",
+            "l2": "working set >> L2 (each level-0 activation is 295 MB; weights 4.4 GB)"}
+
+
+class CpuSampler:
+    """The reference's PyTorch-CPU path for this workload = the fp32 oracle (the reference itself cannot execute here:
+    SURVEY.md 8c).  One SAMPLE = one denoise step (adapter cond branch + trunk + UNet, fp32) at the FULL 576x1024
+    spatial size on 2 of the 50 CFG-batched frames of a step (one CFG half, 2 frames: batch items and frames are
+    processed independently except for the T-wide temporal layers); clip time = sample x25 (frames) x25 (steps),
+    VAE / CLIP excluded (3 % of a clip).  The spatial shape is never reduced, so every run measures the same thing."""
+
+    FRAMES = 2
+
+    def __init__(self):
+        from oracle.models import FlowControlNet, UNetSpatioTemporalConditionControlNetModel
+        self.host_cores = os.cpu_count() or 1
+        # 32 threads: on the 128-core GPU box the fp32 oracle got slower with 128 (contended host, round-1 measurement);
+        # tune() may raise this to 64 when that is measurably faster
+        self.threads = min(self.host_cores, 32)
+        torch.set_num_threads(self.threads)
+        cfg = dict(num_frames=self.FRAMES)
+        with torch.device("meta"):
+            unet = UNetSpatioTemporalConditionControlNetModel(**cfg)
+            adapter = FlowControlNet(**cfg)
+        for m in (unet, adapter):
+            m.to_empty(device="cpu")
             with torch.no_grad():
-                dres, mid, _, _ = adapter(sample, t, emb, ids, controlnet_cond=cond, controlnet_flow=flow)
-                return unet(sample, t, emb, dres, mid, added_time_ids=ids)[0]
-        return one
+                for n_, p in m.named_parameters():
+                    if p.ndim > 1:
+                        p.normal_(0.0, 0.02)
+                    elif n_.endswith("weight"):
+                        p.fill_(1.0)
+                    else:
+                        p.zero_()
+            m.eval()
+        g = torch.Generator().manual_seed(0)
+        Tm = self.FRAMES
+        self.unet, self.adapter = unet, adapter
+        self.emb = torch.randn(1, 1, 1024, generator=g)
+        self.ids = torch.tensor([[6.0, 128.0, 0.02]])
+        self.t = torch.tensor(1.6377)
+        self.sample = torch.randn(1, Tm, 8, H // 8, W // 8, generator=g)
+        self.cond = torch.rand(1, 3, H, W, generator=g) * 2 - 1
+        self.flow = torch.randn(1, Tm - 1, 2, H, W, generator=g)
 
-    # probe the smallest shape first and move up while the estimated run (FLOP-scaled) still fits the budget
-    evals = steps + max(warmup - 1, 0)
-    pick = len(shapes) - 1
-    one = make(*shapes[pick][:2])
-    t0 = time.perf_counter()
-    one()  # doubles as warm-up
-    probe = time.perf_counter() - t0
-    while pick > 0 and probe * (shapes[pick - 1][2] / shapes[pick][2]) * (evals + 1) <= budget_s:
-        pick -= 1
-        one = make(*shapes[pick][:2])
+    def one(self):
         t0 = time.perf_counter()
-        one()
-        probe = time.perf_counter() - t0
-    hh, ww, rel = shapes[pick]
-    for _ in range(max(warmup - 1, 0)):
-        one()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        one()
-    dt = (time.perf_counter() - t0) / steps
-    clip_s = dt / rel * (2 * T / (2 * Tm)) * STEPS
-    desc = (f"1 denoise step (oracle adapter+UNet, fp32, {cores} threads) at {hh}x{ww} on {2 * Tm} of {2 * T} frames; "
-            f"clip time = sample x{1 / rel:.2f} (FLOP ratio to 576x1024) x{T / Tm:.1f} (frames) x{STEPS} steps; "
-            "VAE/CLIP excluded")
-    return T / clip_s, dt, cores, desc
+        with torch.no_grad():
+            dres, mid, _, _ = self.adapter(self.sample, self.t, self.emb, self.ids, controlnet_cond=self.cond,
+                                           controlnet_flow=self.flow)
+            out = self.unet(self.sample, self.t, self.emb, dres, mid, added_time_ids=self.ids)[0]
+        assert out.shape == (1, self.FRAMES, 4, H // 8, W // 8)
+        return time.perf_counter() - t0
+
+    def tune(self, first_s):
+        """Second warm-up sample with 64 threads when the host has them; keep whichever was faster."""
+        if self.host_cores < 64:
+            return self.one()
+        torch.set_num_threads(64)
+        dt = self.one()
+        if dt < 0.9 * first_s:
+            self.threads = 64
+        else:
+            torch.set_num_threads(self.threads)
+        return dt
+
+    def fps(self, sample_s):
+        return T / (sample_s * (2 * T / self.FRAMES) * STEPS)
+
+    def describe(self):
+        return (f"1 denoise step (oracle adapter + UNet, fp32, {self.threads} threads of {self.host_cores} host cores) at "
+                f"{H}x{W} on {self.FRAMES} of {2 * T} frames; clip time = sample x{2 * T // self.FRAMES} (frames) "
+                f"x{STEPS} (steps); VAE/CLIP excluded")
+
+
+def _cpu_sample(steps, warmup):
+    """-> (frames/s, seconds per sample, threads, host cores, description): `warmup` untimed + `steps` timed samples."""
+    cs = CpuSampler()
+    first = cs.one() if warmup >= 1 else None
+    if warmup >= 2:
+        cs.tune(first)
+    for _ in range(max(warmup - 2, 0)):
+        cs.one()
+    dts = [cs.one() for _ in range(steps)]
+    dt = sum(dts) / len(dts)
+    return cs.fps(dt), dt, cs.threads, cs.host_cores, cs.describe()
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    fps, dt, cores, desc = _cpu_sample(max(args.steps, 1), min(args.warmup, 1), budget_s=180.0)
+    K = max(args.steps, 1)
+    W_ = min(max(args.warmup, 1), 2)   # each warm-up is a 10 s CPU sample: 2 (the second picks the thread count)
+    fps, dt, threads, host, desc = _cpu_sample(K, W_)
     out = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+           "steps": K, "warmup": args.warmup, "warmup_samples_run": W_, "ms_per_step": dt * 1e3,
+           "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-           "config": {"workload": "configs[1]: Traj adapter 576x1024, 25 frames, 25 steps", "sample": desc},
-           "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc},
+           "config": shared_config(max(args.gpus, 1)),
+           "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "host_cores": host, "kind": "port",
+                            "sample": desc},
            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
@@ -303,19 +324,16 @@ def run_engine(args):
                               "share_of_clip": round(att["ms"] / ms_last, 4)}}
         cpu = None
         if not args.no_cpu_baseline:
-            cfps, cdt, cores, desc = _cpu_sample(1, 1)
-            cpu = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc,
-                   "seconds_per_sample": round(cdt, 2)}
+            cfps, cdt, threads, host, desc = _cpu_sample(1, 1)
+            cpu = {"value": cfps, "unit": "frames/s", "cores": threads, "host_cores": host, "kind": "port",
+                   "sample": desc, "seconds_per_sample": round(cdt, 2)}
         h2d = img_u8.nbytes * 2 + flow_host.numel() * 2
         d2h = world * T * H * W * 3
         out = {"metric": METRIC, "value": round(fps, 4), "unit": "frames/s", "n_gpus": world, "steps": K,
                "warmup": args.warmup, "ms_per_step": round(ms_dev / K, 2), "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
-               "config": {"workload": "configs[1]: Traj adapter 576x1024, 25 frames, 25 steps, fp16, CFG 1->3",
-                          "step": "one clip through FlowControlNetPipeline.__call__", "clips_per_gpu_per_step": 1,
-                          "parallelism": f"clip-parallel x{world}", "l2": "working set >> L2 (each level-0 "
-                          "activation is 295 MB; weights 4.4 GB)",
-                          "vae_clip": "VAE encode and decode native (tcgen05 convs, fused uint8 tail); the CLIP ViT-H "
+               "config": shared_config(world),
+               "engine": {"vae_clip": "VAE encode and decode native (tcgen05 convs, fused uint8 tail); the CLIP ViT-H "
                                       "image encoder (a transformers module passed in by the caller, 0.33 TF once per "
                                       "clip) is PyTorch eager",
                           "phase_ms_last_clip": {k: round(v, 1) for k, v in tim.items()}},

@@ -170,6 +170,11 @@ int mofa_softsplat_avg(const void* feat, const void* flow, float* acc, float* ws
  * ---------------------------------------------------------------------------------------------- */
 int mofa_cfg_euler_step(const void* noise, void* latents_h, const void* image_latents, void* next_in, int32_t T,
                         int32_t HW, float g_min, float g_max, float sigma, float sigma_next, mofa_stream_t stream);
+/* Same step with (sigma, sigma_next) read from device memory `sigmas[0..1]` (fp32) at execution time: the launch
+ * carries no per-step scalar, so one captured CUDA graph of the whole denoise step (adapter + UNet + this kernel) is
+ * replayed for all 25 steps of pipeline.py:447-511 (the timestep reaches mofa_timestep_embedding the same way). */
+int mofa_cfg_euler_step_dev(const void* noise, void* latents_h, const void* image_latents, void* next_in, int32_t T,
+                            int32_t HW, float g_min, float g_max, const float* sigmas, mofa_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * VAE temporal decoder helpers (diffusers 0.24 TemporalDecoder, called from pipeline.py:194-220).
@@ -231,6 +236,18 @@ int mofa_flow_post(const void* flow_in, const void* brush, const void* flow_out,
  * :123): Gaussian blur + bicubic(align_corners) in one pass, fp32 planes [planes, H, W] -> [planes, Ho, Wo] */
 int mofa_resize_antialias(const void* img, void* out, int32_t planes, int32_t H, int32_t W, int32_t Ho, int32_t Wo,
                           mofa_stream_t stream);
+
+/* Sparse motion hints -> dense (flow, mask) planes in front of CMP.
+ * mode 0 = get_sparseflow_and_mask_forward (/root/reference/MOFA-Video-Traj/run_gradio.py:61-86): pts float64
+ *          [K, Tn, 2] (x, y; entry 0 = start, 1.. = interpolated ends), flow fp32 [Tn-1, H, W, 2] and mask fp32
+ *          [Tn-1, H, W], collisions add; sign = -1 for is_backward_flow; B and owner_ws unused.
+ * mode 1 = get_sparse_flow + sample_optical_flow (/root/reference/MOFA-Video-Keypoint/utils/utils.py:81-119): pts =
+ *          landmarks [B, Tn, K, 2] (fp32, or fp64 when dtype64), flow [B, Tn-1, 2, H, W] in the same dtype, mask uint8
+ *          [B, Tn-1, 2, H, W]; assignment, the highest landmark index wins a collision; owner_ws int32 [B, Tn-1, H, W].
+ * Outputs are zero-filled here.  The caller validates that mode-0 start points index inside the image (numpy raises
+ * IndexError there; negative indices wrap). */
+int mofa_sparse_hints(const void* pts, int32_t mode, int32_t dtype64, int32_t B, int32_t Tn, int32_t K, int32_t H,
+                      int32_t W, int32_t sign, void* flow, void* mask, int32_t* owner_ws, mofa_stream_t stream);
 
 #ifdef __cplusplus
 }

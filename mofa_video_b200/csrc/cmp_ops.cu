@@ -489,3 +489,126 @@ extern "C" int mofa_downsample_nearest(const void* x, void* out, int32_t n_img, 
                                                                    static_cast<__half*>(out), n_img, H, W, C, s);
     return check_launch("mofa_downsample_nearest");
 }
+
+// =============================================================================================
+// Sparse motion hints -> dense (flow, mask) planes: the control-signal rasterisation in front of CMP.
+//   mode 0  /root/reference/MOFA-Video-Traj/run_gradio.py:61-86  get_sparseflow_and_mask_forward:
+//           per track k and step i, flow = int64(end - start) * sign written at pixel (int(start.y), int(start.x)) of a
+//           per-track plane, planes summed over k  =>  collisions ADD (flow and mask); float64 arithmetic like numpy.
+//           One thread per (k, i): integer-valued fp32 atomicAdd (exact, order-independent).
+//   mode 1  /root/reference/MOFA-Video-Keypoint/utils/utils.py:81-119  get_sparse_flow + sample_optical_flow:
+//           flow = landmarks[t] - landmarks[0] ASSIGNED at (clip(long(y0)), clip(long(x0))); on a collision the highest
+//           landmark index wins (what the sequential CPU index_put_ of the reference leaves behind): pass 1 atomicMax of
+//           k into an owner plane, pass 2 the owner writes.  Output already in the returned [b, t-1, 2, h, w] layout.
+// =============================================================================================
+namespace mofa {
+
+__global__ void sparse_hints_add_kernel(const double* __restrict__ pts, int K, int n_steps, int H, int W, int sign,
+                                        float* __restrict__ flow, float* __restrict__ mask) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= K * n_steps) return;
+    const int k = idx / n_steps, i = idx - k * n_steps;
+    const double* p0 = pts + static_cast<long long>(k) * (n_steps + 1) * 2;
+    const double sx = p0[0], sy = p0[1];
+    const double ex = p0[(i + 1) * 2 + 0], ey = p0[(i + 1) * 2 + 1];
+    int px = static_cast<int>(sx), py = static_cast<int>(sy);       // int(): truncation toward zero
+    if (px < 0) px += W;                                             // numpy negative-index wrap (host validated range)
+    if (py < 0) py += H;
+    const long long fx = static_cast<long long>(ex - sx) * sign;     // np.int64(): truncation toward zero
+    const long long fy = static_cast<long long>(ey - sy) * sign;
+    const long long pix = (static_cast<long long>(i) * H + py) * W + px;
+    atomicAdd(&flow[pix * 2 + 0], static_cast<float>(fx));
+    atomicAdd(&flow[pix * 2 + 1], static_cast<float>(fy));
+    atomicAdd(&mask[pix], 1.0f);
+}
+
+template <typename T>
+__device__ __forceinline__ void ldmk_pixel(const T* l0, int H, int W, int& py, int& px) {
+    long long x = static_cast<long long>(l0[0]), y = static_cast<long long>(l0[1]);   // .long(): toward zero
+    y = y < 0 ? 0 : (y > H - 1 ? H - 1 : y);                                          // torch.clip
+    x = x < 0 ? 0 : (x > W - 1 ? W - 1 : x);
+    py = static_cast<int>(y);
+    px = static_cast<int>(x);
+}
+
+template <typename T>
+__global__ void sparse_ldmk_owner_kernel(const T* __restrict__ lm, int B, int Tn, int K, int H, int W,
+                                         int* __restrict__ owner) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * (Tn - 1) * K) return;
+    const int k = idx % K, l = (idx / K) % (Tn - 1), b = idx / (K * (Tn - 1));
+    int py, px;
+    ldmk_pixel(lm + (static_cast<long long>(b) * Tn * K + k) * 2, H, W, py, px);
+    atomicMax(&owner[((static_cast<long long>(b) * (Tn - 1) + l) * H + py) * W + px], k);
+}
+
+template <typename T>
+__global__ void sparse_ldmk_write_kernel(const T* __restrict__ lm, int B, int Tn, int K, int H, int W,
+                                         const int* __restrict__ owner, T* __restrict__ flow,
+                                         uint8_t* __restrict__ mask) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * (Tn - 1) * K) return;
+    const int k = idx % K, l = (idx / K) % (Tn - 1), b = idx / (K * (Tn - 1));
+    const T* l0 = lm + (static_cast<long long>(b) * Tn * K + k) * 2;
+    const T* lt = lm + ((static_cast<long long>(b) * Tn + (l + 1)) * K + k) * 2;
+    int py, px;
+    ldmk_pixel(l0, H, W, py, px);
+    if (owner[((static_cast<long long>(b) * (Tn - 1) + l) * H + py) * W + px] != k) return;
+    const long long plane = static_cast<long long>(H) * W;
+    const long long o = (static_cast<long long>(b) * (Tn - 1) + l) * 2 * plane + static_cast<long long>(py) * W + px;
+    flow[o] = lt[0] - l0[0];
+    flow[o + plane] = lt[1] - l0[1];
+    mask[o] = 1;
+    mask[o + plane] = 1;
+}
+
+}  // namespace mofa
+
+extern "C" int mofa_sparse_hints(const void* pts, int32_t mode, int32_t dtype64, int32_t B, int32_t Tn, int32_t K,
+                                 int32_t H, int32_t W, int32_t sign, void* flow, void* mask, int32_t* owner_ws,
+                                 mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!pts || !flow || !mask || K <= 0 || Tn < 2 || H <= 0 || W <= 0 || (mode == 1 && (!owner_ws || B <= 0))) {
+        set_last_error("mofa_sparse_hints: bad arguments");
+        return MOFA_ERR_ARG;
+    }
+    if (mode == 0) {
+        const int n_steps = Tn - 1;
+        const long long px = static_cast<long long>(n_steps) * H * W;
+        cudaMemsetAsync(flow, 0, sizeof(float) * 2 * px, stream);
+        cudaMemsetAsync(mask, 0, sizeof(float) * px, stream);
+        const int n = K * n_steps;
+        mofa::sparse_hints_add_kernel<<<(n + 127) / 128, 128, 0, stream>>>(
+            static_cast<const double*>(pts), K, n_steps, H, W, sign < 0 ? -1 : 1, static_cast<float*>(flow),
+            static_cast<float*>(mask));
+        return check_launch("mofa_sparse_hints(add)");
+    }
+    if (mode != 1) {
+        set_last_error("mofa_sparse_hints: unknown mode %d", mode);
+        return MOFA_ERR_ARG;
+    }
+    const long long px = static_cast<long long>(B) * (Tn - 1) * H * W;
+    cudaMemsetAsync(owner_ws, 0xff, sizeof(int32_t) * px, stream);                       // -1
+    cudaMemsetAsync(flow, 0, (dtype64 ? sizeof(double) : sizeof(float)) * 2 * px, stream);
+    cudaMemsetAsync(mask, 0, 2 * px, stream);
+    const int n = B * (Tn - 1) * K;
+    const int g = (n + 127) / 128;
+    if (dtype64) {
+        mofa::sparse_ldmk_owner_kernel<double><<<g, 128, 0, stream>>>(static_cast<const double*>(pts), B, Tn, K, H, W,
+                                                                        owner_ws);
+        int rc = check_launch("mofa_sparse_hints(owner)");
+        if (rc) return rc;
+        mofa::sparse_ldmk_write_kernel<double><<<g, 128, 0, stream>>>(static_cast<const double*>(pts), B, Tn, K, H, W,
+                                                                        owner_ws, static_cast<double*>(flow),
+                                                                        static_cast<uint8_t*>(mask));
+    } else {
+        mofa::sparse_ldmk_owner_kernel<float><<<g, 128, 0, stream>>>(static_cast<const float*>(pts), B, Tn, K, H, W,
+                                                                       owner_ws);
+        int rc = check_launch("mofa_sparse_hints(owner)");
+        if (rc) return rc;
+        mofa::sparse_ldmk_write_kernel<float><<<g, 128, 0, stream>>>(static_cast<const float*>(pts), B, Tn, K, H, W,
+                                                                       owner_ws, static_cast<float*>(flow),
+                                                                       static_cast<uint8_t*>(mask));
+    }
+    return check_launch("mofa_sparse_hints(write)");
+}

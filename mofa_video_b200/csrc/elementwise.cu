@@ -460,7 +460,11 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, __half* _
 __global__ void __launch_bounds__(256)
 cfg_euler_kernel(const __half* __restrict__ noise, __half* __restrict__ latents, const __half* __restrict__ img_lat,
                  __half* __restrict__ next_in, int T, int HW, float g_min, float g_max, float sigma,
-                 float sigma_next) {
+                 float sigma_next, const float* __restrict__ sigmas_dev) {
+    if (sigmas_dev) {  // CUDA-graph replay: the step's (sigma, sigma_next) live in device memory, not in the launch
+        sigma = sigmas_dev[0];
+        sigma_next = sigmas_dev[1];
+    }
     const long long total = static_cast<long long>(T) * HW;
     const float in_scale = rsqrtf(sigma_next * sigma_next + 1.0f);
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -696,8 +700,22 @@ extern "C" int mofa_cfg_euler_step(const void* noise, void* latents_h, const voi
     }
     cfg_euler_kernel<<<grid_for(static_cast<long long>(T) * HW), 256, 0, stream>>>(
         static_cast<const __half*>(noise), static_cast<__half*>(latents_h), static_cast<const __half*>(image_latents),
-        static_cast<__half*>(next_in), T, HW, g_min, g_max, sigma, sigma_next);
+        static_cast<__half*>(next_in), T, HW, g_min, g_max, sigma, sigma_next, nullptr);
     return check_launch("mofa_cfg_euler_step");
+}
+
+extern "C" int mofa_cfg_euler_step_dev(const void* noise, void* latents_h, const void* image_latents, void* next_in,
+                                       int32_t T, int32_t HW, float g_min, float g_max, const float* sigmas,
+                                       mofa_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!noise || !latents_h || !image_latents || !next_in || !sigmas || T <= 0 || HW <= 0) {
+        set_last_error("mofa_cfg_euler_step_dev: bad arguments");
+        return MOFA_ERR_ARG;
+    }
+    cfg_euler_kernel<<<grid_for(static_cast<long long>(T) * HW), 256, 0, stream>>>(
+        static_cast<const __half*>(noise), static_cast<__half*>(latents_h), static_cast<const __half*>(image_latents),
+        static_cast<__half*>(next_in), T, HW, g_min, g_max, 0.f, 0.f, sigmas);
+    return check_launch("mofa_cfg_euler_step_dev");
 }
 
 // =============================================================================================

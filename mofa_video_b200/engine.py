@@ -246,6 +246,20 @@ class Net:
     def new(self, *shape, dtype=torch.float16):
         return torch.empty(*shape, dtype=dtype, device=self.device)
 
+    persistent = False  # set by a pipeline that replays a captured CUDA graph of the step (graph_step.StepRunner)
+
+    def pbuf(self, key, *shape, dtype=torch.float16):
+        """Per-clip conditioning tensor.  With `persistent` the same storage is handed out for the same (key, shape)
+        on every clip, so a captured step graph -- whose kernel arguments are raw addresses -- stays valid from clip to
+        clip; otherwise a fresh tensor (callers such as the Keypoint loop keep several views' tensors alive)."""
+        if not self.persistent:
+            return self.new(*shape, dtype=dtype)
+        cache = self.__dict__.setdefault("_pbufs", {})
+        k = (key, tuple(shape), dtype)
+        if k not in cache:
+            cache[k] = self.new(*shape, dtype=dtype)
+        return cache[k]
+
     # ------------------------------------------------------------------ per-clip / per-step conditioning
     def prepare_clip(self, image_embeddings, added_time_ids):
         """Loop-invariant vectors: collapsed cross-attention outputs [B, C] and the added-time embedding."""
@@ -253,10 +267,10 @@ class Net:
         ctx = image_embeddings.reshape(image_embeddings.shape[0], -1).to(torch.float16).contiguous()  # [B, 1024]
         self.B = ctx.shape[0]
         self.xvec = []
-        for (wv, wo, bo) in self.xattn:
+        for k, (wv, wo, bo) in enumerate(self.xattn):
             v = self.new(self.B, wv.shape[0])
             ops.linear_small(ctx, wv, None, v, 0, 0)
-            o = self.new(self.B, wo.shape[0])
+            o = self.pbuf(("xvec", k), self.B, wo.shape[0])
             ops.linear_small(v, wo, bo, o, 0, 0)
             self.xvec.append(o)
         ids = added_time_ids.to(device=self.device, dtype=torch.float32).flatten().contiguous()
@@ -266,13 +280,17 @@ class Net:
         (w1, b1), (w2, b2) = self.p["add_embedding"]
         hdn = self.new(self.B, w1.shape[0])
         ops.linear_small(e, w1, b1, hdn, 0, 1)
-        self.aug_emb = self.new(self.B, w2.shape[0])
+        self.aug_emb = self.pbuf("aug_emb", self.B, w2.shape[0])
         ops.linear_small(hdn, w2, b2, self.aug_emb, 0, 0)
 
     def time_embed(self, t_value):
         """emb = time_embedding(Timesteps(t)) + aug_emb; then every time_emb_proj(SiLU(emb)) in one call."""
         ops = self.ops
-        tt = torch.full((self.B,), float(t_value), dtype=torch.float32, device=self.device)
+        if isinstance(t_value, torch.Tensor):   # [B] fp32 on the device, read at execution time (graph replay)
+            tt = t_value
+            assert tt.dtype == torch.float32 and tt.numel() == self.B
+        else:
+            tt = torch.full((self.B,), float(t_value), dtype=torch.float32, device=self.device)
         e = self.new(self.B, self.time_dim)
         ops.timestep_embedding(tt, e, self.time_dim)
         (w1, b1), (w2, b2) = self.p["time_embedding"]
@@ -503,9 +521,9 @@ class Net:
         self.cond_feats = feats
         warped = []
         Fn = T - 1
-        for (ft, hs, ws) in feats:
+        for lvl, (ft, hs, ws) in enumerate(feats):
             C = ft.shape[1]
-            out = self.new(T * hs * ws, C)
+            out = self.pbuf(("warped", lvl), T * hs * ws, C)
             out[: hs * ws].copy_(ft)
             acc = self.new(Fn * hs * ws * C, dtype=torch.float32)
             wsum = self.new(Fn * hs * ws, dtype=torch.float32)

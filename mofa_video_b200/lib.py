@@ -23,7 +23,7 @@ EXPORTS = [
     "mofa_timestep_embedding", "mofa_softsplat_avg", "mofa_cfg_euler_step", "mofa_softmax_rows",
     "mofa_vae_time_conv_out", "mofa_im2col", "mofa_pool2d", "mofa_resize_bilinear_ac", "mofa_cmp_fuser",
     "mofa_copy_cols", "mofa_flow_pyramid", "mofa_mask_blend", "mofa_downsample_nearest", "mofa_flow_post",
-    "mofa_resize_antialias",
+    "mofa_resize_antialias", "mofa_cfg_euler_step_dev", "mofa_sparse_hints",
 ]
 
 
@@ -75,6 +75,8 @@ def load():
     lib.mofa_timestep_embedding.argtypes = [vp, vp, i32, i32, vp]
     lib.mofa_softsplat_avg.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.mofa_cfg_euler_step.argtypes = [vp, vp, vp, vp, i32, i32, f32, f32, f32, f32, vp]
+    lib.mofa_cfg_euler_step_dev.argtypes = [vp, vp, vp, vp, i32, i32, f32, f32, vp, vp]
+    lib.mofa_sparse_hints.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]
     lib.mofa_softmax_rows.argtypes = [vp, i64, i32, i64, vp]
     lib.mofa_vae_time_conv_out.argtypes = [vp, vp, vp, vp, vp, i32, i64, vp]
     lib.mofa_im2col.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]
@@ -110,8 +112,16 @@ def _chk_h(*ts):
             assert t.is_cuda and t.dtype == torch.float16 and t.is_contiguous(), (t.dtype, t.shape, t.is_contiguous())
 
 
+_graph_launches = 0  # kernels executed by CUDA-graph replays (the C counter only sees launches enqueued by the host)
+
+
+def note_graph_replay(n_kernels):
+    global _graph_launches
+    _graph_launches += int(n_kernels)
+
+
 def launch_count():
-    return int(load().mofa_launch_count())
+    return int(load().mofa_launch_count()) + _graph_launches
 
 
 # optional per-launch device timing (CUDA events on the launching stream) used by bench.py's roofline line
@@ -156,7 +166,13 @@ class _Timed:
 
 
 def launch_count_reset():
+    global _graph_launches
+    _graph_launches = 0
     load().mofa_launch_count_reset()
+
+
+def profiling():
+    return _prof is not None
 
 
 def pick_bn(n, geglu=False):
@@ -326,6 +342,15 @@ def cfg_euler_step(noise, latents_h, image_latents, next_in, T, HW, g_min, g_max
     return next_in
 
 
+def cfg_euler_step_dev(noise, latents_h, image_latents, next_in, T, HW, g_min, g_max, sigmas):
+    """cfg_euler_step with (sigma, sigma_next) = sigmas[0:2], a float32 device tensor read at execution time."""
+    _chk_h(noise, latents_h, image_latents, next_in)
+    assert sigmas.is_cuda and sigmas.dtype == torch.float32 and sigmas.numel() >= 2
+    _check(load().mofa_cfg_euler_step_dev(_p(noise), _p(latents_h), _p(image_latents), _p(next_in), T, HW, g_min, g_max,
+                                          _p(sigmas), _stream()), "mofa_cfg_euler_step_dev")
+    return next_in
+
+
 def softmax_rows(x, L=None):
     """In-place softmax over the rows of a fp16 matrix [rows, ld] (first L columns)."""
     _chk_h(x)
@@ -405,6 +430,29 @@ def flow_post(flow_in, out, F, Hs, Ws, H, W, brush=None, flow_out=None):
     _check(load().mofa_flow_post(_p(flow_in), _p(brush), _p(flow_out), _p(out), F, Hs, Ws, H, W, _stream()),
            "mofa_flow_post")
     return out
+
+
+def sparse_hints_add(pts, flow, mask, sign=1):
+    """mode 0: pts float64 [K, Tn, 2] on the device; flow fp32 [Tn-1, H, W, 2], mask fp32 [Tn-1, H, W] (zero-filled here)."""
+    K, Tn, _ = pts.shape
+    n, H, W, _ = flow.shape
+    assert pts.is_cuda and pts.dtype == torch.float64 and pts.is_contiguous() and n == Tn - 1
+    assert flow.dtype == mask.dtype == torch.float32 and flow.is_contiguous() and mask.is_contiguous()
+    _check(load().mofa_sparse_hints(_p(pts), 0, 1, 1, Tn, K, H, W, sign, _p(flow), _p(mask), None, _stream()),
+           "mofa_sparse_hints")
+    return flow, mask
+
+
+def sparse_hints_assign(landmarks, flow, mask, owner):
+    """mode 1: landmarks [B, Tn, K, 2] fp32 / fp64; flow [B, Tn-1, 2, H, W] same dtype, mask uint8 same shape,
+    owner int32 [B, Tn-1, H, W] workspace."""
+    B, Tn, K, _ = landmarks.shape
+    H, W = flow.shape[-2:]
+    assert landmarks.is_cuda and landmarks.is_contiguous() and landmarks.dtype in (torch.float32, torch.float64)
+    assert flow.dtype == landmarks.dtype and mask.dtype == torch.uint8 and owner.dtype == torch.int32
+    _check(load().mofa_sparse_hints(_p(landmarks), 1, int(landmarks.dtype == torch.float64), B, Tn, K, H, W, 1,
+                                    _p(flow), _p(mask), _p(owner), _stream()), "mofa_sparse_hints")
+    return flow, mask
 
 
 def resize_antialias(img, out):

@@ -154,6 +154,19 @@ class FlowControlNetPipeline:
         return cls(vae=vae, image_encoder=image_encoder, unet=unet, controlnet=controlnet, scheduler=scheduler,
                    feature_extractor=feature_extractor)
 
+    def _step_runner(self, unet_net, ad_net, T, h, w, g_min, g_max, cond_scale):
+        """graph_step.StepRunner for this (networks, shape, guidance, scale); at most two are kept (each holds the
+        activation pool of one captured step)."""
+        from mofa_video_b200.graph_step import StepRunner
+        cache = self.__dict__.setdefault("_runners", {})
+        key = (id(unet_net), id(ad_net), T, h, w, float(g_min), float(g_max), float(cond_scale))
+        if key not in cache:
+            while len(cache) >= 2:
+                cache.pop(next(iter(cache)))
+            cache[key] = StepRunner(self._ops, unet_net, ad_net, T, h, w, g_min, g_max, cond_scale, self._device)
+            cache[key].use_graph = cache[key].use_graph and getattr(self, "use_cuda_graph", True)
+        return cache[key]
+
     def to(self, device=None, *a, **k):
         if device is not None:
             self._device = torch.device(device)
@@ -339,27 +352,25 @@ class FlowControlNetPipeline:
         h, w = height // self.vae_scale_factor, width // self.vae_scale_factor
         hw, T = h * w, num_frames
         unet_net, ad_net = self.unet.net, self.controlnet.net
+        # the step runner owns the persistent state (latents, model input) and, on CUDA, the captured graph of one
+        # denoise step; it must exist before this clip's conditioning is written (persistent addresses, graph_step.py)
+        runner = self._step_runner(unet_net, ad_net, T, h, w, min_guidance_scale, max_guidance_scale,
+                                   controlnet_cond_scale)
         unet_net.prepare_clip(image_embeddings, added_time_ids)
         ad_net.prepare_clip(image_embeddings, added_time_ids)
         self.controlnet.prepare_condition(cond, controlnet_flow, force=True)
-        lat_h = latents[0].to(torch.float16).reshape(T, 4, hw).contiguous()
-        img_lat = image_latents.to(torch.float16).reshape(2, 4, hw).contiguous()
-        next_in = torch.empty(2 * T * hw, 8, dtype=torch.float16, device=device)
         sig = self.scheduler._sigmas_host
         ts = self.scheduler._timesteps_host
         self.scheduler._step_index = 0
-        ops.cfg_euler_step(None, lat_h, img_lat, next_in, T, hw, min_guidance_scale, max_guidance_scale, 0.0, sig[0])
+        runner.begin_clip(latents[0].reshape(T, 4, hw), image_latents.reshape(2, 4, hw), ts, sig)
         ev["enc"].record()
 
-        # 8. denoising loop (pipeline.py:447-511)
+        # 8. denoising loop (pipeline.py:447-511): one graph replay (or the same body eagerly) per step
         for i in range(len(ts)):
-            res, mid = ad_net.adapter_forward(next_in, ts[i], h, w, controlnet_cond_scale)
-            noise_pred = unet_net.unet_forward(next_in, ts[i], h, w, res, mid)
-            ops.cfg_euler_step(noise_pred, lat_h, img_lat, next_in, T, hw, min_guidance_scale, max_guidance_scale,
-                               sig[i], sig[i + 1])
+            runner.step(i)
             self.scheduler._step_index = i + 1
             if callback_on_step_end is not None:
-                cur = lat_h.reshape(1, T, 4, h, w)
+                cur = runner.lat_h.reshape(1, T, 4, h, w)
                 kw = {k: cur for k in callback_on_step_end_tensor_inputs if k == "latents"}
                 outs = callback_on_step_end(self, i, timesteps[i], kw) or {}
                 new = outs.pop("latents", None)
@@ -367,9 +378,9 @@ class FlowControlNetPipeline:
                 # (pipeline.py:502-509; an in-place edit of the tensor it was handed counts too): rebuild the fused
                 # model input from it
                 if new is not None and new is not cur:
-                    lat_h.copy_(new.reshape(T, 4, hw))
-                ops.cfg_euler_step(None, lat_h, img_lat, next_in, T, hw, min_guidance_scale, max_guidance_scale,
-                                   0.0, sig[i + 1])
+                    runner.lat_h.copy_(new.reshape(T, 4, hw))
+                runner.rebuild_input(sig[i + 1])
+        lat_h = runner.lat_h.clone()    # the runner's storage is reused by the next clip
         latents = lat_h.reshape(1, T, 4, h, w)
         ev["loop"].record()
 

@@ -788,8 +788,59 @@ def make_keypoint_network():
     print("keypoint network golden written:", tuple(mid.shape), float(mid.abs().mean()), g["n_params"])
 
 
+def _extract_functions(path, names, namespace):
+    """exec() the named top-level function definitions of a reference file, verbatim (ast), into `namespace`."""
+    import ast
+    with open(path) as f:
+        tree = ast.parse(f.read())
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert len(body) == len(names), (path, names)
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), namespace)
+    return namespace
+
+
+def sparse_flow_cases():
+    """Seeded inputs of the control-signal rasterisation goldens (shared with the tests)."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    K, n, H, W = 7, 5, 24, 32
+    pts = np.zeros((K, n + 1, 2))
+    pts[:, 0, 0] = rng.uniform(0, W - 1, K)
+    pts[:, 0, 1] = rng.uniform(0, H - 1, K)
+    pts[5, 0] = pts[2, 0]                                    # two tracks from the same pixel: their flows add
+    pts[:, 1:] = pts[:, 0:1] + rng.normal(0, 6, (K, n, 2))
+    g = torch.Generator().manual_seed(4)
+    lm = torch.rand(2, 4, 9, 2, generator=g) * torch.tensor([W + 4.0, H + 4.0]) - 2   # some landmarks off the image
+    lm[:, 0, 3] = lm[:, 0, 6]                                # two landmarks on the same pixel: the later one wins
+    return {"points": pts, "n_steps": n, "H": H, "W": W, "landmarks": lm, "t": 4}
+
+
+def make_sparse_flow():
+    """tests/golden/sparse_flow_ref.pt: outputs of the reference's OWN get_sparseflow_and_mask_forward
+    (MOFA-Video-Traj/run_gradio.py:61-86) and get_sparse_flow / sample_optical_flow (MOFA-Video-Keypoint/utils/utils.py:
+    81-119), both extracted verbatim from their files."""
+    import numpy as np
+    c = sparse_flow_cases()
+    t_ns = _extract_functions("/root/reference/MOFA-Video-Traj/run_gradio.py", ["get_sparseflow_and_mask_forward"],
+                              {"np": np})
+    k_ns = _extract_functions("/root/reference/MOFA-Video-Keypoint/utils/utils.py",
+                              ["sample_optical_flow", "get_sparse_flow"], {"torch": torch})
+    out = {}
+    for back in (False, True):
+        f, m = t_ns["get_sparseflow_and_mask_forward"](c["points"], c["n_steps"], c["H"], c["W"], is_backward_flow=back)
+        out[f"traj_flow_back{int(back)}"] = torch.from_numpy(f)
+        out[f"traj_mask_back{int(back)}"] = torch.from_numpy(m)
+    f, m = k_ns["get_sparse_flow"](c["landmarks"].clone(), c["H"], c["W"], c["t"])
+    out["ldmk_flow"], out["ldmk_mask"] = f.contiguous(), m.contiguous()
+    torch.save(out, os.path.join(OUT, "sparse_flow_ref.pt"))
+    print("sparse-flow golden written:", {k: tuple(v.shape) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--sparse-flow" in sys.argv:
+        make_sparse_flow()
+        sys.exit(0)
     make_scheduler()
     if "--networks" in sys.argv or "--all" in sys.argv:
         make_networks()

@@ -236,6 +236,56 @@ def cfg_euler_step(noise, latents_h, image_latents, next_in, T, HW, g_min, g_max
     return next_in
 
 
+def cfg_euler_step_dev(noise, latents_h, image_latents, next_in, T, HW, g_min, g_max, sigmas):
+    return cfg_euler_step(noise, latents_h, image_latents, next_in, T, HW, g_min, g_max, float(sigmas[0]),
+                          float(sigmas[1]))
+
+
+def sparse_hints_add(pts, flow, mask, sign=1):
+    """mofa_sparse_hints mode 0 (T/run_gradio.py:61-86): float64 points, collisions add."""
+    K, Tn, _ = pts.shape
+    _, H, W, _ = flow.shape
+    flow.zero_()
+    mask.zero_()
+    p = pts.cpu().numpy()
+    for k in range(K):
+        px, py = int(p[k, 0, 0]), int(p[k, 0, 1])
+        for i in range(Tn - 1):
+            d = (p[k, i + 1] - p[k, 0]).astype("int64") * sign
+            flow[i, py, px, 0] += float(d[0])
+            flow[i, py, px, 1] += float(d[1])
+            mask[i, py, px] += 1.0
+    return flow, mask
+
+
+def sparse_hints_assign(landmarks, flow, mask, owner):
+    """mofa_sparse_hints mode 1 (K/utils/utils.py:81-119): assignment, the highest landmark index wins."""
+    B, Tn, K, _ = landmarks.shape
+    H, W = flow.shape[-2:]
+    flow.zero_()
+    mask.zero_()
+    for b in range(B):
+        for k in range(K):
+            x = min(max(int(landmarks[b, 0, k, 0].long()), 0), W - 1)
+            y = min(max(int(landmarks[b, 0, k, 1].long()), 0), H - 1)
+            for l in range(Tn - 1):
+                flow[b, l, :, y, x] = landmarks[b, l + 1, k] - landmarks[b, 0, k]
+                mask[b, l, :, y, x] = 1
+    return flow, mask
+
+
+def profiling():
+    return False
+
+
+def note_graph_replay(n):
+    pass
+
+
+def launch_count():
+    return 0
+
+
 def softmax_rows(x, L=None):
     L = L if L is not None else x.shape[1]
     x[:, :L] = torch.softmax(x[:, :L].float(), dim=-1).half()

@@ -1,0 +1,69 @@
+"""-m gpu: the CUDA-graph replay of the denoise step (mofa_video_b200/graph_step.py) against the same step enqueued
+eagerly: the graph is captured on the first clip and REUSED by later clips with different images / flows / seeds /
+embeddings, so every tensor it reads must be rewritten in place -- a stale address or a stale per-step scalar shows up
+here as a mismatch.  Also: launches executed by replays are counted, profiling mode bypasses the graph."""
+import pytest
+import torch
+
+from oracle import fixtures
+from test_engine_gpu import _TinyClip, build_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def _pipe(e_unet, e_ad, cfg, use_graph):
+    from mofa_video_b200.models.autoencoder_kl_temporal_decoder import AutoencoderKLTemporalDecoder
+    from mofa_video_b200.pipeline.pipeline import FlowControlNetPipeline
+    from mofa_video_b200.utils.scheduling_euler_discrete_karras_fix import EulerDiscreteScheduler
+    torch.manual_seed(5)
+    vae = AutoencoderKLTemporalDecoder(block_out_channels=(64, 64, 128, 128)).eval().cuda().half()
+    clip = _TinyClip(cfg["cross_attention_dim"]).eval().cuda().half()
+    p = FlowControlNetPipeline(vae=vae, image_encoder=clip, unet=e_unet, controlnet=e_ad,
+                               scheduler=EulerDiscreteScheduler())
+    p.use_cuda_graph = use_graph
+    return p
+
+
+def test_graph_replay_equals_eager_across_clips():
+    from mofa_video_b200 import lib
+    cfg = dict(fixtures.TINY_CONFIG)
+    H, W, T = 128, 192, cfg["num_frames"]
+    _, _, e_unet, e_ad = build_pair(cfg)
+    _, _, e_unet2, e_ad2 = build_pair(cfg)
+    pg, pe = _pipe(e_unet, e_ad, cfg, True), _pipe(e_unet2, e_ad2, cfg, False)
+    outs = []
+    for k in range(3):
+        image = fixtures.make_image(H, W, seed=1234 + k)
+        flow = fixtures.make_flow(T, H, W, seed=1235 + k) * (1.0 + 0.5 * k)
+        lat0 = torch.randn(1, T, 4, H // 8, W // 8, generator=torch.Generator().manual_seed(9 + k)).half()
+        kw = dict(height=H, width=W, num_inference_steps=4, output_type="latent")
+        lib.launch_count_reset()
+        a = pg(image, image, flow, latents=lat0.clone(), generator=torch.Generator().manual_seed(11 + k), **kw).frames
+        n_graph = lib.launch_count()
+        lib.launch_count_reset()
+        b = pe(image, image, flow, latents=lat0.clone(), generator=torch.Generator().manual_seed(11 + k), **kw).frames
+        n_eager = lib.launch_count()
+        assert torch.isfinite(a).all()
+        err = ((a.float() - b.float()).abs().max() / b.float().abs().max()).item()
+        assert err < 2e-3, f"clip {k}: graph vs eager {err}"
+        assert abs(n_graph - n_eager) <= 2, (n_graph, n_eager)      # replayed kernels are counted
+        outs.append(a.clone())
+    runner = next(iter(pg._runners.values()))
+    assert runner.graph is not None and runner.kernels_per_step > 100
+    assert (outs[0].float() - outs[1].float()).abs().max() > 1e-2     # the clips really differ
+    # a callback that edits the latents still works between replays
+    image, flow = fixtures.make_image(H, W), fixtures.make_flow(T, H, W)
+    lat0 = torch.randn(1, T, 4, H // 8, W // 8, generator=torch.Generator().manual_seed(9)).half()
+
+    def cb(p, i, t, d):
+        return {"latents": d["latents"] * 0.5} if i == 1 else {}
+    kw = dict(height=H, width=W, num_inference_steps=4, output_type="latent", callback_on_step_end=cb)
+    a = pg(image, image, flow, latents=lat0.clone(), generator=torch.Generator().manual_seed(1), **kw).frames
+    b = pe(image, image, flow, latents=lat0.clone(), generator=torch.Generator().manual_seed(1), **kw).frames
+    assert ((a.float() - b.float()).abs().max() / b.float().abs().max()).item() < 2e-3
+    # profiling mode runs the same body eagerly (per-launch events cannot be recorded inside a replay)
+    lib.profile_start()
+    c = pg(image, image, flow, latents=lat0.clone(), generator=torch.Generator().manual_seed(1), **kw).frames
+    prof = lib.profile_stop()
+    assert sum(v["launches"] for v in prof.values()) > 100
+    assert ((c.float() - b.float()).abs().max() / b.float().abs().max()).item() < 2e-3

@@ -176,3 +176,25 @@ def test_adapter_parameter_names_match_the_reference_training_dump():
     if os.path.exists(ref_file):  # builder container only: check the digest against the file itself
         ref = sorted(line.strip() for line in open(ref_file) if line.strip())
         assert hashlib.sha256("\n".join(ref).encode()).hexdigest() == digest
+
+
+def test_softsplat_oracle_matches_reference_kernel_golden():
+    """oracle/softsplat.py vs outputs of the reference's OWN CUDA-C kernel + Python wrapper (softsplat.py:232-335), run on a
+    B200 (oracle/make_softsplat_ref.py; fp32 atomics => summation order differs: 1e-5 relative)."""
+    import os
+    import pytest
+    from oracle import make_softsplat_ref as msr
+    from oracle.softsplat import softsplat, softsplat_out
+    if not os.path.exists(msr.GOLDEN):
+        pytest.skip("tests/golden/softsplat_ref.pt not generated yet")
+    gold = torch.load(msr.GOLDEN)
+    assert len(gold["cases"]) == len(msr.CASES)
+    for i, c in enumerate(gold["cases"]):
+        x, fl = c["x"].float(), c["flow"].float()
+        x2, fl2 = msr.make_case(i)
+        assert torch.equal(x, x2) and torch.equal(fl.nan_to_num(7.0, 8.0, 9.0), fl2.nan_to_num(7.0, 8.0, 9.0))
+        ones = torch.cat([x, x.new_ones(x.shape[0], 1, x.shape[2], x.shape[3])], 1)
+        s = softsplat_out(ones, fl)
+        assert (s - c["out_sum"]).abs().max().item() <= 1e-5 * max(1.0, c["out_sum"].abs().max().item()), i
+        a = softsplat(x, fl, None, "avg")
+        assert (a - c["out_avg"]).abs().max().item() <= 1e-4 * max(1.0, c["out_avg"].abs().max().item()), i
