@@ -243,9 +243,11 @@ def run_engine(args):
 
     host_out = torch.empty(world if rank == 0 else 1, T, H, W, 3, dtype=torch.uint8).pin_memory()
 
+    host_gen = torch.Generator().manual_seed(42 + rank)   # PIL inputs: the noise is drawn on the CPU (pipeline.py:339-341)
+
     def clip_e2e():
         out = pipe(pil, pil, flow_host, height=H, width=W, num_frames=T, num_inference_steps=STEPS,
-                   decode_chunk_size=8, generator=lat_gen, output_type="uint8_pt")
+                   decode_chunk_size=8, generator=host_gen, output_type="uint8_pt")
         u8 = out.frames[0]  # uint8 [T, H, W, 3] on the device (post-processing fused in the decoder tail)
         bufs = parallel.gather_frames(u8, dst=0)  # the path's only collective; identity at N=1
         if rank == 0:
