@@ -177,7 +177,8 @@ def finish():
             @staticmethod
             def apply(ten_in, ten_flow):
                 want = torch.cat([x, x.new_ones(x.shape[0], 1, x.shape[2], x.shape[3])], 1)
-                assert torch.equal(ten_in, want) and torch.equal(ten_flow, fl)
+                assert torch.equal(ten_in, want) and torch.equal(ten_flow.nan_to_num(7.0, 8.0, 9.0),
+                                                                 fl.nan_to_num(7.0, 8.0, 9.0))
                 return raw.clone()
         ref.softsplat_func = _Recorded           # the reference wrapper's only use of the kernel (:250)
         out_avg = ref.softsplat(x, fl, None, "avg")
