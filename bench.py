@@ -242,17 +242,38 @@ def run_engine(args):
                     decode_chunk_size=8, generator=lat_gen, output_type="uint8_pt")
 
     host_out = torch.empty(world if rank == 0 else 1, T, H, W, 3, dtype=torch.uint8).pin_memory()
+    # N > 1: the decoder's uint8 epilogue stores straight into rank 0's gather buffer over NVLink (parallel.PeerFrameGather,
+    # SURVEY 8f-3); if peer mapping is unavailable on this box the portable NCCL gather is used and the line says so
+    gather, gather_kind = None, "none (1 GPU)"
+    if world > 1:
+        try:
+            gather = parallel.PeerFrameGather((T, H, W, 3))
+            gather_kind = "decoder epilogue -> NVLink peer stores into rank 0 (no NCCL on the data path)"
+        except Exception as exc:  # noqa: BLE001
+            gather_kind = f"nccl gather (peer mapping unavailable: {type(exc).__name__}: {exc})"[:200]
+        flags = [gather is not None]
+        allf = [None] * world
+        dist.all_gather_object(allf, flags[0])
+        if not all(allf):
+            gather = None
 
     host_gen = torch.Generator().manual_seed(42 + rank)   # PIL inputs: the noise is drawn on the CPU (pipeline.py:339-341)
 
     def clip_e2e():
         out = pipe(pil, pil, flow_host, height=H, width=W, num_frames=T, num_inference_steps=STEPS,
                    decode_chunk_size=8, generator=host_gen, output_type="uint8_pt")
-        u8 = out.frames[0]  # uint8 [T, H, W, 3] on the device (post-processing fused in the decoder tail)
-        bufs = parallel.gather_frames(u8, dst=0)  # the path's only collective; identity at N=1
-        if rank == 0:
-            for r, b in enumerate(bufs):
-                host_out[r].copy_(b, non_blocking=True)
+        u8 = out.frames[0]  # uint8 [T, H, W, 3] (post-processing fused in the decoder tail); with the peer gather this
+                            # IS slot `rank` of rank 0's buffer, already written over NVLink by the tail kernel
+        if gather is not None:
+            gather.publish()
+            if rank == 0:
+                host_out.copy_(gather.collect(), non_blocking=True)
+                gather.release()
+        else:
+            bufs = parallel.gather_frames(u8, dst=0)  # portable form: one NCCL gather; identity at N=1
+            if rank == 0:
+                for r, b in enumerate(bufs):
+                    host_out[r].copy_(b, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     def sync_all():
@@ -292,10 +313,15 @@ def run_engine(args):
     tim = pipe.last_timings_ms()
     ms_dev += ms_last
     launches = lib.launch_count()
-    if world > 1:  # NCCL communicator / gather buffers are created at the first collective: keep that out of the timing
+    if world > 1 and gather is None:  # NCCL communicator / buffers are created at the first collective: not timed
         parallel.gather_frames(torch.zeros(T, H, W, 3, dtype=torch.uint8, device=dev), dst=0)
         torch.cuda.synchronize()
+    pipe.frame_sink = gather
+    clip_e2e()                      # one untimed e2e clip (first use of the host-input path and of the gather)
     ms_e2e = timed(clip_e2e, K)
+    pipe.frame_sink = None
+    if gather is not None:
+        gather.check()
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -342,7 +368,7 @@ def run_engine(args):
                "roofline": roof, "cpu_baseline": cpu,
                "e2e": {"value": round(fps_e2e, 4), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
                        "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e / K, 2)},
-               "gpu_launches": int(launches), "clocks": clocks}
+               "gather": gather_kind, "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -237,6 +237,19 @@ int mofa_flow_post(const void* flow_in, const void* brush, const void* flow_out,
 int mofa_resize_antialias(const void* img, void* out, int32_t planes, int32_t H, int32_t W, int32_t Ho, int32_t Wo,
                           mofa_stream_t stream);
 
+/* Peer-store gather of the decoded frames (the one kernel -> collective edge of the path).
+ * Rank r's decoder tail (mofa_vae_time_conv_out) writes its uint8 frames straight into slot r of a buffer that lives in
+ * rank 0's HBM (an IPC-mapped peer pointer passed as `out_u8`): NVLink stores issued by the epilogue itself, no staging
+ * copy and no NCCL call.  These three entry points are the synchronisation around it:
+ *   mofa_peer_enable  cudaDeviceEnablePeerAccess(current -> peer_device), idempotent
+ *   mofa_peer_signal  one thread: __threadfence_system(), then st.release.sys of `value` to `flag` (local or peer memory);
+ *                     stream-ordered after the tail kernels, so it publishes all their stores
+ *   mofa_peer_wait    n threads spin (ld.acquire.sys, nanosleep) until flags[i] >= value (wrap-safe), at most `timeout_s`
+ *                     seconds (then *timed_out = 1 + index of the first silent flag, if timed_out != NULL) */
+int mofa_peer_enable(int32_t peer_device);
+int mofa_peer_signal(void* flag, uint32_t value, mofa_stream_t stream);
+int mofa_peer_wait(const void* flags, int32_t n, uint32_t value, double timeout_s, void* timed_out, mofa_stream_t stream);
+
 /* Sparse motion hints -> dense (flow, mask) planes in front of CMP.
  * mode 0 = get_sparseflow_and_mask_forward (/root/reference/MOFA-Video-Traj/run_gradio.py:61-86): pts float64
  *          [K, Tn, 2] (x, y; entry 0 = start, 1.. = interpolated ends), flow fp32 [Tn-1, H, W, 2] and mask fp32

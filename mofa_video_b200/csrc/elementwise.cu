@@ -815,7 +815,137 @@ vae_time_conv_out_kernel(const __half* __restrict__ y, const float* __restrict__
     }
 }
 
+// uint8-only tail, four pixels per thread: 24-byte fp16 reads per temporal tap, ONE 12-byte run of output per thread as three
+// aligned 32-bit stores -- the form that also travels well when `out_u8` is another GPU's memory (NVLink peer stores into the
+// gather buffer of rank 0, parallel.PeerFrameGather: the frame epilogue fused with the path's only collective).
+__global__ void __launch_bounds__(256)
+vae_time_conv_out_u8x4_kernel(const __half* __restrict__ y, const float* __restrict__ w, const float* __restrict__ b,
+                              uint32_t* __restrict__ out_u8, int T, long long HW) {
+    const long long quads = HW >> 2;
+    const long long total = static_cast<long long>(T) * quads;
+    float wr[27];
+#pragma unroll
+    for (int i = 0; i < 27; ++i) wr[i] = w[i];
+    const float b0 = b[0], b1 = b[1], b2 = b[2];
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int t = static_cast<int>(idx / quads);
+        const long long p = (idx - static_cast<long long>(t) * quads) << 2;
+        float acc[4][3];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            acc[q][0] = b0;
+            acc[q][1] = b1;
+            acc[q][2] = b2;
+        }
+#pragma unroll
+        for (int dt = 0; dt < 3; ++dt) {
+            const int tt = t + dt - 1;
+            if (tt < 0 || tt >= T) continue;
+            // 12 fp16 = 24 bytes, 8-byte aligned (p % 4 == 0): three 64-bit loads
+            const uint2* src = reinterpret_cast<const uint2*>(y + (static_cast<long long>(tt) * HW + p) * 3);
+            uint2 r[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) r[k] = __ldg(src + k);
+            const __half* h = reinterpret_cast<const __half*>(r);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float x0 = __half2float(h[q * 3 + 0]), x1 = __half2float(h[q * 3 + 1]),
+                            x2 = __half2float(h[q * 3 + 2]);
+#pragma unroll
+                for (int co = 0; co < 3; ++co)
+                    acc[q][co] += wr[(co * 3 + 0) * 3 + dt] * x0 + wr[(co * 3 + 1) * 3 + dt] * x1 +
+                                  wr[(co * 3 + 2) * 3 + dt] * x2;
+            }
+        }
+        uint32_t o[3] = {0u, 0u, 0u};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int co = 0; co < 3; ++co) {
+                const float u = fminf(fmaxf(acc[q][co] * 0.5f + 0.5f, 0.f), 1.f) * 255.f;
+                const int byte = q * 3 + co;
+                o[byte >> 2] |= static_cast<uint32_t>(__float2int_rn(u)) << ((byte & 3) * 8);
+            }
+        uint32_t* dst = out_u8 + ((static_cast<long long>(t) * HW + p) * 3 >> 2);
+        dst[0] = o[0];
+        dst[1] = o[1];
+        dst[2] = o[2];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// cross-GPU flags for the peer-store gather: publish (after this GPU's stores) / wait (before reading them)
+// ---------------------------------------------------------------------------------------------
+__global__ void peer_signal_kernel(uint32_t* flag, uint32_t value) {
+    __threadfence_system();   // every store this GPU issued before this kernel is visible system-wide first
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+
+__global__ void peer_wait_kernel(const uint32_t* flags, int n, uint32_t value, unsigned long long timeout_ns,
+                                 uint32_t* timed_out) {
+    const int i = threadIdx.x;
+    if (i >= n) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
+        if (static_cast<int32_t>(v - value) >= 0) break;            // epochs only grow
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) {                                 // a dead peer must not hang this GPU
+            if (timed_out) *timed_out = 1u + static_cast<uint32_t>(i);
+            break;
+        }
+        __nanosleep(200);
+    }
+}
+
 }  // namespace mofa
+
+extern "C" int mofa_peer_enable(int32_t peer_device) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur == peer_device) return MOFA_OK;
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, cur, peer_device);
+    if (!can) {
+        set_last_error("mofa_peer_enable: device %d cannot access device %d (no NVLink / P2P path)", cur, peer_device);
+        return MOFA_ERR_CUDA;
+    }
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return MOFA_OK;
+    }
+    if (e != cudaSuccess) {
+        set_last_error("mofa_peer_enable: %s", cudaGetErrorString(e));
+        return MOFA_ERR_CUDA;
+    }
+    return MOFA_OK;
+}
+
+extern "C" int mofa_peer_signal(void* flag, uint32_t value, mofa_stream_t stream_) {
+    if (!flag) {
+        set_last_error("mofa_peer_signal: null flag");
+        return MOFA_ERR_ARG;
+    }
+    mofa::peer_signal_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream_)>>>(static_cast<uint32_t*>(flag), value);
+    return check_launch("mofa_peer_signal");
+}
+
+extern "C" int mofa_peer_wait(const void* flags, int32_t n, uint32_t value, double timeout_s, void* timed_out,
+                              mofa_stream_t stream_) {
+    if (!flags || n <= 0 || n > 1024) {
+        set_last_error("mofa_peer_wait: bad arguments");
+        return MOFA_ERR_ARG;
+    }
+    const unsigned long long ns = static_cast<unsigned long long>((timeout_s > 0 ? timeout_s : 30.0) * 1e9);
+    mofa::peer_wait_kernel<<<1, ((n + 31) / 32) * 32, 0, static_cast<cudaStream_t>(stream_)>>>(
+        static_cast<const uint32_t*>(flags), n, value, ns, static_cast<uint32_t*>(timed_out));
+    return check_launch("mofa_peer_wait");
+}
 
 extern "C" int mofa_softmax_rows(void* x, int64_t rows, int32_t L, int64_t ld, mofa_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -836,6 +966,13 @@ extern "C" int mofa_vae_time_conv_out(const void* y, const float* w, const float
     }
     long long blocks = (static_cast<long long>(T) * HW + 255) / 256;
     if (blocks > 148LL * 16) blocks = 148LL * 16;
+    if (out_u8 && !out_f32 && (HW % 4) == 0 && (reinterpret_cast<uintptr_t>(out_u8) % 4) == 0) {
+        long long b4 = (static_cast<long long>(T) * (HW / 4) + 255) / 256;
+        if (b4 > 148LL * 16) b4 = 148LL * 16;
+        mofa::vae_time_conv_out_u8x4_kernel<<<static_cast<unsigned>(b4), 256, 0, stream>>>(
+            static_cast<const __half*>(y), w, b, static_cast<uint32_t*>(out_u8), T, HW);
+        return check_launch("mofa_vae_time_conv_out");
+    }
     mofa::vae_time_conv_out_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
         static_cast<const __half*>(y), w, b, out_f32, static_cast<uint8_t*>(out_u8), T, HW);
     return check_launch("mofa_vae_time_conv_out");

@@ -23,7 +23,7 @@ EXPORTS = [
     "mofa_timestep_embedding", "mofa_softsplat_avg", "mofa_cfg_euler_step", "mofa_softmax_rows",
     "mofa_vae_time_conv_out", "mofa_im2col", "mofa_pool2d", "mofa_resize_bilinear_ac", "mofa_cmp_fuser",
     "mofa_copy_cols", "mofa_flow_pyramid", "mofa_mask_blend", "mofa_downsample_nearest", "mofa_flow_post",
-    "mofa_resize_antialias", "mofa_cfg_euler_step_dev", "mofa_sparse_hints",
+    "mofa_resize_antialias", "mofa_cfg_euler_step_dev", "mofa_sparse_hints", "mofa_peer_enable", "mofa_peer_signal", "mofa_peer_wait",
 ]
 
 
@@ -77,6 +77,9 @@ def load():
     lib.mofa_cfg_euler_step.argtypes = [vp, vp, vp, vp, i32, i32, f32, f32, f32, f32, vp]
     lib.mofa_cfg_euler_step_dev.argtypes = [vp, vp, vp, vp, i32, i32, f32, f32, vp, vp]
     lib.mofa_sparse_hints.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.mofa_peer_enable.argtypes = [i32]
+    lib.mofa_peer_signal.argtypes = [vp, ctypes.c_uint32, vp]
+    lib.mofa_peer_wait.argtypes = [vp, i32, ctypes.c_uint32, ctypes.c_double, vp, vp]
     lib.mofa_softmax_rows.argtypes = [vp, i64, i32, i64, vp]
     lib.mofa_vae_time_conv_out.argtypes = [vp, vp, vp, vp, vp, i32, i64, vp]
     lib.mofa_im2col.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]
@@ -453,6 +456,22 @@ def sparse_hints_assign(landmarks, flow, mask, owner):
     _check(load().mofa_sparse_hints(_p(landmarks), 1, int(landmarks.dtype == torch.float64), B, Tn, K, H, W, 1,
                                     _p(flow), _p(mask), _p(owner), _stream()), "mofa_sparse_hints")
     return flow, mask
+
+
+def peer_enable(peer_device):
+    _check(load().mofa_peer_enable(int(peer_device)), "mofa_peer_enable")
+
+
+def peer_signal(flag, value):
+    """flag: one int32 element (local or IPC-mapped peer memory)."""
+    assert flag.dtype == torch.int32 and flag.numel() >= 1
+    _check(load().mofa_peer_signal(_p(flag), int(value) & 0xffffffff, _stream()), "mofa_peer_signal")
+
+
+def peer_wait(flags, value, timeout_s=30.0, timed_out=None):
+    assert flags.dtype == torch.int32 and flags.is_contiguous()
+    _check(load().mofa_peer_wait(_p(flags), flags.numel(), int(value) & 0xffffffff, float(timeout_s), _p(timed_out),
+                                 _stream()), "mofa_peer_wait")
 
 
 def resize_antialias(img, out):

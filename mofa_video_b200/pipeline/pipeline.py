@@ -241,11 +241,20 @@ class FlowControlNetPipeline:
         if output_type == "latent":
             return latents
         if output_type in ("pil", "uint8", "uint8_pt") and hasattr(self.vae, "decode_uint8"):
-            # native decoder: time_conv_out + (x/2+0.5).clamp*255 -> uint8 fused in the decoder's tail kernel
+            # native decoder: time_conv_out + (x/2+0.5).clamp*255 -> uint8 fused in the decoder's tail kernel, every chunk
+            # written in place into one clip buffer [T, H, W, 3] -- this GPU's, or (frame_sink, multi-GPU serving) slot r
+            # of rank 0's gather buffer reached over NVLink, so the epilogue IS the gather
             lat = latents.to(torch.float16).flatten(0, 1) * (1 / self.vae.config.scaling_factor)
-            u8 = torch.cat([self.vae.decode_uint8(lat[i:i + decode_chunk_size],
-                                                  num_frames=lat[i:i + decode_chunk_size].shape[0])
-                            for i in range(0, lat.shape[0], decode_chunk_size)], dim=0)  # [T, H, W, 3]
+            sink = getattr(self, "frame_sink", None)
+            n, hh, ww = lat.shape[0], lat.shape[-2] * self.vae_scale_factor, lat.shape[-1] * self.vae_scale_factor
+            if sink is not None and output_type == "uint8_pt":
+                u8 = sink.begin()                       # waits (on the stream) until the previous clip was consumed
+                assert tuple(u8.shape) == (n, hh, ww, 3)
+            else:
+                u8 = torch.empty(n, hh, ww, 3, dtype=torch.uint8, device=lat.device)
+            for i in range(0, n, decode_chunk_size):
+                ch = lat[i:i + decode_chunk_size]
+                self.vae.decode_uint8(ch, num_frames=ch.shape[0], out=u8[i:i + ch.shape[0]])
             if output_type == "uint8_pt":
                 return [u8]
             if output_type == "uint8":

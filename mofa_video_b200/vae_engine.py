@@ -281,9 +281,14 @@ class NativeTemporalDecoderVAE:
         self.net.decode_chunk(self._cl(z), n, h, w, out_f32=out)
         return SimpleNamespace(sample=out)
 
-    def decode_uint8(self, z, num_frames=1):
-        """Same, but the fused tail writes post-processed uint8 frames [n, 8h, 8w, 3] directly."""
+    def decode_uint8(self, z, num_frames=1, out=None):
+        """Same, but the fused tail writes post-processed uint8 frames [n, 8h, 8w, 3] directly -- into `out` when given
+        (any uint8 memory this GPU can address: a slice of a clip buffer, or another GPU's memory mapped over NVLink,
+        parallel.PeerFrameGather)."""
         n, c, h, w = z.shape
-        out = torch.empty(n, 8 * h, 8 * w, 3, dtype=torch.uint8, device=self._device)
+        if out is None:
+            out = torch.empty(n, 8 * h, 8 * w, 3, dtype=torch.uint8, device=self._device)
+        else:
+            assert out.dtype == torch.uint8 and out.is_contiguous() and tuple(out.shape) == (n, 8 * h, 8 * w, 3)
         self.net.decode_chunk(self._cl(z), n, h, w, out_u8=out)
         return out
