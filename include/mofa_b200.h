@@ -237,6 +237,12 @@ int mofa_flow_post(const void* flow_in, const void* brush, const void* flow_out,
 int mofa_resize_antialias(const void* img, void* out, int32_t planes, int32_t H, int32_t W, int32_t Ho, int32_t Wo,
                           mofa_stream_t stream);
 
+/* Multi-head self-attention for small sequences and head dims other than 64 (CLIP ViT-H/14 image encoder of
+ * /root/reference/MOFA-Video-Traj/pipeline/pipeline.py:114-141: 16 heads x 80, 257 tokens): qkv fp16 [n_seq, L, 3*C]
+ * (q | k | v per token, C = heads * head_dim), out fp16 [n_seq, L, C]; softmax(q k^T * scale) v in fp32. */
+int mofa_attn_small(const void* qkv, void* out, int32_t n_seq, int32_t L, int32_t heads, int32_t head_dim, float scale,
+                    mofa_stream_t stream);
+
 /* Peer-store gather of the decoded frames (the one kernel -> collective edge of the path).
  * Rank r's decoder tail (mofa_vae_time_conv_out) writes its uint8 frames straight into slot r of a buffer that lives in
  * rank 0's HBM (an IPC-mapped peer pointer passed as `out_u8`): NVLink stores issued by the epilogue itself, no staging

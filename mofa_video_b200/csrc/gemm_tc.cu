@@ -96,11 +96,14 @@ union H8 {
     __half h[8];
 };
 
-// act: 0 none, 1 SiLU, (2 GEGLU handled separately), 3 ReLU, 4 sigmoid
+// act: 0 none, 1 SiLU, (2 GEGLU handled separately), 3 ReLU, 4 sigmoid, (5 ReLU after the residual), 6 GELU (erf),
+// 7 quick-GELU x * sigmoid(1.702 x)  -- 6 / 7 are the CLIP vision MLP activations (hidden_act "gelu" / "quick_gelu")
 MOFA_DEVICE float apply_act(float v, int act) {
     if (act == 1) return silu_f(v);
     if (act == 3) return fmaxf(v, 0.f);
     if (act == 4) return sigmoid_f(v);
+    if (act == 6) return gelu_erf_f(v);
+    if (act == 7) return v * sigmoid_f(1.702f * v);
     return v;
 }
 
@@ -451,6 +454,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 } else if (p.act == 4) {
 #pragma unroll
                                     for (int j = 0; j < 32; ++j) v[j] = sigmoid_f(v[j]);
+                                } else if (p.act == 6) {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+                                } else if (p.act == 7) {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) v[j] = v[j] * sigmoid_f(1.702f * v[j]);
                                 }
                             }
                         }

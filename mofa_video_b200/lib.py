@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libmofa_b200.so")
 
 A_LINEAR, A_CONV3X3, A_TEMPORAL3 = 0, 1, 2
 ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3, 4
+ACT_GELU, ACT_QUICK_GELU = 6, 7
 
 EXPORTS = [
     "mofa_last_error", "mofa_version", "mofa_launch_count", "mofa_launch_count_reset", "mofa_gemm",
@@ -24,6 +25,7 @@ EXPORTS = [
     "mofa_vae_time_conv_out", "mofa_im2col", "mofa_pool2d", "mofa_resize_bilinear_ac", "mofa_cmp_fuser",
     "mofa_copy_cols", "mofa_flow_pyramid", "mofa_mask_blend", "mofa_downsample_nearest", "mofa_flow_post",
     "mofa_resize_antialias", "mofa_cfg_euler_step_dev", "mofa_sparse_hints", "mofa_peer_enable", "mofa_peer_signal", "mofa_peer_wait",
+    "mofa_attn_small",
 ]
 
 
@@ -80,6 +82,7 @@ def load():
     lib.mofa_peer_enable.argtypes = [i32]
     lib.mofa_peer_signal.argtypes = [vp, ctypes.c_uint32, vp]
     lib.mofa_peer_wait.argtypes = [vp, i32, ctypes.c_uint32, ctypes.c_double, vp, vp]
+    lib.mofa_attn_small.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp]
     lib.mofa_softmax_rows.argtypes = [vp, i64, i32, i64, vp]
     lib.mofa_vae_time_conv_out.argtypes = [vp, vp, vp, vp, vp, i32, i64, vp]
     lib.mofa_im2col.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]
@@ -255,6 +258,13 @@ def attn_spatial(qkv, out, frames, L, heads, scale):
     _chk_h(qkv, out)
     with _Timed("attn_spatial", 4.0 * frames * heads * L * L * 64, f"L={L} heads={heads}"):
         _check(load().mofa_attn_spatial(_p(qkv), _p(out), frames, L, heads, scale, _stream()), "mofa_attn_spatial")
+    return out
+
+
+def attn_small(qkv, out, n_seq, L, heads, head_dim, scale):
+    """qkv [n_seq * L, 3 * heads * head_dim] -> out [n_seq * L, heads * head_dim] (CLIP image encoder)."""
+    _chk_h(qkv, out)
+    _check(load().mofa_attn_small(_p(qkv), _p(out), n_seq, L, heads, head_dim, scale, _stream()), "mofa_attn_small")
     return out
 
 

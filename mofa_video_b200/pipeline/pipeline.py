@@ -99,7 +99,7 @@ class FlowControlNetPipeline:
     _callback_tensor_inputs = ["latents"]
 
     def __init__(self, vae, image_encoder, unet, controlnet, scheduler, feature_extractor=None, ops=None,
-                 device=None, native_vae=None):
+                 device=None, native_vae=None, native_clip=None):
         """`ops` / `device` / `native_vae` exist for the CPU host-logic tests only (tests/ref_ops.py states every C-ABI
         op in PyTorch); a product user never passes them: the default binds the CUDA library and fails if it is
         missing, and re-hosts the VAE on the kernels."""
@@ -107,7 +107,10 @@ class FlowControlNetPipeline:
         self._ops, self._device, _ = resolve_backend(ops, device)  # no fallback: raises if the library is missing
         if native_vae is None:
             native_vae = True
-        self.image_encoder, self.unet, self.controlnet = image_encoder, unet, controlnet
+        if native_clip is None:
+            native_clip = True
+        self.unet, self.controlnet = unet, controlnet
+        self.image_encoder = self._adopt_image_encoder(image_encoder) if native_clip else image_encoder
         self.vae = self._adopt_vae(vae) if native_vae else vae
         self.scheduler, self.feature_extractor = scheduler, feature_extractor
         self.vae_scale_factor = 2 ** (len(self.vae.config.block_out_channels) - 1)
@@ -115,6 +118,19 @@ class FlowControlNetPipeline:
 
     _VAE_KEYS = ("encoder.conv_in.weight", "quant_conv.weight", "decoder.conv_in.weight",
                  "decoder.mid_block.attentions.0.to_q.weight", "decoder.time_conv_out.weight")
+
+    def _adopt_image_encoder(self, enc):
+        """transformers' CLIPVisionModelWithProjection (T/run_gradio.py:98) is re-hosted on the kernels
+        (clip_engine.NativeClipVision); any other image encoder runs as the module the caller built."""
+        from mofa_video_b200.clip_engine import NativeClipVision, is_clip_vision_with_projection
+        if isinstance(enc, NativeClipVision) or not is_clip_vision_with_projection(enc):
+            return enc
+        try:
+            return NativeClipVision(enc, ops=self._ops, device=self._device)
+        except NotImplementedError as exc:
+            import warnings
+            warnings.warn(f"image encoder kept as the caller's module: {exc}")
+            return enc
 
     def _adopt_vae(self, vae):
         """What the reference's scripts hand over is diffusers' AutoencoderKLTemporalDecoder (T/run_gradio.py:101-102).

@@ -46,9 +46,9 @@ def denoise_hybrid(ops, unet_net, face_net, drag_net, by_rows, lat, il, sig, tst
 
 class FlowControlNetPipeline(_TrajPipeline):
     def __init__(self, vae, image_encoder, unet, drag_controlnet, face_controlnet, scheduler, feature_extractor=None,
-                 ops=None, device=None, native_vae=None):
+                 ops=None, device=None, native_vae=None, native_clip=None):
         super().__init__(vae, image_encoder, unet, drag_controlnet, scheduler, feature_extractor, ops=ops, device=device,
-                         native_vae=native_vae)
+                         native_vae=native_vae, native_clip=native_clip)
         self.drag_controlnet, self.face_controlnet = drag_controlnet, face_controlnet
 
     @classmethod

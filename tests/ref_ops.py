@@ -13,6 +13,7 @@ import torch.nn.functional as F
 
 A_LINEAR, A_CONV3X3, A_TEMPORAL3 = 0, 1, 2
 ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3, 4
+ACT_GELU, ACT_QUICK_GELU = 6, 7
 
 
 def pick_bn(n, geglu=False):
@@ -36,6 +37,10 @@ def _epilogue(acc, *, N, bn, act, bias, rowbias, rows_per_group, rowbias_mod, re
         v = F.relu(v)
     elif act == ACT_SIGMOID:
         v = torch.sigmoid(v)
+    elif act == ACT_GELU:
+        v = F.gelu(v)
+    elif act == ACT_QUICK_GELU:
+        v = v * torch.sigmoid(1.702 * v)
     elif act == ACT_GEGLU:
         # weight rows packed per N tile as [bn/2 value | bn/2 gate]
         t = v.view(rows, N // bn, 2, bn // 2)
@@ -91,6 +96,14 @@ def attn_spatial(qkv, out, frames, L, heads, scale):
     s = (q @ k.transpose(-1, -2)) * scale
     o = torch.softmax(s, dim=-1) @ v
     out.view(frames, L, heads, 64).copy_(o.permute(0, 2, 1, 3).half())
+    return out
+
+
+def attn_small(qkv, out, n_seq, L, heads, head_dim, scale):
+    t = qkv.float().reshape(n_seq, L, 3, heads, head_dim).permute(2, 0, 3, 1, 4)
+    q, k, v = t[0], t[1], t[2]
+    o = torch.softmax((q @ k.transpose(-1, -2)) * scale, dim=-1) @ v
+    out.view(n_seq, L, heads, head_dim).copy_(o.permute(0, 2, 1, 3).half())
     return out
 
 
