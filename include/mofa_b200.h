@@ -242,6 +242,12 @@ int mofa_resize_antialias(const void* img, void* out, int32_t planes, int32_t H,
  * (q | k | v per token, C = heads * head_dim), out fp16 [n_seq, L, C]; softmax(q k^T * scale) v in fp32. */
 int mofa_attn_small(const void* qkv, void* out, int32_t n_seq, int32_t L, int32_t heads, int32_t head_dim, float scale,
                     mofa_stream_t stream);
+/* The same kernel on the temporal layout qkv [B, T, HW, 3*C] -> out [B, T, HW, C]: one sequence of T tokens per (b, pixel).
+ * With mofa_attn_small (spatial: n_seq = frames, L = h*w) this is the UNet's attention for checkpoints whose head_dim is not
+ * 64 (e.g. the class-default heads (5,10,10,20) of unet_spatio_temporal_condition_controlnet.py:93 -> d = 128);
+ * mofa_attn_spatial / mofa_attn_temporal are the d = 64 tensor-core kernels. */
+int mofa_attn_small_temporal(const void* qkv, void* out, int32_t B, int32_t T, int32_t HW, int32_t heads,
+                             int32_t head_dim, float scale, mofa_stream_t stream);
 
 /* Peer-store gather of the decoded frames (the one kernel -> collective edge of the path).
  * Rank r's decoder tail (mofa_vae_time_conv_out) writes its uint8 frames straight into slot r of a buffer that lives in

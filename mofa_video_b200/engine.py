@@ -220,7 +220,8 @@ class Net:
     def _pack_tr(self, pk, pre, C, heads):
         sb, tb = pre + ".transformer_blocks.0", pre + ".temporal_transformer_blocks.0"
         t = {"C": C, "heads": heads}
-        assert C // heads == 64, "kernels are specialised for head_dim 64 (SVD-XT config.json heads [5,10,20,20])"
+        if C % heads or (C // heads) % 2 or C // heads > 128:
+            raise ValueError(f"attention head_dim {C}/{heads}: the kernels take even head dims <= 128")
         t["norm"], t["proj_in"], t["proj_out"] = pk.norm(pre + ".norm"), pk.lin(pre + ".proj_in"), pk.lin(pre + ".proj_out")
 
         def qkv(a):
@@ -360,7 +361,11 @@ class Net:
         qkv = self.new(rows, 3 * C)
         lin(hn, t["s_qkv"], qkv)
         a = self.new(rows, C)
-        ops.attn_spatial(qkv, a, frames, hw, heads, scale)
+        d = C // heads
+        if d == 64:      # SVD-XT (heads 5,10,20,20): the tcgen05 kernel
+            ops.attn_spatial(qkv, a, frames, hw, heads, scale)
+        else:            # any other checkpoint geometry (class default (5,10,10,20) -> d = 128): the generic kernel
+            ops.attn_small(qkv, a, frames, hw, heads, d, scale)
         h2 = self.new(rows, C)
         lin(a, t["s_o"][0], h2, bias=t["s_o"][1], res1=h, rowbias=self.xvec[t["s_x"]], rows_per_group=T * hw)
         ops.layernorm(h2, t["s_n3"][0], t["s_n3"][1], hn, 1e-5)
@@ -379,7 +384,10 @@ class Net:
         lin(f, t["t_ffi2"][0], g, bias=t["t_ffi2"][1], res1=hmix)
         ops.layernorm(g, t["t_n1"][0], t["t_n1"][1], hn, 1e-5)
         lin(hn, t["t_qkv"], qkv)
-        ops.attn_temporal(qkv, a, B, T, hw, heads, scale)
+        if d == 64 and T <= 32:
+            ops.attn_temporal(qkv, a, B, T, hw, heads, scale)
+        else:
+            ops.attn_small_temporal(qkv, a, B, T, hw, heads, d, scale)
         g2 = self.new(rows, C)
         # diffusers 0.24 quirk: temporal cross-attention row i sees the context of batch item (i % B)
         assert hw % B == 0

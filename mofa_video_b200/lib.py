@@ -25,7 +25,7 @@ EXPORTS = [
     "mofa_vae_time_conv_out", "mofa_im2col", "mofa_pool2d", "mofa_resize_bilinear_ac", "mofa_cmp_fuser",
     "mofa_copy_cols", "mofa_flow_pyramid", "mofa_mask_blend", "mofa_downsample_nearest", "mofa_flow_post",
     "mofa_resize_antialias", "mofa_cfg_euler_step_dev", "mofa_sparse_hints", "mofa_peer_enable", "mofa_peer_signal", "mofa_peer_wait",
-    "mofa_attn_small",
+    "mofa_attn_small", "mofa_attn_small_temporal",
 ]
 
 
@@ -83,6 +83,7 @@ def load():
     lib.mofa_peer_signal.argtypes = [vp, ctypes.c_uint32, vp]
     lib.mofa_peer_wait.argtypes = [vp, i32, ctypes.c_uint32, ctypes.c_double, vp, vp]
     lib.mofa_attn_small.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp]
+    lib.mofa_attn_small_temporal.argtypes = [vp, vp, i32, i32, i32, i32, i32, f32, vp]
     lib.mofa_softmax_rows.argtypes = [vp, i64, i32, i64, vp]
     lib.mofa_vae_time_conv_out.argtypes = [vp, vp, vp, vp, vp, i32, i64, vp]
     lib.mofa_im2col.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]
@@ -265,6 +266,13 @@ def attn_small(qkv, out, n_seq, L, heads, head_dim, scale):
     """qkv [n_seq * L, 3 * heads * head_dim] -> out [n_seq * L, heads * head_dim] (CLIP image encoder)."""
     _chk_h(qkv, out)
     _check(load().mofa_attn_small(_p(qkv), _p(out), n_seq, L, heads, head_dim, scale, _stream()), "mofa_attn_small")
+    return out
+
+
+def attn_small_temporal(qkv, out, B, T, HW, heads, head_dim, scale):
+    _chk_h(qkv, out)
+    _check(load().mofa_attn_small_temporal(_p(qkv), _p(out), B, T, HW, heads, head_dim, scale, _stream()),
+           "mofa_attn_small_temporal")
     return out
 
 

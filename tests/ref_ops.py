@@ -107,6 +107,14 @@ def attn_small(qkv, out, n_seq, L, heads, head_dim, scale):
     return out
 
 
+def attn_small_temporal(qkv, out, B, T, HW, heads, head_dim, scale):
+    t = qkv.float().reshape(B, T, HW, 3, heads, head_dim).permute(3, 0, 2, 4, 1, 5)  # [3,B,HW,h,T,d]
+    q, k, v = t[0], t[1], t[2]
+    o = torch.softmax((q @ k.transpose(-1, -2)) * scale, dim=-1) @ v                # [B,HW,h,T,d]
+    out.view(B, T, HW, heads, head_dim).copy_(o.permute(0, 3, 1, 2, 4).half())
+    return out
+
+
 def attn_temporal(qkv, out, B, T, HW, heads, scale):
     t = qkv.float().reshape(B, T, HW, 3, heads, 64).permute(3, 0, 2, 4, 1, 5)  # [3,B,HW,h,T,64]
     q, k, v = t[0], t[1], t[2]

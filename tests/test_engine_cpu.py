@@ -77,3 +77,33 @@ def test_engine_full_frame_count():
     r = run_pair(16, 16, cfg)
     e = rel_err(r["out"], r["ref"])
     assert e < 5e-3, f"unet output rel err {e}"
+
+
+def test_step_with_head_dim_128_matches_oracle_cpu():
+    """Heads (1, 2, 2, 4) on widths (64, 128, 256, 256) give head dims 64 / 64 / 128 / 64 -- the geometry of the reference
+    class default (5, 10, 10, 20) (unet_spatio_temporal_condition_controlnet.py:93): the d != 64 level runs the generic
+    attention statements (mofa_attn_small / mofa_attn_small_temporal)."""
+    import torch
+    import ref_ops
+    from mofa_video_b200.models.svdxt_featureflow_forward_controlnet_s2d_fixcmp_norefine import FlowControlNet
+    from mofa_video_b200.models.unet_spatio_temporal_condition_controlnet import \
+        UNetSpatioTemporalConditionControlNetModel
+    from oracle import fixtures
+    cfg = dict(fixtures.TINY_CONFIG)
+    cfg["num_attention_heads"] = (1, 2, 2, 4)
+    unet, adapter = fixtures.make_models(cfg, seed=0, adapter_gain=20.0)
+    inp = fixtures.make_step_inputs(cfg, 16, 16)
+    t = torch.tensor(1.6377)
+    with torch.no_grad():
+        dres, mid, _, _ = adapter(inp["sample"], t, inp["encoder_hidden_states"], inp["added_time_ids"],
+                                  controlnet_cond=inp["controlnet_cond"], controlnet_flow=inp["controlnet_flow"])
+        ref = unet(inp["sample"], t, inp["encoder_hidden_states"], dres, mid, added_time_ids=inp["added_time_ids"])[0]
+    mk = dict(device="cpu", ops=ref_ops)
+    eu = UNetSpatioTemporalConditionControlNetModel.from_state_dict(unet.state_dict(), unet.config.__dict__, **mk)
+    ea = FlowControlNet.from_state_dict(adapter.state_dict(), adapter.config.__dict__, **mk)
+    down, midr, _, _ = ea.forward(inp["sample"], 1.6377, inp["encoder_hidden_states"], inp["added_time_ids"],
+                                  controlnet_cond=inp["controlnet_cond"], controlnet_flow=inp["controlnet_flow"],
+                                  return_dict=False)
+    out = eu.forward(inp["sample"], 1.6377, inp["encoder_hidden_states"], down, midr,
+                     added_time_ids=inp["added_time_ids"], return_dict=False)[0]
+    assert ((out.float() - ref).abs().max() / ref.abs().max()).item() < 5e-3

@@ -73,6 +73,34 @@ def test_step_full_width_channels():
     one_step(cfg, 16, 16, 1e-2)
 
 
+def test_step_head_dim_128_generic_attention():
+    """Reference class-default head geometry (d = 128 on one level): mofa_attn_small / mofa_attn_small_temporal."""
+    cfg = dict(fixtures.TINY_CONFIG)
+    cfg["num_attention_heads"] = (1, 2, 2, 4)
+    one_step(cfg, 16, 24, 1e-2)
+
+
+def test_attn_small_temporal_and_long_sequence():
+    """The generic kernel on the strided temporal layout and across several 256-key passes (online softmax)."""
+    import ref_ops
+    from mofa_video_b200 import lib
+    g = torch.Generator().manual_seed(5)
+    B, T, HW, heads, d = 2, 7, 40, 3, 128
+    C = heads * d
+    qkv = torch.randn(B * T * HW, 3 * C, generator=g).half().cuda()
+    out, ref = torch.empty(B * T * HW, C, dtype=torch.half, device="cuda"), torch.empty(B * T * HW, C, dtype=torch.half)
+    lib.attn_small_temporal(qkv, out, B, T, HW, heads, d, d ** -0.5)
+    ref_ops.attn_small_temporal(qkv.cpu(), ref, B, T, HW, heads, d, d ** -0.5)
+    assert (out.float().cpu() - ref.float()).abs().max().item() < 3e-3
+    n, L, heads, d = 2, 700, 2, 96
+    C = heads * d
+    qkv = torch.randn(n * L, 3 * C, generator=g).half().cuda()
+    out, ref = torch.empty(n * L, C, dtype=torch.half, device="cuda"), torch.empty(n * L, C, dtype=torch.half)
+    lib.attn_small(qkv, out, n, L, heads, d, d ** -0.5)
+    ref_ops.attn_small(qkv.cpu(), ref, n, L, heads, d, d ** -0.5)
+    assert (out.float().cpu() - ref.float()).abs().max().item() < 3e-3
+
+
 def test_softsplat_entry_point():
     from mofa_video_b200.models.softsplat import softsplat
     g = torch.Generator().manual_seed(3)
