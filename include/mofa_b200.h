@@ -85,6 +85,16 @@ typedef struct mofa_gemm_args {
   int32_t dilation;       /* CONV3X3 only: tap spacing (0/1 = dense; 2, 4 = CMP's dilated ResNet stages) */
   int32_t ksize;          /* CONV3X3 mode kernel size: 0/3 = 3x3, 5, 7 ("same" padding, K = ksize^2 * C;
                              7x7 = ForegroundMatting heads of the Keypoint adapter) */
+  /* GroupNorm statistics of THIS output for the GroupNorm that consumes it next (conv -> GroupNorm -> SiLU -> conv
+   * chains of ResnetBlock2D / TemporalResnetBlock): the epilogue adds sum and sum of squares of the fp16-rounded
+   * outputs into gn_stats[(row / gn_rows_per_stat) * gn_groups + (gn_c_off + col) / gn_cpg][0..1] (fp32, zeroed by this
+   * call), so mofa_groupnorm runs its apply pass only (silu flag bit 1) -- one read of the tensor saved.  NULL = off. */
+  float* gn_stats;
+  int64_t gn_rows_per_stat;
+  int32_t gn_groups;      /* groups of the consuming GroupNorm (32) */
+  int32_t gn_cpg;         /* channels per group of the consumer (even) */
+  int32_t gn_c_off;       /* channel offset of this tensor inside the consumer's (concatenated) input */
+  int32_t gn_pad;
 } mofa_gemm_args;
 
 int mofa_gemm(const mofa_gemm_args* args, mofa_stream_t stream);

@@ -111,18 +111,21 @@ class NativeClipVision:
         hcur = self.new(n * L, C)
         ops.layernorm(tok, self.pre_ln[0], self.pre_ln[1], hcur, self.eps)
         scale = 1.0 / math.sqrt(self.d)
+        # 257 tokens are only 3 M tiles: narrow N tiles (64 weight rows) spread each weight matrix over 60-240 CTAs, so
+        # the weight stream (1.26 GB per image) is pulled by the whole machine instead of 15-60 SMs
+        nb = 64
         hn, qkv, att = self.new(n * L, C), self.new(n * L, 3 * C), self.new(n * L, C)
         mid = self.new(n * L, self.layers[0]["fc1"][0].shape[0])
         for ly in self.layers:
             ops.layernorm(hcur, ly["ln1"][0], ly["ln1"][1], hn, self.eps)
-            ops.linear(hn, ly["qkv_w"], qkv, bias=ly["qkv_b"])
+            ops.linear(hn, ly["qkv_w"], qkv, bias=ly["qkv_b"], bn=nb)
             ops.attn_small(qkv, att, n, L, self.heads, self.d, scale)
             h2 = self.new(n * L, C)
-            ops.linear(att, ly["o"][0], h2, bias=ly["o"][1], res1=hcur)
+            ops.linear(att, ly["o"][0], h2, bias=ly["o"][1], res1=hcur, bn=nb)
             ops.layernorm(h2, ly["ln2"][0], ly["ln2"][1], hn, self.eps)
-            ops.linear(hn, ly["fc1"][0], mid, bias=ly["fc1"][1], act=self.act)
+            ops.linear(hn, ly["fc1"][0], mid, bias=ly["fc1"][1], act=self.act, bn=nb)
             hcur = self.new(n * L, C)
-            ops.linear(mid, ly["fc2"][0], hcur, bias=ly["fc2"][1], res1=h2)
+            ops.linear(mid, ly["fc2"][0], hcur, bias=ly["fc2"][1], res1=h2, bn=nb)
         cls = hcur.view(n, L, C)[:, 0].contiguous()
         pooled = self.new(n, C)
         ops.layernorm(cls, self.post_ln[0], self.post_ln[1], pooled, self.eps)

@@ -534,7 +534,9 @@ extern "C" int mofa_groupnorm(const void* x1, int32_t C1, const void* x2, int32_
         return MOFA_ERR_ARG;
     }
     const long long nstat = rows / rows_per_stat;
-    cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * nstat, stream);
+    const bool stats_ready = (silu & 2) != 0;   // accumulated by the producing GEMM's epilogue (mofa_gemm_args.gn_stats)
+    silu &= 1;
+    if (!stats_ready) cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * nstat, stream);
     const int vecs = C / 8;
     const int nv = (vecs + 255) / 256;
     const int VX = (vecs + nv - 1) / nv;
@@ -553,12 +555,14 @@ extern "C" int mofa_groupnorm(const void* x1, int32_t C1, const void* x2, int32_
     };
     int rpb, sps, grid;
     long long n_slabs;
-    plan(16, 3, rpb, sps, n_slabs, grid);
-    groupnorm_stats_kernel<<<grid, block, 0, stream>>>(static_cast<const __half*>(x1), C1,
-                                                       static_cast<const __half*>(x2), C2, rows_per_stat, rpb, sps,
-                                                       n_slabs, groups, stats);
-    int rc = check_launch("mofa_groupnorm(stats)");
-    if (rc) return rc;
+    if (!stats_ready) {
+        plan(16, 3, rpb, sps, n_slabs, grid);
+        groupnorm_stats_kernel<<<grid, block, 0, stream>>>(static_cast<const __half*>(x1), C1,
+                                                           static_cast<const __half*>(x2), C2, rows_per_stat, rpb, sps,
+                                                           n_slabs, groups, stats);
+        int rc = check_launch("mofa_groupnorm(stats)");
+        if (rc) return rc;
+    }
     plan(8, 3, rpb, sps, n_slabs, grid);
     groupnorm_apply_kernel<<<grid, block, 0, stream>>>(
         static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2, static_cast<const __half*>(gamma),

@@ -48,6 +48,8 @@ struct GemmKernelParams {
     int tma_out;  // epilogue through staging + TMA store (needs 16-byte aligned rows, N_out >= 64)
     long long M;
     int H, W, tiles_x, tiles_y, BH, BW, dil, ks;
+    int BN, n_img;  // conv: images per M tile (> 1 when one image is smaller than 128 pixels or its rows do not fill tiles)
+    int sBH, sBN;   // conv: rows / images covered by one warp's 32-row TMA store box
     int T, HW, tiles_p;
     __half* out;
     long long ldc;
@@ -62,6 +64,9 @@ struct GemmKernelParams {
     const __half* res2;
     long long ldr2;
     float alpha, beta1, beta2;
+    float* gn_stats;            // GroupNorm statistics of the output (see mofa_gemm_args.gn_stats) or nullptr
+    long long gn_rows_per_stat;
+    int gn_groups, gn_cpg, gn_c_off;
 };
 
 struct TileCoord {
@@ -78,8 +83,9 @@ MOFA_DEVICE TileCoord tile_coord(const GemmKernelParams& p, int mt) {
         c.m0 = static_cast<long long>(mt) * BM;
     } else if (p.mode == MOFA_A_CONV3X3) {
         int per_img = p.tiles_x * p.tiles_y;
-        c.n_img = mt / per_img;
-        int r = mt - c.n_img * per_img;
+        const int grp = mt / per_img;
+        c.n_img = grp * p.BN;
+        int r = mt - grp * per_img;
         int ty = r / p.tiles_x;
         c.y0 = ty * p.BH;
         c.x0 = (r - ty * p.tiles_x) * p.BW;
@@ -281,7 +287,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t idesc = umma_idesc_f16(static_cast<uint32_t>(n_this), false);
             const uint32_t as = iter & 1u;
             const uint32_t aphase = (iter >> 1) & 1u;
-            mbar_wait(&tempty_bar[as], aphase ^ 1);
+            // kGeglu: the epilogue warps pre-load the bias into the accumulator (tcgen05.st) before they release a stage, so
+            // the k-th use of a stage waits for the k-th release (parity k & 1) and every MMA accumulates; otherwise the
+            // first use of a stage finds it free (previous-phase parity) and the first MMA overwrites.
+            mbar_wait(&tempty_bar[as], kGeglu ? aphase : (aphase ^ 1));
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + as * acc_stride;
             for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -293,7 +302,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
                     // +32 B per K=16 step inside the 128 B swizzle atom: +2 in 16 B address units
-                    umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kGeglu || (kb | k) != 0) ? 1u : 0u);
                 }
                 umma_commit(&empty_bar[stage]);
                 if (++stage == p.stages) {
@@ -313,6 +322,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int half_bn = p.bn >> 1;
         uint32_t iter = 0;
         int mt, nt;
+        // kGeglu: accumulator columns this warp owns <- bias of N tile `nt_pre` (value half | gate half of the packed rows),
+        // so the epilogue has no bias loads / converts / adds (it is issue-bound: ~3450 issue clocks per 128 x 256 tile
+        // against 2560 clocks of MMA at K = 320, profiles/r1_ncu_geglu320_v3.csv)
+        auto prefill_bias = [&](uint32_t as_pre, int nt_pre) {
+            const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as_pre * acc_stride;
+            const int n_chunks_pre = (half_bn + 63) >> 6;
+#pragma unroll 1
+            for (int c = half; c < n_chunks_pre; c += 2) {
+#pragma unroll 1
+                for (int part = 0; part < 4; ++part) {  // (value | gate) x (two 32-column halves of the 64-column chunk)
+                    const int col = (part >> 1) * half_bn + c * 64 + (part & 1) * 32;
+                    uint32_t r[32];
+                    if (p.bias && (c * 64 + (part & 1) * 32) < half_bn) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            H8 b;
+                            b.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nt_pre * p.bn + col + g * 8));
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) r[g * 8 + j] = __float_as_uint(__half2float(b.h[j]));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = 0u;
+                    }
+                    if ((c * 64 + (part & 1) * 32) < half_bn) tmem_st_32x32(tbase + col, r);
+                }
+            }
+            tmem_st_wait();
+        };
+        if constexpr (kGeglu) {
+            for (int pre = 0; pre < 2; ++pre) {
+                int mt_pre, nt_pre;
+                if (tile_at(pre, mt_pre, nt_pre)) prefill_bias(static_cast<uint32_t>(pre), nt_pre);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&tempty_bar[0]);
+                mbar_arrive(&tempty_bar[1]);
+            }
+        }
         for (; tile_at(static_cast<int>(iter), mt, nt); ++iter) {
             const TileCoord tc = tile_coord(p, mt);
             const uint32_t as = iter & 1u;
@@ -324,10 +374,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 row = tc.m0 + r;
                 valid = row < p.M;
             } else if (p.mode == MOFA_A_CONV3X3) {
-                const int y = tc.y0 + r / p.BW;
+                // tile rows are ordered (image, y, x), x fastest -- the order the 4-D TMA box lands in shared memory
                 const int x = tc.x0 + r % p.BW;
-                valid = (y < p.H) && (x < p.W);
-                row = (static_cast<long long>(tc.n_img) * p.H + y) * p.W + x;
+                const int ry = r / p.BW;
+                const int y = tc.y0 + ry % p.BH;
+                const int ni = tc.n_img + ry / p.BH;
+                valid = (y < p.H) && (x < p.W) && (ni < p.n_img);
+                row = (static_cast<long long>(ni) * p.H + y) * p.W + x;
             } else {
                 const int pp = tc.p0 + r;
                 valid = pp < p.HW;
@@ -394,23 +447,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 uint32_t ag[32];
                                 tmem_ld_32x32(taddr + half_bn + col0, ag);
                                 tmem_ld_wait();
+                                // the bias is already inside the accumulator (prefill_bias)
 #pragma unroll
-                                for (int g = 0; g < 4; ++g) {
-                                    const int nb = nt * p.bn + col0 + g * 8;
-                                    H8 bv, bg;
-                                    bv.u = make_uint4(0, 0, 0, 0);
-                                    bg.u = make_uint4(0, 0, 0, 0);
-                                    if (p.bias) {
-                                        bv.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nb));
-                                        bg.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nb + half_bn));
-                                    }
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) {
-                                        const float val = __uint_as_float(acc[g * 8 + j]) + __half2float(bv.h[j]);
-                                        const float gate = __uint_as_float(ag[g * 8 + j]) + __half2float(bg.h[j]);
-                                        v[g * 8 + j] = val * gelu_erf_f(gate);
-                                    }
-                                }
+                                for (int j = 0; j < 32; ++j)
+                                    v[j] = __uint_as_float(acc[j]) * gelu_erf_relu_form(__uint_as_float(ag[j]));
                             } else {
                                 uint4 bvv[4];  // bias: requested while the TMEM load is in flight
                                 if (p.bias) {
@@ -500,12 +540,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
+                    if (p.gn_stats) {
+                        // GroupNorm statistics of what was just staged (the fp16-rounded outputs the consumer will read):
+                        // lane l owns the column pair (2l, 2l+1) of this 64-column chunk and walks the warp's 32 rows of
+                        // the swizzled staging tile (one 128-byte row per step: conflict-free), fp32 sums; a group never
+                        // splits a pair (channels per group is even).  Rows past the tensor and statistic boundaries
+                        // inside the 32 rows (several small images per tile) come from two ballots.
+                        const long long st = valid ? row / p.gn_rows_per_stat : -1;
+                        const long long st_prev = __shfl_up_sync(0xffffffffu, st, 1);
+                        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+                        const uint32_t bmask = __ballot_sync(0xffffffffu, lane > 0 && valid && st != st_prev) & vmask;
+                        const int colp = nt * out_cols_tile + c * 64 + 2 * lane;     // global output column of the pair
+                        const bool col_ok = colp < p.N_out;
+                        const int grp = (p.gn_c_off + colp) / p.gn_cpg;
+                        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                        int seg_row = -1;                                            // first row of the running segment
+                        const uint8_t* lane_base = stg + ((lane & 3) << 2);
+                        auto flush = [&](int sr) {
+                            const long long st_seg = __shfl_sync(0xffffffffu, st, sr);
+                            if (col_ok) {
+                                float* dst = p.gn_stats + (st_seg * p.gn_groups + grp) * 2;
+                                atomicAdd(dst, s0 + s1);
+                                atomicAdd(dst + 1, q0 + q1);
+                            }
+                            s0 = s1 = q0 = q1 = 0.f;
+                        };
+#pragma unroll
+                        for (int rr = 0; rr < 32; ++rr) {
+                            if (!((vmask >> rr) & 1u)) continue;                      // warp-uniform
+                            if (seg_row < 0) {
+                                seg_row = rr;
+                            } else if ((bmask >> rr) & 1u) {                          // statistic index changes here
+                                flush(seg_row);
+                                seg_row = rr;
+                            }
+                            const __half2 hv = *reinterpret_cast<const __half2*>(
+                                lane_base + rr * 128 + ((((lane >> 2) ^ (rr & 7))) << 4));
+                            const float2 f = __half22float2(hv);
+                            s0 += f.x;
+                            s1 += f.y;
+                            q0 = fmaf(f.x, f.x, q0);
+                            q1 = fmaf(f.y, f.y, q1);
+                        }
+                        if (seg_row >= 0) flush(seg_row);
+                    }
                     if (lane == 0) {
                         const int n0 = nt * out_cols_tile + c * 64;
                         if (p.mode == MOFA_A_LINEAR) {
                             tma_store_2d(&tmOut, stg, n0, static_cast<int>(tc.m0) + q * 32);
                         } else if (p.mode == MOFA_A_CONV3X3) {
-                            tma_store_4d(&tmOut, stg, n0, tc.x0, tc.y0 + (q * 32) / p.BW, tc.n_img);
+                            // this warp's 32 rows = sBN images x sBH rows x BW pixels of the tile
+                            const int ry0 = (q * 32) / p.BW;
+                            tma_store_4d(&tmOut, stg, n0, tc.x0, tc.y0 + ry0 % p.BH, tc.n_img + ry0 / p.BH);
                         } else {
                             const int b = tc.frame / p.T;
                             tma_store_4d(&tmOut, stg, n0, tc.p0 + q * 32, tc.frame - b * p.T, b);
@@ -535,6 +621,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
+            }
+            if constexpr (kGeglu) {  // bias of the tile that will use this accumulator stage next
+                int mt_nx, nt_nx;
+                if (tile_at(static_cast<int>(iter) + 2, mt_nx, nt_nx)) prefill_bias(as, nt_nx);
             }
             tc_fence_before();
             __syncwarp();
@@ -687,8 +777,24 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
     p.alpha = a->alpha;
     p.beta1 = a->beta1;
     p.beta2 = a->beta2;
+    p.gn_stats = nullptr;
+    if (a->gn_stats) {
+        if (!tma_out || a->gn_rows_per_stat <= 0 || a->gn_groups <= 0 || a->gn_cpg <= 0 || (a->gn_cpg & 1) ||
+            a->gn_c_off < 0 || (a->gn_c_off & 1)) {
+            set_last_error("mofa_gemm: gn_stats needs the TMA-store epilogue (16-byte rows, N_out >= 64) and an even "
+                           "gn_cpg / gn_c_off (cpg=%d c_off=%d)", a->gn_cpg, a->gn_c_off);
+            return MOFA_ERR_ARG;
+        }
+        p.gn_stats = a->gn_stats;
+        p.gn_rows_per_stat = a->gn_rows_per_stat;
+        p.gn_groups = a->gn_groups;
+        p.gn_cpg = a->gn_cpg;
+        p.gn_c_off = a->gn_c_off;
+    }
     p.BW = 1;
     p.BH = 1;
+    p.BN = 1;
+    p.sBH = p.sBN = 1;
     p.tiles_p = 1;
     p.tiles_x = p.tiles_y = 1;
     p.T = 1;
@@ -746,23 +852,43 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
         p.H = a->H;
         p.W = a->W;
         p.dil = a->dilation > 0 ? a->dilation : 1;
+        // M tile = BN images x BH rows x BW pixels (powers of two, product 128): the split with the fewest tiles.  A 9 x 16
+        // feature map (level 3 of 576 x 1024) as 8-row tiles wastes 7/16 of every second tile (round 1: 681 vs 1209 TFLOP/s
+        // for the same conv at 18 x 32); as {16 px, 1 row, 8 images} it wastes 12 %.
         p.BW = floor_pow2(a->W < 32 ? a->W : 32);
-        p.BH = BM / p.BW;
+        {
+            long long best = -1;
+            for (int bh = BM / p.BW; bh >= 1; bh >>= 1) {
+                const int bnn = BM / (p.BW * bh);
+                const long long tiles = static_cast<long long>((a->W + p.BW - 1) / p.BW) * ((a->H + bh - 1) / bh) *
+                                        ((a->n_img + bnn - 1) / bnn);
+                if (best < 0 || tiles < best) {
+                    best = tiles;
+                    p.BH = bh;
+                    p.BN = bnn;
+                }
+            }
+        }
+        p.n_img = a->n_img;
         p.tiles_x = (a->W + p.BW - 1) / p.BW;
         p.tiles_y = (a->H + p.BH - 1) / p.BH;
-        p.m_tiles = a->n_img * p.tiles_x * p.tiles_y;
+        p.m_tiles = ((a->n_img + p.BN - 1) / p.BN) * p.tiles_x * p.tiles_y;
+        p.sBH = (32 / p.BW) < p.BH ? (32 / p.BW) : p.BH;
+        if (p.sBH < 1) p.sBH = 1;
+        p.sBN = 32 / (p.BW * p.sBH);
+        if (p.sBN < 1) p.sBN = 1;
         p.kb_per_tap = a->C / BK;
         p.num_kb = p.ks * p.ks * p.kb_per_tap;
         p.kb_split = p.num_kb;
         uint64_t dims[4] = {(uint64_t)a->C, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
         uint64_t strides[3] = {(uint64_t)a->C * 2, (uint64_t)a->W * a->C * 2, (uint64_t)a->H * a->W * a->C * 2};
-        uint32_t box[4] = {BK, (uint32_t)p.BW, (uint32_t)p.BH, 1};
+        uint32_t box[4] = {BK, (uint32_t)p.BW, (uint32_t)p.BH, (uint32_t)p.BN};
         if ((rc = make_tmap_f16(&tmA, a->a, 4, dims, strides, box)) != MOFA_OK) return rc;
         tmA2 = tmA;
         if (tma_out) {
             uint64_t od[4] = {(uint64_t)n_out_cols, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
             uint64_t os[3] = {ldc_b, (uint64_t)a->W * ldc_b, (uint64_t)a->H * a->W * ldc_b};
-            uint32_t ob[4] = {64, (uint32_t)p.BW, (uint32_t)(32 / p.BW), 1};
+            uint32_t ob[4] = {64, (uint32_t)p.BW, (uint32_t)p.sBH, (uint32_t)p.sBN};
             if ((rc = make_tmap_f16(&tmOut, a->out, 4, od, os, ob)) != MOFA_OK) return rc;
         }
     } else if (a->mode == MOFA_A_TEMPORAL3) {
@@ -810,6 +936,13 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
     const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + kEpiWarps * kStagingBytes +
                               (2 * stages + 4) * 8 + 16 + 1024;
 
+    if (p.gn_stats) {
+        const long long rows_total = a->mode == MOFA_A_LINEAR ? a->M
+                                     : a->mode == MOFA_A_CONV3X3 ? static_cast<long long>(a->n_img) * a->H * a->W
+                                                                 : static_cast<long long>(a->B) * a->T * a->HW;
+        const long long n_stat = (rows_total + p.gn_rows_per_stat - 1) / p.gn_rows_per_stat;
+        cudaMemsetAsync(p.gn_stats, 0, sizeof(float) * 2 * p.gn_groups * n_stat, stream);
+    }
     const long long total = static_cast<long long>(p.m_tiles) * p.n_tiles;
     int grid = num_sms();
     if (a->max_ctas > 0 && a->max_ctas < grid) grid = a->max_ctas;

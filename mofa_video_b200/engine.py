@@ -306,19 +306,30 @@ class Net:
         return temb_all
 
     # ------------------------------------------------------------------ blocks
-    def resblock(self, r, x, x2, temb_all, hw, H, W):
+    def resblock2(self, r, x, x2, temb_all, hw, H, W, x_stats=None, want_stats=False):
+        """SpatioTemporalResBlock.  GroupNorm statistics travel with the data: every GroupNorm whose input is produced by
+        a GEMM of this function (norm2 <- conv1, temporal norm1 <- conv2, temporal norm2 <- temporal conv1) gets its
+        (sum, sum of squares) from that GEMM's epilogue and runs its apply pass only.  `x_stats`: statistics of `x` for
+        norm1 from the producer of x (previous resblock); `want_stats`: also accumulate the per-frame statistics of this
+        block's output for the GroupNorm that consumes it (next resblock / transformer).  Returns (out, stats or None)."""
         ops, B, T = self.ops, self.B, self.T
         rows = x.shape[0]
         n_img = rows // hw
         cin, cout = r["cin"], r["cout"]
+        fuse = cout % 64 == 0 and (cout // 32) % 2 == 0     # TMA-store epilogue with an even number of channels per group
         stats = self.new(n_img * 64, dtype=torch.float32)
         h = self.new(rows, cin)
-        ops.groupnorm(x, r["n1"][0], r["n1"][1], h, hw, r["eps"], True, stats, x2=x2)
+        if x_stats is not None and x2 is None:
+            ops.groupnorm(x, r["n1"][0], r["n1"][1], h, hw, r["eps"], True, x_stats, stats_ready=True)
+        else:
+            ops.groupnorm(x, r["n1"][0], r["n1"][1], h, hw, r["eps"], True, stats, x2=x2)
         h1 = self.new(rows, cout)
+        gn = dict(gn_stats=stats, gn_rows_per_stat=hw) if fuse else {}
         ops.gemm(ops.A_CONV3X3, h, r["c1"][0], h1, N=cout, n_img=n_img, H=H, W=W, C=cin, bias=r["c1"][1],
                  rowbias=None if r["temb_sp"] is None else temb_all[:, r["temb_sp"]:r["temb_sp"] + cout],
-                 rows_per_group=T * hw)
-        ops.groupnorm(h1, r["n2"][0], r["n2"][1], h1n := self.new(rows, cout), hw, r["eps"], True, stats)
+                 rows_per_group=T * hw, **gn)
+        ops.groupnorm(h1, r["n2"][0], r["n2"][1], h1n := self.new(rows, cout), hw, r["eps"], True, stats,
+                      stats_ready=fuse)
         if r["sc"] is not None:
             xs = self.new(rows, cout)
             if x2 is not None:
@@ -330,30 +341,43 @@ class Net:
             assert x2 is None
             xs = x
         hs = self.new(rows, cout)
-        ops.gemm(ops.A_CONV3X3, h1n, r["c2"][0], hs, N=cout, n_img=n_img, H=H, W=W, C=cout, bias=r["c2"][1], res1=xs)
+        gn = dict(gn_stats=stats, gn_rows_per_stat=T * hw) if fuse else {}
+        ops.gemm(ops.A_CONV3X3, h1n, r["c2"][0], hs, N=cout, n_img=n_img, H=H, W=W, C=cout, bias=r["c2"][1], res1=xs,
+                 **gn)
         # temporal resnet (GroupNorm statistics span all T frames of a batch item) + learned blend
         g = self.new(rows, cout)
-        ops.groupnorm(hs, r["tn1"][0], r["tn1"][1], g, T * hw, r["teps"], True, stats)
+        ops.groupnorm(hs, r["tn1"][0], r["tn1"][1], g, T * hw, r["teps"], True, stats, stats_ready=fuse)
         g1 = self.new(rows, cout)
         ops.gemm(ops.A_TEMPORAL3, g, r["tc1"][0], g1, N=cout, B=B, T=T, HW=hw, C=cout, bias=r["tc1"][1],
                  rowbias=None if r["temb_tp"] is None else temb_all[:, r["temb_tp"]:r["temb_tp"] + cout],
-                 rows_per_group=T * hw)
-        ops.groupnorm(g1, r["tn2"][0], r["tn2"][1], g, T * hw, r["teps"], True, stats)
+                 rows_per_group=T * hw, **gn)
+        ops.groupnorm(g1, r["tn2"][0], r["tn2"][1], g, T * hw, r["teps"], True, stats, stats_ready=fuse)
         out = self.new(rows, cout)
+        out_stats = None
+        gn = {}
+        if want_stats and fuse:
+            out_stats = self.new(n_img * 64, dtype=torch.float32)
+            gn = dict(gn_stats=out_stats, gn_rows_per_stat=hw)
         # alpha*hs + (1-alpha)*(hs + conv) = hs + (1-alpha)*conv
         ops.gemm(ops.A_TEMPORAL3, g, r["tc2"][0], out, N=cout, B=B, T=T, HW=hw, C=cout, bias=r["tc2"][1],
-                 alpha=1.0 - r["alpha"], res1=hs, beta1=1.0)
-        return out
+                 alpha=1.0 - r["alpha"], res1=hs, beta1=1.0, **gn)
+        return out, out_stats
 
-    def transformer(self, t, x, hw):
+    def resblock(self, r, x, x2, temb_all, hw, H, W):
+        return self.resblock2(r, x, x2, temb_all, hw, H, W)[0]
+
+    def transformer(self, t, x, hw, x_stats=None):
         ops, B, T = self.ops, self.B, self.T
         rows, C, heads = x.shape[0], t["C"], t["heads"]
         frames = rows // hw
         scale = 1.0 / math.sqrt(C // heads)
-        stats = self.new(frames * 64, dtype=torch.float32)
         lin = ops.linear
         hn = self.new(rows, C)
-        ops.groupnorm(x, t["norm"][0], t["norm"][1], hn, hw, 1e-6, False, stats)
+        if x_stats is not None:   # accumulated by the epilogue of the GEMM that produced x (resblock(want_stats=True))
+            ops.groupnorm(x, t["norm"][0], t["norm"][1], hn, hw, 1e-6, False, x_stats, stats_ready=True)
+        else:
+            stats = self.new(frames * 64, dtype=torch.float32)
+            ops.groupnorm(x, t["norm"][0], t["norm"][1], hn, hw, 1e-6, False, stats)
         h = self.new(rows, C)
         lin(hn, t["proj_in"][0], h, bias=t["proj_in"][1])
         # ---- spatial BasicTransformerBlock
@@ -414,10 +438,15 @@ class Net:
         return out, Ho, Wo
 
     def down_block(self, blk, x, temb_all, hw, H, W, skips, after_each=None):
+        st = None
         for j, r in enumerate(blk["res"]):
-            x = self.resblock(r, x, None, temb_all, hw, H, W)
+            last = j == len(blk["res"]) - 1
+            # the output's GroupNorm statistics ride along when the next op is a GroupNorm over the same tensor
+            x, st = self.resblock2(r, x, None, temb_all, hw, H, W, x_stats=st,
+                                   want_stats=bool(blk["attn"]) or not last)
             if blk["attn"]:
-                x = self.transformer(blk["attn"][j], x, hw)
+                x = self.transformer(blk["attn"][j], x, hw, x_stats=st)
+                st = None
             skips.append((x, hw, H, W))
         if blk["down"] is not None:
             w, b = blk["down"]
@@ -430,8 +459,8 @@ class Net:
         return x, hw, H, W
 
     def mid_block(self, m, x, temb_all, hw, H, W):
-        x = self.resblock(m["res"][0], x, None, temb_all, hw, H, W)
-        x = self.transformer(m["attn"][0], x, hw)
+        x, st = self.resblock2(m["res"][0], x, None, temb_all, hw, H, W, want_stats=True)
+        x = self.transformer(m["attn"][0], x, hw, x_stats=st)
         return self.resblock(m["res"][1], x, None, temb_all, hw, H, W)
 
     def _conv_in(self, x_in, n_img, H, W):
@@ -480,9 +509,11 @@ class Net:
             for j, r in enumerate(blk["res"]):
                 s, shw, sH, sW = skips.pop()
                 assert shw == hw
-                x = self.resblock(r, x, s, temb_all, hw, H, W)
                 if blk["attn"]:
-                    x = self.transformer(blk["attn"][j], x, hw)
+                    x, st = self.resblock2(r, x, s, temb_all, hw, H, W, want_stats=True)
+                    x = self.transformer(blk["attn"][j], x, hw, x_stats=st)
+                else:
+                    x = self.resblock(r, x, s, temb_all, hw, H, W)
             if blk["up"] is not None:
                 C = x.shape[1]
                 n_img = x.shape[0] // hw

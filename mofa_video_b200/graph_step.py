@@ -80,6 +80,7 @@ class StepRunner:
             with torch.cuda.graph(g):
                 self._body()
             self.kernels_per_step = ops.launch_count() - n0
+            ops.note_graph_replay(-self.kernels_per_step)   # the capture enqueued nothing: only replays execute kernels
             self.graph = g
         self.graph.replay()
         ops.note_graph_replay(self.kernels_per_step)

@@ -44,6 +44,8 @@ class GemmArgs(ctypes.Structure):
         ("res1", ctypes.c_void_p), ("ldr1", ctypes.c_int64), ("res2", ctypes.c_void_p), ("ldr2", ctypes.c_int64),
         ("alpha", ctypes.c_float), ("beta1", ctypes.c_float), ("beta2", ctypes.c_float),
         ("max_ctas", ctypes.c_int32), ("dilation", ctypes.c_int32), ("ksize", ctypes.c_int32),
+        ("gn_stats", ctypes.c_void_p), ("gn_rows_per_stat", ctypes.c_int64), ("gn_groups", ctypes.c_int32),
+        ("gn_cpg", ctypes.c_int32), ("gn_c_off", ctypes.c_int32), ("gn_pad", ctypes.c_int32),
     ]
 
 
@@ -202,8 +204,11 @@ def pick_bn(n, geglu=False):
 
 def gemm(mode, a, w, out, *, N, bn=None, act=ACT_NONE, a2=None, M=0, K=0, K1=0, lda=0, lda2=0, n_img=0, H=0, W=0,
          C=0, B=0, T=0, HW=0, ldc=None, bias=None, rowbias=None, rows_per_group=1, rowbias_mod=0, res1=None, res2=None,
-         alpha=1.0, beta1=1.0, beta2=1.0, max_ctas=0, dilation=1, ksize=3, c_off=0):
-    """c_off: first output column inside rows of width ldc (in-place channel concat; multiple of 8)."""
+         alpha=1.0, beta1=1.0, beta2=1.0, max_ctas=0, dilation=1, ksize=3, c_off=0, gn_stats=None,
+         gn_rows_per_stat=0, gn_groups=32, gn_cpg=0, gn_c_off=0):
+    """c_off: first output column inside rows of width ldc (in-place channel concat; multiple of 8).
+    gn_stats (fp32 [rows / gn_rows_per_stat, gn_groups, 2]): GroupNorm statistics of this output, accumulated by the
+    epilogue for the GroupNorm that consumes it (gn_cpg channels per group; default N_out / gn_groups)."""
     lib = load()
     _chk_h(a, a2, w, out, bias, res1, res2)
     if rowbias is not None:  # may be a column slice of a wider [groups, total] matrix
@@ -232,6 +237,13 @@ def gemm(mode, a, w, out, *, N, bn=None, act=ACT_NONE, a2=None, M=0, K=0, K1=0, 
     g.max_ctas = max_ctas
     g.dilation = dilation
     g.ksize = ksize
+    if gn_stats is not None:
+        assert gn_stats.dtype == torch.float32 and gn_stats.is_cuda and gn_rows_per_stat > 0
+        g.gn_stats, g.gn_rows_per_stat, g.gn_groups = gn_stats.data_ptr(), gn_rows_per_stat, gn_groups
+        g.gn_cpg = gn_cpg if gn_cpg else n_out // gn_groups
+        g.gn_c_off = gn_c_off
+    else:
+        g.gn_stats = None
     if _prof is not None:
         if mode == A_LINEAR:
             kind, work = "gemm_linear", 2.0 * M * N * K
@@ -282,14 +294,17 @@ def attn_temporal(qkv, out, B, T, HW, heads, scale):
     return out
 
 
-def groupnorm(x1, gamma, beta, out, rows_per_stat, eps, silu, stats, x2=None, groups=32):
+def groupnorm(x1, gamma, beta, out, rows_per_stat, eps, silu, stats, x2=None, groups=32, stats_ready=False):
+    """stats_ready: `stats` already holds (sum, sum of squares) per (statistic, group) -- accumulated by the producing
+    GEMM's epilogue (gemm(..., gn_stats=)) -- so only the apply pass runs."""
     _chk_h(x1, x2, gamma, beta, out)
     rows = x1.shape[0]
     C1 = x1.shape[1]
     C2 = x2.shape[1] if x2 is not None else 0
     assert stats.dtype == torch.float32 and stats.numel() >= (rows // rows_per_stat) * groups * 2
     _check(load().mofa_groupnorm(_p(x1), C1, _p(x2), C2, _p(gamma), _p(beta), _p(out), rows, rows_per_stat, groups,
-                                 eps, 1 if silu else 0, _p(stats), _stream()), "mofa_groupnorm")
+                                 eps, (1 if silu else 0) | (2 if stats_ready else 0), _p(stats), _stream()),
+           "mofa_groupnorm")
     return out
 
 

@@ -57,7 +57,8 @@ def _epilogue(acc, *, N, bn, act, bias, rowbias, rows_per_group, rowbias_mod, re
 
 def gemm(mode, a, w, out, *, N, bn=None, act=ACT_NONE, a2=None, M=0, K=0, K1=0, lda=0, lda2=0, n_img=0, H=0, W=0,
          C=0, B=0, T=0, HW=0, ldc=None, bias=None, rowbias=None, rows_per_group=1, rowbias_mod=0, res1=None, res2=None,
-         alpha=1.0, beta1=1.0, beta2=1.0, max_ctas=0, dilation=1, ksize=3, c_off=0):
+         alpha=1.0, beta1=1.0, beta2=1.0, max_ctas=0, dilation=1, ksize=3, c_off=0, gn_stats=None,
+         gn_rows_per_stat=0, gn_groups=32, gn_cpg=0, gn_c_off=0):
     if bn is None:
         bn = pick_bn(N, act == ACT_GEGLU)
     wf = w.float()
@@ -81,6 +82,16 @@ def gemm(mode, a, w, out, *, N, bn=None, act=ACT_NONE, a2=None, M=0, K=0, K1=0, 
     n_out = res.shape[1]
     ld = ldc if ldc is not None else n_out
     out.view(-1, ld)[: res.shape[0], c_off:c_off + n_out] = res
+    if gn_stats is not None:  # (sum, sum of squares) of the fp16 outputs per (statistic, consumer group)
+        cpg = gn_cpg if gn_cpg else n_out // gn_groups
+        rf = res.float()
+        n_stat = rf.shape[0] // gn_rows_per_stat
+        st = gn_stats.view(-1)[: n_stat * gn_groups * 2].view(n_stat, gn_groups, 2)
+        st.zero_()
+        grp = (gn_c_off + torch.arange(n_out, device=rf.device)) // cpg
+        r3 = rf.view(n_stat, gn_rows_per_stat, n_out)
+        st[:, :, 0].index_add_(1, grp, r3.sum(1))
+        st[:, :, 1].index_add_(1, grp, (r3 * r3).sum(1))
     return out
 
 
@@ -124,13 +135,20 @@ def attn_temporal(qkv, out, B, T, HW, heads, scale):
     return out
 
 
-def groupnorm(x1, gamma, beta, out, rows_per_stat, eps, silu, stats, x2=None, groups=32):
+def groupnorm(x1, gamma, beta, out, rows_per_stat, eps, silu, stats, x2=None, groups=32, stats_ready=False):
     x = x1.float() if x2 is None else torch.cat([x1.float(), x2.float()], dim=1)
     rows, C = x.shape
     n = rows // rows_per_stat
     xg = x.view(n, rows_per_stat, groups, C // groups)
-    mean = xg.mean(dim=(1, 3), keepdim=True)
-    var = xg.var(dim=(1, 3), unbiased=False, keepdim=True)
+    if stats_ready:   # statistics accumulated by the producing GEMM's epilogue (gemm(..., gn_stats=))
+        st = stats.view(-1)[: n * groups * 2].view(n, groups, 2)
+        cnt = float(rows_per_stat * (C // groups))
+        mean = (st[:, :, 0] / cnt).view(n, 1, groups, 1)
+        var = (st[:, :, 1] / cnt).view(n, 1, groups, 1) - mean * mean
+        var = var.clamp_min(0.0)
+    else:
+        mean = xg.mean(dim=(1, 3), keepdim=True)
+        var = xg.var(dim=(1, 3), unbiased=False, keepdim=True)
     y = ((xg - mean) * torch.rsqrt(var + eps)).view(rows, C) * gamma.float() + beta.float()
     if silu:
         y = F.silu(y)

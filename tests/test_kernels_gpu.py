@@ -139,6 +139,71 @@ def test_gemm_temporal3(B, T, HW, C, N):
     close(out, ref, 3e-2, 1e-2, f"temporal3 {B}x{T}x{HW}x{C}->{N}")
 
 
+@pytest.mark.parametrize("n_img,H,W,C,N", [
+    (50, 9, 16, 64, 128),    # level 3 of 576x1024: tiles of {16 px, 1 row, 8 images}; 50 images = 6 full groups + 2
+    (6, 8, 8, 64, 64),       # level 3 of 512x512: two whole images per tile
+    (5, 18, 32, 64, 192),    # level 2: {32 px, 2 rows, 2 images}, odd image count
+    (3, 5, 3, 64, 64),       # W not a power of two, everything ragged
+])
+def test_gemm_conv3x3_small_maps_multi_image_tiles(n_img, H, W, C, N):
+    lib = L()
+    x, w = rnd(n_img * H * W, C, scale=0.5), rnd(N, 9 * C, scale=0.03)
+    bias, rowbias, res = rnd(N), rnd(n_img, N), rnd(n_img * H * W, N)
+    out = torch.zeros(n_img * H * W, N, dtype=torch.half, device=DEV)
+    ref = torch.zeros_like(out)
+    kw = dict(N=N, n_img=n_img, H=H, W=W, C=C, bias=bias, rowbias=rowbias, rows_per_group=H * W, res1=res)
+    lib.gemm(lib.A_CONV3X3, x, w, out, **kw)
+    R.gemm(R.A_CONV3X3, x, w, ref, **kw)
+    torch.cuda.synchronize()
+    close(out, ref, 3e-2, 1e-2, f"conv3x3 small map {n_img}x{H}x{W}x{C}->{N}")
+
+
+@pytest.mark.parametrize("mode,shape", [
+    ("conv", (4, 16, 32, 64, 320, 16 * 32)),       # spatial statistics (one per image), N = 320: groups of 10
+    ("conv", (50, 9, 16, 64, 128, 9 * 16)),        # several images inside one warp's 32 rows
+    ("conv", (4, 12, 20, 64, 128, 2 * 12 * 20)),   # temporal statistics (2 frames per batch item), ragged tiles
+    ("temporal", (2, 5, 144, 64, 64, 5 * 144)),    # temporal conv -> temporal GroupNorm
+    ("temporal", (2, 3, 200, 128, 640, 200)),      # temporal conv -> per-frame GroupNorm (resblock output), cpg 20
+    ("linear", (700, 128, 192, 350)),              # linear, ragged M, statistic boundary inside a tile
+])
+def test_gemm_groupnorm_statistics_in_epilogue(mode, shape):
+    """gn_stats: (sum, sum of squares) of the fp16 outputs per (statistic, group), accumulated by the epilogue; then
+    mofa_groupnorm(stats_ready) == the two-pass GroupNorm."""
+    lib = L()
+    if mode == "conv":
+        n_img, H, W, C, N, rps = shape
+        rows = n_img * H * W
+        x, w = rnd(rows, C, scale=0.5), rnd(N, 9 * C, scale=0.03)
+        kw = dict(N=N, n_img=n_img, H=H, W=W, C=C, bias=rnd(N), res1=rnd(rows, N))
+        m = lib.A_CONV3X3
+    elif mode == "temporal":
+        B, T, HW, C, N, rps = shape
+        rows = B * T * HW
+        x, w = rnd(rows, C, scale=0.5), rnd(N, 3 * C, scale=0.05)
+        kw = dict(N=N, B=B, T=T, HW=HW, C=C, bias=rnd(N), res1=rnd(rows, N), alpha=0.4)
+        m = lib.A_TEMPORAL3
+    else:
+        rows, K, N, rps = shape
+        x, w = rnd(rows, K, scale=0.5), rnd(N, K, scale=0.05)
+        kw = dict(N=N, M=rows, K=K, lda=K, bias=rnd(N))
+        m = lib.A_LINEAR
+    n_stat = rows // rps
+    out = torch.zeros(rows, N, dtype=torch.half, device=DEV)
+    st = torch.full((n_stat * 64,), 123.0, device=DEV)          # must be zeroed by the call
+    lib.gemm(m, x, w, out, gn_stats=st, gn_rows_per_stat=rps, **kw)
+    torch.cuda.synchronize()
+    of = out.float().view(n_stat, rps, 32, N // 32)
+    want = torch.stack([of.sum(dim=(1, 3)), (of * of).sum(dim=(1, 3))], dim=-1)      # [n_stat, 32, 2]
+    got = st.view(n_stat, 32, 2)
+    close(got, want, 0.05, 2e-3, f"gn statistics {mode} {shape}")
+    gamma, beta = rnd(N), rnd(N)
+    y1, y2 = torch.empty_like(out), torch.empty_like(out)
+    lib.groupnorm(out, gamma, beta, y1, rps, 1e-5, True, st, stats_ready=True)
+    st2 = torch.empty(n_stat * 64, device=DEV)
+    lib.groupnorm(out, gamma, beta, y2, rps, 1e-5, True, st2)
+    close(y1, y2, 4e-3, 4e-3, f"groupnorm from epilogue statistics {mode} {shape}")
+
+
 # ------------------------------------------------------------------------------------------ attention
 @pytest.mark.parametrize("frames,Lq,heads", [(2, 128, 1), (3, 144, 2), (2, 576, 5), (1, 2304, 2), (2, 64, 1),
                                              (1, 9216, 1)])
