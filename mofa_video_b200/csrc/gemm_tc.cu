@@ -171,11 +171,18 @@ __device__ __noinline__ void epilogue_direct8(const GemmKernelParams& p, const f
     }
 }
 
-template <bool kGeglu>
+// kEpi selects the epilogue body so that the two production kernels stay small (the epilogue is unrolled 32 wide and was
+// fetch-limited: stall_no_instruction 0.45 per issue, profiles/r1_ncu_geglu320_v3.csv):
+//   0 plain (bias / row-group bias / alpha / residuals)   -- every conv and linear of the denoise step except GEGLU
+//   1 GEGLU                                               -- FeedForward first projections
+//   2 generic activations (SiLU, ReLU, sigmoid, GELU, quick-GELU, ReLU-after-residual): conditioning convs, CMP, VAE, CLIP
+// kStats (plain only): GroupNorm statistics of the output accumulated from the staging tile (mofa_gemm_args.gn_stats).
+template <int kEpi, bool kStats>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                const GemmKernelParams p) {
+    constexpr bool kGeglu = kEpi == 1;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024 B alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -287,10 +294,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t idesc = umma_idesc_f16(static_cast<uint32_t>(n_this), false);
             const uint32_t as = iter & 1u;
             const uint32_t aphase = (iter >> 1) & 1u;
-            // kGeglu: the epilogue warps pre-load the bias into the accumulator (tcgen05.st) before they release a stage, so
-            // the k-th use of a stage waits for the k-th release (parity k & 1) and every MMA accumulates; otherwise the
-            // first use of a stage finds it free (previous-phase parity) and the first MMA overwrites.
-            mbar_wait(&tempty_bar[as], kGeglu ? aphase : (aphase ^ 1));
+            mbar_wait(&tempty_bar[as], aphase ^ 1);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + as * acc_stride;
             for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -302,7 +306,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
                     // +32 B per K=16 step inside the 128 B swizzle atom: +2 in 16 B address units
-                    umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kGeglu || (kb | k) != 0) ? 1u : 0u);
+                    umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                 }
                 umma_commit(&empty_bar[stage]);
                 if (++stage == p.stages) {
@@ -322,47 +326,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int half_bn = p.bn >> 1;
         uint32_t iter = 0;
         int mt, nt;
-        // kGeglu: accumulator columns this warp owns <- bias of N tile `nt_pre` (value half | gate half of the packed rows),
-        // so the epilogue has no bias loads / converts / adds (it is issue-bound: ~3450 issue clocks per 128 x 256 tile
-        // against 2560 clocks of MMA at K = 320, profiles/r1_ncu_geglu320_v3.csv)
-        auto prefill_bias = [&](uint32_t as_pre, int nt_pre) {
-            const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as_pre * acc_stride;
-            const int n_chunks_pre = (half_bn + 63) >> 6;
-#pragma unroll 1
-            for (int c = half; c < n_chunks_pre; c += 2) {
-#pragma unroll 1
-                for (int part = 0; part < 4; ++part) {  // (value | gate) x (two 32-column halves of the 64-column chunk)
-                    const int col = (part >> 1) * half_bn + c * 64 + (part & 1) * 32;
-                    uint32_t r[32];
-                    if (p.bias && (c * 64 + (part & 1) * 32) < half_bn) {
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            H8 b;
-                            b.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nt_pre * p.bn + col + g * 8));
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) r[g * 8 + j] = __float_as_uint(__half2float(b.h[j]));
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) r[j] = 0u;
-                    }
-                    if ((c * 64 + (part & 1) * 32) < half_bn) tmem_st_32x32(tbase + col, r);
-                }
-            }
-            tmem_st_wait();
-        };
-        if constexpr (kGeglu) {
-            for (int pre = 0; pre < 2; ++pre) {
-                int mt_pre, nt_pre;
-                if (tile_at(pre, mt_pre, nt_pre)) prefill_bias(static_cast<uint32_t>(pre), nt_pre);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&tempty_bar[0]);
-                mbar_arrive(&tempty_bar[1]);
-            }
-        }
         for (; tile_at(static_cast<int>(iter), mt, nt); ++iter) {
             const TileCoord tc = tile_coord(p, mt);
             const uint32_t as = iter & 1u;
@@ -446,11 +409,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if constexpr (kGeglu) {
                                 uint32_t ag[32];
                                 tmem_ld_32x32(taddr + half_bn + col0, ag);
-                                tmem_ld_wait();
-                                // the bias is already inside the accumulator (prefill_bias)
+                                // bias requested while the two TMEM loads are in flight (it tested slower to pre-load the
+                                // bias into the accumulator with tcgen05.st before the MMAs: 525 vs 678 TFLOP/s at K = 320,
+                                // profiles/r2_step_detail_a.txt -- the pre-load sits on the epilogue's critical path)
+                                uint4 bvv[4], bgv[4];
 #pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    v[j] = __uint_as_float(acc[j]) * gelu_erf_relu_form(__uint_as_float(ag[j]));
+                                for (int g = 0; g < 4; ++g) {
+                                    const int nb = nt * p.bn + col0 + g * 8;
+                                    bvv[g] = make_uint4(0, 0, 0, 0);
+                                    bgv[g] = make_uint4(0, 0, 0, 0);
+                                    if (p.bias) {
+                                        bvv[g] = __ldg(reinterpret_cast<const uint4*>(p.bias + nb));
+                                        bgv[g] = __ldg(reinterpret_cast<const uint4*>(p.bias + nb + half_bn));
+                                    }
+                                }
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) {
+                                    H8 bv, bg;
+                                    bv.u = bvv[g];
+                                    bg.u = bgv[g];
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        const float val = __uint_as_float(acc[g * 8 + j]) + __half2float(bv.h[j]);
+                                        const float gate = __uint_as_float(ag[g * 8 + j]) + __half2float(bg.h[j]);
+                                        v[g * 8 + j] = val * gelu_erf_relu_form(gate);
+                                    }
+                                }
                             } else {
                                 uint4 bvv[4];  // bias: requested while the TMEM load is in flight
                                 if (p.bias) {
@@ -485,6 +470,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                         }
                                     }
                                 }
+                                if constexpr (kEpi == 2) {
                                 if (p.act == 1) {
 #pragma unroll
                                     for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
@@ -500,6 +486,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 } else if (p.act == 7) {
 #pragma unroll
                                     for (int j = 0; j < 32; ++j) v[j] = v[j] * sigmoid_f(1.702f * v[j]);
+                                }
                                 }
                             }
                         }
@@ -525,9 +512,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 for (int j = 0; j < 8; ++j) v[g * 8 + j] = fmaf(p.beta2, __half2float(a.h[j]), v[g * 8 + j]);
                             }
                         }
-                        if (p.act == 5) {  // ReLU after the residual add (ResNet bottleneck)
+                        if constexpr (kEpi == 2) {
+                            if (p.act == 5) {  // ReLU after the residual add (ResNet bottleneck)
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                            }
                         }
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
@@ -540,49 +529,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (p.gn_stats) {
+                    if constexpr (kStats) {
                         // GroupNorm statistics of what was just staged (the fp16-rounded outputs the consumer will read):
                         // lane l owns the column pair (2l, 2l+1) of this 64-column chunk and walks the warp's 32 rows of
                         // the swizzled staging tile (one 128-byte row per step: conflict-free), fp32 sums; a group never
-                        // splits a pair (channels per group is even).  Rows past the tensor and statistic boundaries
-                        // inside the 32 rows (several small images per tile) come from two ballots.
+                        // splits a pair (channels per group is even).  Common case: all 32 rows valid and inside one
+                        // statistic -> a rolled 32-step loop and two atomics per lane; otherwise (ragged tiles, several
+                        // small images per warp) a segment loop driven by two ballots.
                         const long long st = valid ? row / p.gn_rows_per_stat : -1;
                         const long long st_prev = __shfl_up_sync(0xffffffffu, st, 1);
                         const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-                        const uint32_t bmask = __ballot_sync(0xffffffffu, lane > 0 && valid && st != st_prev) & vmask;
+                        const uint32_t bmask = __ballot_sync(0xffffffffu, lane > 0 && valid && st != st_prev);
                         const int colp = nt * out_cols_tile + c * 64 + 2 * lane;     // global output column of the pair
                         const bool col_ok = colp < p.N_out;
-                        const int grp = (p.gn_c_off + colp) / p.gn_cpg;
+                        float* gdst = p.gn_stats + ((p.gn_c_off + colp) / p.gn_cpg) * 2;
+                        const long long gstride = 2LL * p.gn_groups;
+                        const uint32_t lane_base = smem_u32(stg) + ((lane & 3) << 2);
+                        const uint32_t chunk = lane >> 2;
                         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-                        int seg_row = -1;                                            // first row of the running segment
-                        const uint8_t* lane_base = stg + ((lane & 3) << 2);
-                        auto flush = [&](int sr) {
-                            const long long st_seg = __shfl_sync(0xffffffffu, st, sr);
-                            if (col_ok) {
-                                float* dst = p.gn_stats + (st_seg * p.gn_groups + grp) * 2;
-                                atomicAdd(dst, s0 + s1);
-                                atomicAdd(dst + 1, q0 + q1);
-                            }
-                            s0 = s1 = q0 = q1 = 0.f;
-                        };
-#pragma unroll
+                        int seg_row = -1;
+#pragma unroll 4
                         for (int rr = 0; rr < 32; ++rr) {
                             if (!((vmask >> rr) & 1u)) continue;                      // warp-uniform
-                            if (seg_row < 0) {
-                                seg_row = rr;
-                            } else if ((bmask >> rr) & 1u) {                          // statistic index changes here
-                                flush(seg_row);
+                            if (seg_row >= 0 && ((bmask >> rr) & 1u)) {               // statistic index changes here
+                                const long long st_seg = __shfl_sync(0xffffffffu, st, seg_row);
+                                if (col_ok) {
+                                    atomicAdd(gdst + st_seg * gstride, s0 + s1);
+                                    atomicAdd(gdst + st_seg * gstride + 1, q0 + q1);
+                                }
+                                s0 = s1 = q0 = q1 = 0.f;
                                 seg_row = rr;
                             }
-                            const __half2 hv = *reinterpret_cast<const __half2*>(
-                                lane_base + rr * 128 + ((((lane >> 2) ^ (rr & 7))) << 4));
-                            const float2 f = __half22float2(hv);
+                            if (seg_row < 0) seg_row = rr;
+                            uint32_t hv;
+                            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(hv)
+                                         : "r"(lane_base + rr * 128 + ((chunk ^ (rr & 7)) << 4)));
+                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hv));
                             s0 += f.x;
                             s1 += f.y;
                             q0 = fmaf(f.x, f.x, q0);
                             q1 = fmaf(f.y, f.y, q1);
                         }
-                        if (seg_row >= 0) flush(seg_row);
+                        if (seg_row >= 0) {
+                            const long long st_seg = __shfl_sync(0xffffffffu, st, seg_row);
+                            if (col_ok) {
+                                atomicAdd(gdst + st_seg * gstride, s0 + s1);
+                                atomicAdd(gdst + st_seg * gstride + 1, q0 + q1);
+                            }
+                        }
                     }
                     if (lane == 0) {
                         const int n0 = nt * out_cols_tile + c * 64;
@@ -621,10 +615,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
-            }
-            if constexpr (kGeglu) {  // bias of the tile that will use this accumulator stage next
-                int mt_nx, nt_nx;
-                if (tile_at(static_cast<int>(iter) + 2, mt_nx, nt_nx)) prefill_bias(as, nt_nx);
             }
             tc_fence_before();
             __syncwarp();
@@ -948,21 +938,25 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
     if (a->max_ctas > 0 && a->max_ctas < grid) grid = a->max_ctas;
     if (total < grid) grid = static_cast<int>(total);
 
+    using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmKernelParams);
+    static const Kern kernels[4] = {gemm_tc_kernel<0, false>, gemm_tc_kernel<0, true>, gemm_tc_kernel<1, false>,
+                                    gemm_tc_kernel<2, false>};
     static bool configured = false;
     if (!configured) {
-        cudaError_t e1 = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              227 * 1024);
-        cudaError_t e2 = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              227 * 1024);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) {
-            set_last_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-            return MOFA_ERR_CUDA;
+        for (Kern k : kernels) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) {
+                set_last_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+                return MOFA_ERR_CUDA;
+            }
         }
         configured = true;
     }
-    if (geglu)
-        gemm_tc_kernel<true><<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, tmOut, p);
-    else
-        gemm_tc_kernel<false><<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, tmOut, p);
+    if (p.gn_stats && a->act != 0) {
+        set_last_error("mofa_gemm: gn_stats is implemented for the plain epilogue (act 0), got act %d", a->act);
+        return MOFA_ERR_ARG;
+    }
+    const Kern kern = geglu ? kernels[2] : (a->act != 0 ? kernels[3] : (p.gn_stats ? kernels[1] : kernels[0]));
+    kern<<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, tmOut, p);
     return check_launch("mofa_gemm");
 }
