@@ -35,18 +35,32 @@ def unique_views(views):
     return [(v, m) for v, m in uniq]
 
 
+def views_for_rank(n_views, world, rank):
+    """Window k of a long video -> rank k mod world (the windows of one step are independent)."""
+    return list(range(rank, n_views, world))
+
+
 def denoise_windowed(ops, unet_net, ad_net, view_states, lat, il, sig, tsteps, h, w, T, g_min, g_max, scale,
-                     on_step=None):
+                     on_step=None, shard=None):
     """The loop of svdxt_pipeline_ctrlnet_loop.py:445-511 on channels-last fp16 buffers.
-    view_states: [((ts, te), multiplicity, (warped, ldmk))] -- cached conditioning of every distinct view;
-    lat fp16 [F, 4, hw]; il fp16 [2, 4, hw] (image latents are the same for every frame).  Returns the final lat."""
+    view_states: [((ts, te), multiplicity, (warped, ldmk))] -- cached conditioning of every distinct view (entries this
+    rank does not own may be None);  lat fp16 [F, 4, hw]; il fp16 [2, 4, hw] (image latents are the same for every frame).
+    shard = (world, rank): the views of every step are split over the ranks (view k -> rank k mod world) and the
+    per-frame (value, count) sums meet in ONE all-reduce per step -- the only exchange of the path that is not a final
+    gather ([F, 5, hw] fp32: 1.6 MB at 512x512x37 frames); every rank then holds the same averaged latents.
+    Returns the final lat."""
+    import torch.distributed as dist
     F_, _, hw = lat.shape
     dev = lat.device
+    world, rank = shard if shard is not None else (1, 0)
     next_in = torch.empty(2 * T * hw, 8, dtype=torch.float16, device=dev)
     for i in range(len(tsteps)):
-        value = torch.zeros(F_, 4, hw, dtype=torch.float32, device=dev)
-        count = torch.zeros(F_, 1, 1, dtype=torch.float32, device=dev)
-        for k, ((ts, te), mult, (warped, ldm)) in enumerate(view_states):
+        acc = torch.zeros(F_, 5, hw, dtype=torch.float32, device=dev)      # channels 0-3: value, channel 4: count
+        value, count = acc[:, :4], acc[:, 4:5, :1]
+        for k, state in enumerate(view_states):
+            if k % world != rank:
+                continue
+            (ts, te), mult, (warped, ldm) = state
             lt = lat[[0] + list(range(ts, te))].contiguous()             # [T, 4, hw] window of the latents
             ad_net.warped, ad_net.ldmk = warped, ldm
             ops.cfg_euler_step(None, lt, il, next_in, T, hw, g_min, g_max, 0.0, sig[i])
@@ -59,6 +73,8 @@ def denoise_windowed(ops, unet_net, ad_net, view_states, lat, il, sig, tsteps, h
             else:
                 value[ts:te] += mult * lt[1:].float()
                 count[ts:te] += mult
+        if world > 1:
+            dist.all_reduce(acc)                                           # NCCL on device tensors, gloo on CPU tensors
         lat = torch.where(count > 0, value / count.clamp(min=1), value).to(torch.float16)
         if on_step is not None:
             lat = on_step(i, lat)
@@ -75,7 +91,11 @@ class FlowControlNetPipeline(_TrajPipeline):
                  output_type: Optional[str] = "pil",
                  callback_on_step_end: Optional[Callable[[int, int, Dict], None]] = None,
                  callback_on_step_end_tensor_inputs: List[str] = ["latents"], return_dict: bool = True,
-                 controlnet_cond_scale=1.0, batch_size=1, window_size=25, stride=12):
+                 controlnet_cond_scale=1.0, batch_size=1, window_size=25, stride=12, shard_windows=False):
+        """shard_windows (engine extension, default off = every process renders its own clip): when torch.distributed is
+        initialised, ONE long clip is rendered by all ranks together -- the temporal windows of each denoise step are
+        split over the ranks and their latents averaged with one all-reduce per step (all ranks must pass the same
+        inputs and seeds; all return the same frames)."""
         ops = self._ops
         num_frames = num_frames if num_frames is not None else self.unet.config.num_frames
         decode_chunk_size = decode_chunk_size if decode_chunk_size is not None else num_frames
@@ -95,8 +115,15 @@ class FlowControlNetPipeline(_TrajPipeline):
         unet_net, ad = self.unet.net, self.controlnet
         unet_net.prepare_clip(image_embeddings, added_time_ids)
         ad.net.prepare_clip(image_embeddings, added_time_ids)
+        import torch.distributed as dist
+        shard = None
+        if shard_windows and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            shard = (dist.get_world_size(), dist.get_rank())
         states = []
-        for (ts, te), mult in unique_views(window_views(num_frames, window_size, stride)):
+        for k, ((ts, te), mult) in enumerate(unique_views(window_views(num_frames, window_size, stride))):
+            if shard is not None and k % shard[0] != shard[1]:
+                states.append(None)            # another rank's window: no conditioning needed here
+                continue
             # loop-invariant conditioning of every distinct view
             fl = flow[:, (ts - 1):(te - 1)]
             lm = torch.cat([ldmk[:, 0:1], ldmk[:, ts:te]], dim=1)
@@ -117,7 +144,7 @@ class FlowControlNetPipeline(_TrajPipeline):
             return cur_lat if new is None else new.reshape(num_frames, 4, hw).to(torch.float16).contiguous()
 
         lat = denoise_windowed(ops, unet_net, ad.net, states, lat, il, sig, tsteps, h, w, T, min_guidance_scale,
-                               max_guidance_scale, controlnet_cond_scale, on_step)
+                               max_guidance_scale, controlnet_cond_scale, on_step, shard=shard)
         latents = lat.reshape(1, num_frames, 4, h, w)
         frames = self._decode_output(latents, num_frames, decode_chunk_size, output_type)
         if not return_dict:
