@@ -189,6 +189,51 @@ class Net:
         self.temb.finish(pk)
         self.p = p
 
+    # ------------------------------------------------------------------ packed-weight cache
+    _TRANSIENT = ("ops", "pk_bn", "device", "_pbufs", "warped", "cond_feats", "xvec", "aug_emb", "ldmk", "B")
+
+    def packed_state(self):
+        """Everything __init__ computed from the checkpoint (kernel-native operands, on the CPU) -- what a process
+        needs to skip the repack: `Net.from_packed(state, ops, device)`."""
+        def cpu(v):
+            if isinstance(v, torch.Tensor):
+                return v.detach().cpu()
+            if isinstance(v, dict):
+                return {k: cpu(x) for k, x in v.items()}
+            if isinstance(v, (list, tuple)):
+                return type(v)(cpu(x) for x in v)
+            if isinstance(v, _TembBank):
+                b = _TembBank()
+                b.__dict__.update({k: cpu(x) for k, x in v.__dict__.items()})
+                return b
+            return v
+        return {"class": type(self).__name__,
+                "attrs": {k: cpu(v) for k, v in self.__dict__.items() if k not in self._TRANSIENT}}
+
+    @classmethod
+    def from_packed(cls, state, ops, device):
+        if state["class"] != cls.__name__:
+            raise ValueError(f"packed weights of {state['class']} offered to {cls.__name__}")
+        dev = torch.device(device)
+
+        def put(v):
+            if isinstance(v, torch.Tensor):
+                return v.to(dev)
+            if isinstance(v, dict):
+                return {k: put(x) for k, x in v.items()}
+            if isinstance(v, (list, tuple)):
+                return type(v)(put(x) for x in v)
+            if isinstance(v, _TembBank):
+                v.__dict__.update({k: put(x) for k, x in v.__dict__.items()})
+                return v
+            return v
+        net = cls.__new__(cls)
+        net.__dict__.update({k: put(v) for k, v in state["attrs"].items()})
+        net.ops, net.device, net.pk_bn = ops, dev, ops.pick_bn
+        if hasattr(net, "occ") or "ldmk_convs" in net.p:
+            net.ldmk = None
+        return net
+
     # ------------------------------------------------------------------ packing of composite blocks
     def _pack_im2col_conv(self, pk, name, stride):
         w = pk.get(name + ".weight")

@@ -29,6 +29,7 @@ DEFAULT_CONFIG = dict(
 # (no GPU in the builder container) switch both through `default_backend(...)` so that UNMODIFIED reference code --
 # e.g. T/run_gradio.py:init_models, which never passes ops= / device= -- can be executed against these classes.
 _BACKEND = {"ops": None, "device": "cuda"}
+PACK_FORMAT = "mofa-b200-pack-v2"   # bump when engine.Net's packed layout changes (invalidates pack caches)
 
 
 class default_backend:
@@ -113,9 +114,55 @@ class EngineModel:
     # -- construction --------------------------------------------------------------------------
     @classmethod
     def from_pretrained(cls, path, subfolder=None, variant=None, low_cpu_mem_usage=True, torch_dtype=None,
-                        device=None, **_ignored):
+                        device=None, pack_cache=None, **_ignored):
+        """Reads config.json + diffusion_pytorch_model[.variant].safetensors (the reference's call, T/run_gradio.py:
+        103-110).  `pack_cache` (or $MOFA_B200_PACK_CACHE): a directory where the kernel-native repack of the checkpoint
+        (fused q|k|v, interleaved GEGLU rows, [Cout, ky*kx*cin] conv operands, folded mix factors ...) is kept, keyed by
+        the checkpoint file's identity; later processes -- e.g. the 8 ranks of a node -- load that instead of
+        re-deriving 4.4 GB of operands."""
+        cache_dir = pack_cache or os.environ.get("MOFA_B200_PACK_CACHE")
+        if not cache_dir:
+            cfg, sd = read_checkpoint(path, subfolder, variant)
+            return cls(sd, cfg, device=device)
+        import hashlib
+        d = os.path.join(path, subfolder) if subfolder else path
+        ident = [cls.__module__, cls.__name__, PACK_FORMAT]
+        for n in sorted(os.listdir(d)):
+            if n == "config.json" or n.endswith(".safetensors"):
+                st = os.stat(os.path.join(d, n))
+                ident.append((os.path.abspath(os.path.join(d, n)), st.st_size, st.st_mtime_ns))
+        ident.append(variant)
+        fn = os.path.join(cache_dir, hashlib.sha1(repr(ident).encode()).hexdigest() + ".pt")
+        if os.path.exists(fn):
+            blob = torch.load(fn, weights_only=False)
+            return cls._from_packed(blob, device=device)
         cfg, sd = read_checkpoint(path, subfolder, variant)
-        return cls(sd, cfg, device=device)
+        model = cls(sd, cfg, device=device)
+        os.makedirs(cache_dir, exist_ok=True)
+        tmp = fn + f".tmp{os.getpid()}"
+        torch.save({"config": model._cfg, "net": model.net.packed_state(),
+                    "add_in_features": model.add_embedding.linear_1.in_features}, tmp)
+        os.replace(tmp, fn)        # atomic: concurrent ranks either see the whole file or none
+        return model
+
+    @classmethod
+    def _from_packed(cls, blob, device=None, ops=None):
+        self = cls.__new__(cls)
+        self.config = _Config(**blob["config"])
+        self._cfg = blob["config"]
+        self._ops, self._device, _ = resolve_backend(ops, device)
+        self._sd = None
+        net_cls = type(self)._net_class()
+        self.net = net_cls.from_packed(blob["net"], self._ops, self._device)
+        self.add_embedding = SimpleNamespace(linear_1=SimpleNamespace(in_features=int(blob["add_in_features"])))
+        self._clip_key = None
+        self._cond_key = None
+        self._masks = None
+        return self
+
+    @classmethod
+    def _net_class(cls):
+        return engine.Net
 
     @classmethod
     def from_state_dict(cls, state_dict, config=None, device=None, ops=None):
@@ -123,6 +170,9 @@ class EngineModel:
 
     def state_dict(self):
         """The reference-layout tensors this model was built from (not copies)."""
+        if self._sd is None:
+            raise RuntimeError("this model was restored from the packed-weight cache: the reference-layout state dict "
+                               "is not in memory (load the checkpoint without pack_cache to get it)")
         return self._sd
 
     # -- nn.Module look-alikes the reference scripts call ---------------------------------------

@@ -33,6 +33,10 @@ class FlowControlNet(EngineModel):
     def _make_net(self, state_dict, cfg):
         return LdmkAdapterNet(state_dict, cfg, self._ops, self._device)
 
+    @classmethod
+    def _net_class(cls):
+        return LdmkAdapterNet
+
     @staticmethod
     def _fresh_state_dict(cfg):
         """from_unet (K/models/controlnet_sdv.py:572-628): landmark embedding / occlusion nets fresh, zero_module convs zero."""
