@@ -37,6 +37,8 @@ constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kABytes = BM * BK * 2;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kStagingBytes = 4096;  // 32 rows x 128 B per epilogue warp
+constexpr int kGnSlots = 4;               // statistics (frames / batch items) one M tile may span in shared memory
+constexpr int kGnGroups = 32;             // groups one N tile may span in shared memory
 
 struct GemmKernelParams {
     int mode, act;
@@ -196,9 +198,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tfull_bar = bars + 2 * p.stages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    // kStats: per-CTA GroupNorm partial sums [kGnSlots statistics][kGnGroups groups][sum, sum of squares] of the tile being
+    // drained; shared-memory atomics per chunk, ONE flush of global atomics per tile.  (Global atomics per chunk -- 4.6 M per
+    // level-0 launch onto 3200 addresses -- doubled the conv time: profiles/r2_step_detail_b_gnstats_global_atomics.txt.)
+    float* s_gn = reinterpret_cast<float*>(tmem_ptr_smem + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if constexpr (kStats) {
+        for (int i = threadIdx.x; i < kGnSlots * kGnGroups * 2; i += blockDim.x) s_gn[i] = 0.f;
+    }
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
@@ -354,6 +363,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int out_cols_tile = kGeglu ? half_bn : p.bn;          // output columns per full N tile
             int out_cols = p.N_out - nt * out_cols_tile;                // ... of this tile
             out_cols = out_cols > out_cols_tile ? out_cols_tile : out_cols;
+
+            // kStats: statistic indices this tile touches (rows are ordered, so [first valid row, last valid row] bounds them)
+            long long st_first = 0;
+            int gn_g_first = 0;
+            bool gn_smem = false;
+            if constexpr (kStats) {
+                long long r_first, r_last;
+                if (p.mode == MOFA_A_LINEAR) {
+                    r_first = tc.m0;
+                    r_last = tc.m0 + BM - 1 < p.M - 1 ? tc.m0 + BM - 1 : p.M - 1;
+                } else if (p.mode == MOFA_A_CONV3X3) {
+                    r_first = (static_cast<long long>(tc.n_img) * p.H + tc.y0) * p.W + tc.x0;
+                    const int nl = tc.n_img + p.BN - 1 < p.n_img - 1 ? tc.n_img + p.BN - 1 : p.n_img - 1;
+                    const int yl = tc.y0 + p.BH - 1 < p.H - 1 ? tc.y0 + p.BH - 1 : p.H - 1;
+                    const int xl = tc.x0 + p.BW - 1 < p.W - 1 ? tc.x0 + p.BW - 1 : p.W - 1;
+                    r_last = (static_cast<long long>(nl) * p.H + yl) * p.W + xl;
+                } else {
+                    r_first = static_cast<long long>(tc.frame) * p.HW + tc.p0;
+                    r_last = static_cast<long long>(tc.frame) * p.HW + (tc.p0 + BM - 1 < p.HW - 1 ? tc.p0 + BM - 1 : p.HW - 1);
+                }
+                st_first = r_first / p.gn_rows_per_stat;
+                gn_smem = (r_last / p.gn_rows_per_stat - st_first) < kGnSlots;
+                gn_g_first = (p.gn_c_off + nt * out_cols_tile) / p.gn_cpg;
+            }
 
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
@@ -542,8 +575,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint32_t bmask = __ballot_sync(0xffffffffu, lane > 0 && valid && st != st_prev);
                         const int colp = nt * out_cols_tile + c * 64 + 2 * lane;     // global output column of the pair
                         const bool col_ok = colp < p.N_out;
-                        float* gdst = p.gn_stats + ((p.gn_c_off + colp) / p.gn_cpg) * 2;
+                        const int grp = (p.gn_c_off + colp) / p.gn_cpg;
+                        float* gdst = p.gn_stats + grp * 2;
                         const long long gstride = 2LL * p.gn_groups;
+                        const int g_loc = grp - gn_g_first;
+                        const bool to_smem = gn_smem && g_loc < kGnGroups;           // else: straight to global memory
+                        auto add_stat = [&](long long st_seg) {
+                            if (!col_ok) return;
+                            if (to_smem) {
+                                float* d = s_gn + (static_cast<int>(st_seg - st_first) * kGnGroups + g_loc) * 2;
+                                atomicAdd(d, s0 + s1);
+                                atomicAdd(d + 1, q0 + q1);
+                            } else {
+                                atomicAdd(gdst + st_seg * gstride, s0 + s1);
+                                atomicAdd(gdst + st_seg * gstride + 1, q0 + q1);
+                            }
+                        };
                         const uint32_t lane_base = smem_u32(stg) + ((lane & 3) << 2);
                         const uint32_t chunk = lane >> 2;
                         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
@@ -552,11 +599,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int rr = 0; rr < 32; ++rr) {
                             if (!((vmask >> rr) & 1u)) continue;                      // warp-uniform
                             if (seg_row >= 0 && ((bmask >> rr) & 1u)) {               // statistic index changes here
-                                const long long st_seg = __shfl_sync(0xffffffffu, st, seg_row);
-                                if (col_ok) {
-                                    atomicAdd(gdst + st_seg * gstride, s0 + s1);
-                                    atomicAdd(gdst + st_seg * gstride + 1, q0 + q1);
-                                }
+                                add_stat(__shfl_sync(0xffffffffu, st, seg_row));
                                 s0 = s1 = q0 = q1 = 0.f;
                                 seg_row = rr;
                             }
@@ -570,13 +613,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             q0 = fmaf(f.x, f.x, q0);
                             q1 = fmaf(f.y, f.y, q1);
                         }
-                        if (seg_row >= 0) {
-                            const long long st_seg = __shfl_sync(0xffffffffu, st, seg_row);
-                            if (col_ok) {
-                                atomicAdd(gdst + st_seg * gstride, s0 + s1);
-                                atomicAdd(gdst + st_seg * gstride + 1, q0 + q1);
-                            }
-                        }
+                        if (seg_row >= 0) add_stat(__shfl_sync(0xffffffffu, st, seg_row));
                     }
                     if (lane == 0) {
                         const int n0 = nt * out_cols_tile + c * 64;
@@ -619,6 +656,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if constexpr (kStats) {
+                if (gn_smem) {  // tile-uniform: the 8 epilogue warps meet, warp 2 moves the tile's partial sums to global memory
+                    asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+                    if (e == 0) {
+                        for (int i = lane; i < kGnSlots * kGnGroups; i += 32) {
+                            const float a = s_gn[2 * i], b = s_gn[2 * i + 1];
+                            if (a != 0.f || b != 0.f) {
+                                const int g = gn_g_first + (i % kGnGroups);
+                                float* d = p.gn_stats + ((st_first + i / kGnGroups) * p.gn_groups + g) * 2;
+                                atomicAdd(d, a);
+                                atomicAdd(d + 1, b);
+                                s_gn[2 * i] = 0.f;
+                                s_gn[2 * i + 1] = 0.f;
+                            }
+                        }
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+                }
+            }
         }
         if (lane == 0) tma_store_wait_all<0>();  // smem must outlive the last bulk store
     }
@@ -924,7 +980,7 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
     if (stages < 2) stages = 2;
     p.stages = stages;
     const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + kEpiWarps * kStagingBytes +
-                              (2 * stages + 4) * 8 + 16 + 1024;
+                              (2 * stages + 4) * 8 + 16 + 1024 + (p.gn_stats ? kGnSlots * kGnGroups * 8 + 16 : 0);
 
     if (p.gn_stats) {
         const long long rows_total = a->mode == MOFA_A_LINEAR ? a->M
