@@ -180,7 +180,7 @@ __device__ __noinline__ void epilogue_direct8(const GemmKernelParams& p, const f
 //   2 generic activations (SiLU, ReLU, sigmoid, GELU, quick-GELU, ReLU-after-residual): conditioning convs, CMP, VAE, CLIP
 // kStats (plain only): GroupNorm statistics of the output accumulated from the staging tile (mofa_gemm_args.gn_stats).
 template <int kEpi, bool kStats>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __maxnreg__(200)  // 320 threads x 200 registers = 64000 of 65536: one CTA per SM (the shared memory says so anyway)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                const GemmKernelParams p) {
@@ -366,7 +366,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
             // kStats: statistic indices this tile touches (rows are ordered, so [first valid row, last valid row] bounds them)
             long long st_first = 0;
-            int gn_g_first = 0;
+            int gn_g_first = 0, gn_st = -1;
+            uint32_t gn_vmask = 0, gn_bmask = 0;
             bool gn_smem = false;
             if constexpr (kStats) {
                 long long r_first, r_last;
@@ -386,7 +387,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 st_first = r_first / p.gn_rows_per_stat;
                 gn_smem = (r_last / p.gn_rows_per_stat - st_first) < kGnSlots;
                 gn_g_first = (p.gn_c_off + nt * out_cols_tile) / p.gn_cpg;
+                // this thread's row: statistic index relative to the tile's first, validity and segment-boundary masks
+                gn_st = valid ? static_cast<int>(row / p.gn_rows_per_stat - st_first) : -1;
+                const int st_prev = __shfl_up_sync(0xffffffffu, gn_st, 1);
+                gn_vmask = __ballot_sync(0xffffffffu, valid);
+                gn_bmask = __ballot_sync(0xffffffffu, lane > 0 && valid && gn_st != st_prev);
             }
+
+            // Residual rows are this thread's own (one row per thread, 64 bytes per 32-column half-chunk): a load issued
+            // where it is consumed exposes a full DRAM round trip per half-chunk with only two warps per sub-partition to
+            // hide it (round 1 ncu on the K = 320 projections: long_scoreboard 3.97 per issue, issue-active 26 %).  So
+            // the first half-chunk's residual is requested BEFORE the accumulator wait and each later one while the
+            // previous half-chunk is being computed (one extra 4 x 16-byte register buffer).
+            const bool has1 = p.res1 != nullptr, has2 = p.res2 != nullptr;  // uniform
+            uint4 r1n[4];
+            auto load_r1 = [&](int cc, int hh) {
+                const int col0n = cc * 64 + hh * 32;
+                const int n0n = nt * out_cols_tile + col0n;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    r1n[g] = make_uint4(0, 0, 0, 0);
+                    if (valid && col0n < out_cols && n0n + g * 8 < p.N_out)
+                        r1n[g] = __ldg(reinterpret_cast<const uint4*>(p.res1 + row * p.ldr1 + n0n) + g);
+                }
+            };
+            if (p.tma_out && has1 && half * 64 < out_cols) load_r1(half, 0);
 
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
@@ -408,7 +433,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         // loop, so the common case issues only: residual loads, tcgen05.ld, bias add, convert, store.
                         // (ncu on the first version: predicated-off activation/residual code still cost issue slots,
                         //  ~15 instructions per output element.)
-                        const bool has1 = p.res1 != nullptr, has2 = p.res2 != nullptr;  // uniform
                         uint4 r1[4], r2[4], rbv[4];
                         if (!kGeglu && p.rowbias) {  // row-group bias: requested with the residuals, not after the
 #pragma unroll                                       // accumulator wait (its L2 latency sat on the critical path)
@@ -419,13 +443,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     rbv[g] = __ldg(reinterpret_cast<const uint4*>(p.rowbias + group * p.ld_rowbias + nb));
                             }
                         }
-                        if (has1) {  // one batch of loads in flight, consumed after the TMEM load
+                        if (has1) {  // requested one half-chunk ago; now request the next one of this warp
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                r1[g] = make_uint4(0, 0, 0, 0);
-                                if (valid && n_out0 + g * 8 < p.N_out)
-                                    r1[g] = __ldg(reinterpret_cast<const uint4*>(p.res1 + row * p.ldr1 + n_out0) + g);
-                            }
+                            for (int g = 0; g < 4; ++g) r1[g] = r1n[g];
+                            const int cn = hlf == 0 ? c : c + 2;
+                            if (cn * 64 + (hlf ^ 1) * 32 < out_cols && cn < n_chunks) load_r1(cn, hlf ^ 1);
                         }
                         if (has2) {
 #pragma unroll
@@ -569,37 +591,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         // splits a pair (channels per group is even).  Common case: all 32 rows valid and inside one
                         // statistic -> a rolled 32-step loop and two atomics per lane; otherwise (ragged tiles, several
                         // small images per warp) a segment loop driven by two ballots.
-                        const long long st = valid ? row / p.gn_rows_per_stat : -1;
-                        const long long st_prev = __shfl_up_sync(0xffffffffu, st, 1);
-                        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-                        const uint32_t bmask = __ballot_sync(0xffffffffu, lane > 0 && valid && st != st_prev);
+                        const uint32_t vmask = gn_vmask, bmask = gn_bmask;
                         const int colp = nt * out_cols_tile + c * 64 + 2 * lane;     // global output column of the pair
                         const bool col_ok = colp < p.N_out;
                         const int grp = (p.gn_c_off + colp) / p.gn_cpg;
-                        float* gdst = p.gn_stats + grp * 2;
-                        const long long gstride = 2LL * p.gn_groups;
                         const int g_loc = grp - gn_g_first;
                         const bool to_smem = gn_smem && g_loc < kGnGroups;           // else: straight to global memory
-                        auto add_stat = [&](long long st_seg) {
+                        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                        auto add_stat = [&](int st_seg) {   // st_seg: statistic index relative to st_first
                             if (!col_ok) return;
                             if (to_smem) {
-                                float* d = s_gn + (static_cast<int>(st_seg - st_first) * kGnGroups + g_loc) * 2;
+                                float* d = s_gn + (st_seg * kGnGroups + g_loc) * 2;
                                 atomicAdd(d, s0 + s1);
                                 atomicAdd(d + 1, q0 + q1);
                             } else {
-                                atomicAdd(gdst + st_seg * gstride, s0 + s1);
-                                atomicAdd(gdst + st_seg * gstride + 1, q0 + q1);
+                                float* d = p.gn_stats + ((st_first + st_seg) * p.gn_groups + grp) * 2;
+                                atomicAdd(d, s0 + s1);
+                                atomicAdd(d + 1, q0 + q1);
                             }
                         };
                         const uint32_t lane_base = smem_u32(stg) + ((lane & 3) << 2);
                         const uint32_t chunk = lane >> 2;
-                        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
                         int seg_row = -1;
 #pragma unroll 4
                         for (int rr = 0; rr < 32; ++rr) {
                             if (!((vmask >> rr) & 1u)) continue;                      // warp-uniform
                             if (seg_row >= 0 && ((bmask >> rr) & 1u)) {               // statistic index changes here
-                                add_stat(__shfl_sync(0xffffffffu, st, seg_row));
+                                add_stat(__shfl_sync(0xffffffffu, gn_st, seg_row));
                                 s0 = s1 = q0 = q1 = 0.f;
                                 seg_row = rr;
                             }
@@ -613,7 +631,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             q0 = fmaf(f.x, f.x, q0);
                             q1 = fmaf(f.y, f.y, q1);
                         }
-                        if (seg_row >= 0) add_stat(__shfl_sync(0xffffffffu, st, seg_row));
+                        if (seg_row >= 0) add_stat(__shfl_sync(0xffffffffu, gn_st, seg_row));
                     }
                     if (lane == 0) {
                         const int n0 = nt * out_cols_tile + c * 64;
