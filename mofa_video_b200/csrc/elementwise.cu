@@ -2,6 +2,8 @@
 // upsample, NCHW<->NHWC, small-M linear, sinusoidal timestep embedding, fused CFG + Euler step.
 // All activations are fp16 channels-last; statistics and arithmetic are fp32; 16-byte vector accesses.
 #include "../../include/mofa_b200.h"
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mofa {
@@ -117,7 +119,8 @@ groupnorm_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __re
     }
 }
 
-__global__ void __launch_bounds__(256, 3)
+template <int kU, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks)
 groupnorm_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2,
                        const __half* __restrict__ gamma, const __half* __restrict__ beta, __half* __restrict__ out,
                        long long rows_per_stat, int rows_per_block, int slabs_per_stat, long long n_slabs, int groups,
@@ -162,13 +165,13 @@ groupnorm_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __re
                 sh[j] = __half2float(bt.h[j]) - mean * sc[j];
             }
             long long r = r_begin + ty;
-            for (; r + static_cast<long long>(kGnUnroll - 1) * VY < r_end; r += static_cast<long long>(kGnUnroll) * VY) {
-                V8 v[kGnUnroll];
+            for (; r + static_cast<long long>(kU - 1) * VY < r_end; r += static_cast<long long>(kU) * VY) {
+                V8 v[kU];
 #pragma unroll
-                for (int u = 0; u < kGnUnroll; ++u)
+                for (int u = 0; u < kU; ++u)
                     v[u].u = __ldg(reinterpret_cast<const uint4*>(base + (r + static_cast<long long>(u) * VY) * ld));
 #pragma unroll
-                for (int u = 0; u < kGnUnroll; ++u) {
+                for (int u = 0; u < kU; ++u) {
                     V8 o;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -563,11 +566,27 @@ extern "C" int mofa_groupnorm(const void* x1, int32_t C1, const void* x2, int32_
         int rc = check_launch("mofa_groupnorm(stats)");
         if (rc) return rc;
     }
-    plan(8, 3, rpb, sps, n_slabs, grid);
-    groupnorm_apply_kernel<<<grid, block, 0, stream>>>(
-        static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2, static_cast<const __half*>(gamma),
-        static_cast<const __half*>(beta), static_cast<__half*>(out), rows_per_stat, rpb, sps, n_slabs, groups, eps, silu,
-        stats);
+    // apply pass: (loads in flight per thread, resident blocks per SM); variant 0 = round 1's, others trade registers for
+    // occupancy (MOFA_GN_VARIANT, read once; default = measured best on B200, profiles/r2_groupnorm_variants.txt)
+    static int variant = -1;
+    if (variant < 0) {
+        const char* e = getenv("MOFA_GN_VARIANT");
+        variant = e ? atoi(e) : 0;
+        if (variant < 0 || variant > 3) variant = 0;
+    }
+#define MOFA_GN_APPLY(U, B, RPT)                                                                                       \
+    do {                                                                                                               \
+        plan(RPT, B, rpb, sps, n_slabs, grid);                                                                         \
+        groupnorm_apply_kernel<U, B><<<grid, block, 0, stream>>>(                                                      \
+            static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2, static_cast<const __half*>(gamma), \
+            static_cast<const __half*>(beta), static_cast<__half*>(out), rows_per_stat, rpb, sps, n_slabs, groups, eps, \
+            silu, stats);                                                                                              \
+    } while (0)
+    if (variant == 1) MOFA_GN_APPLY(2, 4, 8);
+    else if (variant == 2) MOFA_GN_APPLY(2, 6, 8);
+    else if (variant == 3) MOFA_GN_APPLY(1, 8, 8);
+    else MOFA_GN_APPLY(4, 3, 8);
+#undef MOFA_GN_APPLY
     return check_launch("mofa_groupnorm(apply)");
 }
 

@@ -180,7 +180,7 @@ __device__ __noinline__ void epilogue_direct8(const GemmKernelParams& p, const f
 //   2 generic activations (SiLU, ReLU, sigmoid, GELU, quick-GELU, ReLU-after-residual): conditioning convs, CMP, VAE, CLIP
 // kStats (plain only): GroupNorm statistics of the output accumulated from the staging tile (mofa_gemm_args.gn_stats).
 template <int kEpi, bool kStats>
-__global__ void __maxnreg__(200)  // 320 threads x 200 registers = 64000 of 65536: one CTA per SM (the shared memory says so anyway)
+__global__ void __maxnreg__(192)  // 10 warps x 192 registers (allocated per warp in 512-register units): one CTA per SM
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                const GemmKernelParams p) {

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_engine_gpu.py tests/test_keypoint_gpu.py tests/test_cmp_gpu.py -m gpu -q -p no:cacheprovider > gpurun_out/gpu_tests6.log 2>&1; echo "gpu tests: $?"
-grep -E "passed|failed|FAILED|Error|error" gpurun_out/gpu_tests6.log | tail -20
-timeout 600 python tools/profile_step.py --steps 2 --warmup 1 --detail > gpurun_out/step_detail_r2c.txt 2>&1; echo "profile: $?"
-head -40 gpurun_out/step_detail_r2c.txt | cut -c1-140
+timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_engine_gpu.py tests/test_keypoint_gpu.py tests/test_cmp_gpu.py -m gpu -q -p no:cacheprovider > gpurun_out/gpu_tests7.log 2>&1; echo "gpu tests: $?"
+grep -E "passed|failed|FAILED|Error|error" gpurun_out/gpu_tests7.log | tail -20
+timeout 600 python tools/profile_step.py --steps 2 --warmup 1 --detail > gpurun_out/step_detail_r2d.txt 2>&1; echo "profile: $?"
+head -40 gpurun_out/step_detail_r2d.txt | cut -c1-140
