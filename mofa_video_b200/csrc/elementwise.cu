@@ -566,27 +566,14 @@ extern "C" int mofa_groupnorm(const void* x1, int32_t C1, const void* x2, int32_
         int rc = check_launch("mofa_groupnorm(stats)");
         if (rc) return rc;
     }
-    // apply pass: (loads in flight per thread, resident blocks per SM); variant 0 = round 1's, others trade registers for
-    // occupancy (MOFA_GN_VARIANT, read once; default = measured best on B200, profiles/r2_groupnorm_variants.txt)
-    static int variant = -1;
-    if (variant < 0) {
-        const char* e = getenv("MOFA_GN_VARIANT");
-        variant = e ? atoi(e) : 0;
-        if (variant < 0 || variant > 3) variant = 0;
-    }
-#define MOFA_GN_APPLY(U, B, RPT)                                                                                       \
-    do {                                                                                                               \
-        plan(RPT, B, rpb, sps, n_slabs, grid);                                                                         \
-        groupnorm_apply_kernel<U, B><<<grid, block, 0, stream>>>(                                                      \
-            static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2, static_cast<const __half*>(gamma), \
-            static_cast<const __half*>(beta), static_cast<__half*>(out), rows_per_stat, rpb, sps, n_slabs, groups, eps, \
-            silu, stats);                                                                                              \
-    } while (0)
-    if (variant == 1) MOFA_GN_APPLY(2, 4, 8);
-    else if (variant == 2) MOFA_GN_APPLY(2, 6, 8);
-    else if (variant == 3) MOFA_GN_APPLY(1, 8, 8);
-    else MOFA_GN_APPLY(4, 3, 8);
-#undef MOFA_GN_APPLY
+    // apply pass: 4 loads of 16 bytes in flight per thread, 3 blocks per SM.  Round-2 microbenchmark of (2 loads, 4 blocks),
+    // (2, 6), (1, 8) register / occupancy trade-offs: equal or slower (4.17 TB/s at level 0 for the first two, 3.8 / 3.5 for
+    // the spilling ones; profiles/r2_groupnorm_variants.txt)
+    plan(8, 3, rpb, sps, n_slabs, grid);
+    groupnorm_apply_kernel<4, 3><<<grid, block, 0, stream>>>(
+        static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2, static_cast<const __half*>(gamma),
+        static_cast<const __half*>(beta), static_cast<__half*>(out), rows_per_stat, rpb, sps, n_slabs, groups, eps, silu,
+        stats);
     return check_launch("mofa_groupnorm(apply)");
 }
 

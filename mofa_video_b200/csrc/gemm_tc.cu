@@ -180,7 +180,9 @@ __device__ __noinline__ void epilogue_direct8(const GemmKernelParams& p, const f
 //   2 generic activations (SiLU, ReLU, sigmoid, GELU, quick-GELU, ReLU-after-residual): conditioning convs, CMP, VAE, CLIP
 // kStats (plain only): GroupNorm statistics of the output accumulated from the staging tile (mofa_gemm_args.gn_stats).
 template <int kEpi, bool kStats>
-__global__ void __maxnreg__(192)  // 10 warps x 192 registers (allocated per warp in 512-register units): one CTA per SM
+// 168 registers is the ceiling for a 320-thread CTA: the register file is split per sub-partition (16384 each) and ten warps
+// land 3 + 3 + 2 + 2, so 3 warps x 32 x R <= 16384 (a 176-register build fails to launch: "too many resources requested")
+__global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                const GemmKernelParams p) {
@@ -411,7 +413,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         r1n[g] = __ldg(reinterpret_cast<const uint4*>(p.res1 + row * p.ldr1 + n0n) + g);
                 }
             };
-            if (p.tma_out && has1 && half * 64 < out_cols) load_r1(half, 0);
+            // (not in the statistics kernel: its extra state would spill; its GEMMs are main-loop bound convolutions)
+            constexpr bool kPrefetchRes = !kStats;
+            if (kPrefetchRes && p.tma_out && has1 && half * 64 < out_cols) load_r1(half, 0);
 
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
@@ -443,11 +447,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     rbv[g] = __ldg(reinterpret_cast<const uint4*>(p.rowbias + group * p.ld_rowbias + nb));
                             }
                         }
-                        if (has1) {  // requested one half-chunk ago; now request the next one of this warp
+                        if (has1) {
+                            if constexpr (kPrefetchRes) {  // requested one half-chunk ago; now request this warp's next one
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) r1[g] = r1n[g];
-                            const int cn = hlf == 0 ? c : c + 2;
-                            if (cn * 64 + (hlf ^ 1) * 32 < out_cols && cn < n_chunks) load_r1(cn, hlf ^ 1);
+                                for (int g = 0; g < 4; ++g) r1[g] = r1n[g];
+                                const int cn = hlf == 0 ? c : c + 2;
+                                if (cn * 64 + (hlf ^ 1) * 32 < out_cols && cn < n_chunks) load_r1(cn, hlf ^ 1);
+                            } else {
+                                load_r1(c, hlf);
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) r1[g] = r1n[g];
+                            }
                         }
                         if (has2) {
 #pragma unroll
