@@ -37,8 +37,9 @@ constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kABytes = BM * BK * 2;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kStagingBytes = 4096;  // 32 rows x 128 B per epilogue warp
-constexpr int kGnSlots = 4;               // statistics (frames / batch items) one M tile may span in shared memory
+constexpr int kGnSlots = 2;               // statistics (frames / batch items) one M tile may span in shared memory
 constexpr int kGnGroups = 32;             // groups one N tile may span in shared memory
+constexpr int kGnBufs = 3;                // tiles in flight: an epilogue warp is at most 2 tiles ahead of another (2 TMEM stages)
 
 struct GemmKernelParams {
     int mode, act;
@@ -203,12 +204,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // kStats: per-CTA GroupNorm partial sums [kGnSlots statistics][kGnGroups groups][sum, sum of squares] of the tile being
     // drained; shared-memory atomics per chunk, ONE flush of global atomics per tile.  (Global atomics per chunk -- 4.6 M per
     // level-0 launch onto 3200 addresses -- doubled the conv time: profiles/r2_step_detail_b_gnstats_global_atomics.txt.)
-    float* s_gn = reinterpret_cast<float*>(tmem_ptr_smem + 4);
+    float* s_gn = reinterpret_cast<float*>(tmem_ptr_smem + 4);          // [kGnBufs][kGnSlots][kGnGroups][2]
+    int* s_gn_cnt = reinterpret_cast<int*>(s_gn + kGnBufs * kGnSlots * kGnGroups * 2);   // warps done per buffer
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     if constexpr (kStats) {
-        for (int i = threadIdx.x; i < kGnSlots * kGnGroups * 2; i += blockDim.x) s_gn[i] = 0.f;
+        for (int i = threadIdx.x; i < kGnBufs * kGnSlots * kGnGroups * 2; i += blockDim.x) s_gn[i] = 0.f;
+        if (threadIdx.x < kGnBufs) s_gn_cnt[threadIdx.x] = 0;
     }
 
     if (threadIdx.x == 0) {
@@ -611,7 +614,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         auto add_stat = [&](int st_seg) {   // st_seg: statistic index relative to st_first
                             if (!col_ok) return;
                             if (to_smem) {
-                                float* d = s_gn + (st_seg * kGnGroups + g_loc) * 2;
+                                float* d = s_gn + ((static_cast<int>(iter % kGnBufs) * kGnSlots + st_seg) * kGnGroups + g_loc) * 2;
                                 atomicAdd(d, s0 + s1);
                                 atomicAdd(d + 1, q0 + q1);
                             } else {
@@ -685,22 +688,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[as]);
             if constexpr (kStats) {
-                if (gn_smem) {  // tile-uniform: the 8 epilogue warps meet, warp 2 moves the tile's partial sums to global memory
-                    asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-                    if (e == 0) {
+                if (gn_smem) {
+                    // No barrier: every warp counts itself done with this tile's buffer and the LAST one moves the partial
+                    // sums to global memory.  (Two bar.sync per tile lock-stepped the eight warps and doubled the
+                    // temporal-conv GEMMs: profiles/r2_step_detail_f_gnstats_smem_barriers.txt.)  Three buffers: a warp
+                    // can be at most two tiles ahead of the slowest one (two TMEM stages), so the buffer of tile i is
+                    // flushed and zeroed long before tile i + 3 touches it.
+                    const int buf = static_cast<int>(iter % kGnBufs);
+                    __syncwarp();
+                    int done = 0;
+                    if (lane == 0) {
+                        __threadfence_block();
+                        done = atomicAdd(&s_gn_cnt[buf], 1);
+                    }
+                    done = __shfl_sync(0xffffffffu, done, 0);
+                    if (done == kEpiWarps - 1) {
+                        __threadfence_block();
+                        float* sb = s_gn + buf * kGnSlots * kGnGroups * 2;
                         for (int i = lane; i < kGnSlots * kGnGroups; i += 32) {
-                            const float a = s_gn[2 * i], b = s_gn[2 * i + 1];
+                            const float a = atomicExch(&sb[2 * i], 0.f), b = atomicExch(&sb[2 * i + 1], 0.f);
                             if (a != 0.f || b != 0.f) {
                                 const int g = gn_g_first + (i % kGnGroups);
                                 float* d = p.gn_stats + ((st_first + i / kGnGroups) * p.gn_groups + g) * 2;
                                 atomicAdd(d, a);
                                 atomicAdd(d + 1, b);
-                                s_gn[2 * i] = 0.f;
-                                s_gn[2 * i + 1] = 0.f;
                             }
                         }
+                        __syncwarp();
+                        if (lane == 0) s_gn_cnt[buf] = 0;
                     }
-                    asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
                 }
             }
         }
@@ -1008,7 +1024,7 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
     if (stages < 2) stages = 2;
     p.stages = stages;
     const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + kEpiWarps * kStagingBytes +
-                              (2 * stages + 4) * 8 + 16 + 1024 + (p.gn_stats ? kGnSlots * kGnGroups * 8 + 16 : 0);
+                              (2 * stages + 4) * 8 + 16 + 1024 + (p.gn_stats ? kGnBufs * kGnSlots * kGnGroups * 8 + 32 : 0);
 
     if (p.gn_stats) {
         const long long rows_total = a->mode == MOFA_A_LINEAR ? a->M
