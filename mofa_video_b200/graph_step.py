@@ -84,3 +84,33 @@ class StepRunner:
             self.graph = g
         self.graph.replay()
         ops.note_graph_replay(self.kernels_per_step)
+
+
+class HybridStepRunner(StepRunner):
+    """The Hybrid step (/root/reference/MOFA-Video-Hybrid/pipeline/pipeline.py:432-507): landmark adapter + trajectory
+    adapter on the same fused CFG input, their 12 + 1 residuals blended with the per-level nearest-resized mask, UNet,
+    fused CFG / Euler -- captured and replayed like the Traj step.  `ad_net` = the face (landmark) adapter."""
+
+    def __init__(self, ops, unet_net, face_net, drag_net, T, h, w, g_min, g_max, scale_ldmk, scale_traj, device):
+        super().__init__(ops, unet_net, face_net, T, h, w, g_min, g_max, scale_ldmk, device)
+        self.drag_net, self.scale_traj = drag_net, float(scale_traj)
+        drag_net.persistent = True
+        self.masks = {}          # rows of a residual -> fp16 mask [h_l * w_l] (persistent storage)
+
+    def set_masks(self, by_rows):
+        for rows, m in by_rows.items():
+            if rows not in self.masks:
+                self.masks[rows] = torch.empty_like(m)
+            self.masks[rows].copy_(m)
+
+    def _body(self):
+        ops = self.ops
+        t_dev = self.cur[:self.B]
+        rf, mf = self.ad_net.adapter_forward(self.next_in, t_dev, self.h, self.w, self.cond_scale)
+        rd, md = self.drag_net.adapter_forward(self.next_in, t_dev, self.h, self.w, self.scale_traj)
+        for a, b in zip(rf + [mf], rd + [md]):
+            m = self.masks[a.shape[0]]
+            ops.mask_blend(a, b, m, a, period_rows=m.shape[0])           # face inside the mask, drag outside (:479-488)
+        noise = self.unet_net.unet_forward(self.next_in, t_dev, self.h, self.w, rf, mf)
+        ops.cfg_euler_step_dev(noise, self.lat_h, self.img_lat, self.next_in, self.T, self.hw, self.g_min, self.g_max,
+                               self.cur[self.B:])

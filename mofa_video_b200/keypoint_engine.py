@@ -106,9 +106,13 @@ class LdmkAdapterNet(engine.Net):
             last = k == len(convs) - 1
             x, H, W = self.conv_im2col(c, x, T, H, W, act=0 if last else ops.ACT_SILU)
         C0 = x.shape[1]
+        if self.persistent:   # a captured step graph reads these: same storage for every clip (engine.Net.pbuf)
+            xb = self.pbuf(("ldmk", 1), *x.shape)
+            xb.copy_(x)
+            x = xb
         self.ldmk = {H: x}
         for s in (2, 4):
-            d = self.new(T * (H // s) * (W // s), C0)
+            d = self.pbuf(("ldmk", s), T * (H // s) * (W // s), C0)
             ops.downsample_nearest(x, d, T, H, W, C0, s)
             self.ldmk[H // s] = d
         return masks

@@ -51,6 +51,19 @@ class FlowControlNetPipeline(_TrajPipeline):
                          native_vae=native_vae, native_clip=native_clip)
         self.drag_controlnet, self.face_controlnet = drag_controlnet, face_controlnet
 
+    def _hybrid_runner(self, unet_net, face_net, drag_net, T, h, w, g_min, g_max, scale_ldmk, scale_traj):
+        from mofa_video_b200.graph_step import HybridStepRunner
+        cache = self.__dict__.setdefault("_runners", {})
+        key = ("hybrid", id(unet_net), id(face_net), id(drag_net), T, h, w, float(g_min), float(g_max),
+               float(scale_ldmk), float(scale_traj))
+        if key not in cache:
+            while len(cache) >= 2:
+                cache.pop(next(iter(cache)))
+            cache[key] = HybridStepRunner(self._ops, unet_net, face_net, drag_net, T, h, w, g_min, g_max, scale_ldmk,
+                                          scale_traj, self._device)
+            cache[key].use_graph = cache[key].use_graph and getattr(self, "use_cuda_graph", True)
+        return cache[key]
+
     @classmethod
     def from_pretrained(cls, path, unet=None, drag_controlnet=None, face_controlnet=None, image_encoder=None, vae=None,
                         scheduler=None, feature_extractor=None, torch_dtype=None, **_ignored):
@@ -86,30 +99,29 @@ class FlowControlNetPipeline(_TrajPipeline):
         h, w = height // self.vae_scale_factor, width // self.vae_scale_factor
         hw, T = h * w, num_frames
         unet_net, face, drag = self.unet.net, self.face_controlnet, self.drag_controlnet
+        # step runner first: it makes the conditioning tensors persistent (graph_step.py)
+        runner = self._hybrid_runner(unet_net, face.net, drag.net, T, h, w, min_guidance_scale, max_guidance_scale,
+                                     ctrl_scale_ldmk, ctrl_scale_traj)
         for n in (unet_net, face.net, drag.net):
             n.prepare_clip(image_embeddings, added_time_ids)
         face.prepare_condition(cond, flow, ldmk, force=True)
         drag.prepare_condition(cond, dflow, force=True)
-        by_rows = level_masks(mask, h, w, len(self.unet.config.block_out_channels), T, device)
-        lat = latents[0].to(torch.float16).reshape(T, 4, hw).contiguous()
-        il = image_latents.to(torch.float16).reshape(2, 4, hw).contiguous()
+        runner.set_masks(level_masks(mask, h, w, len(self.unet.config.block_out_channels), T, device))
         sig, tsteps = self.scheduler._sigmas_host, self.scheduler._timesteps_host
         self._num_timesteps = len(tsteps)
-
-        def on_step(i, cur_lat):
-            """Returns True when the callback replaced the latents (the fused next-step input must be rebuilt)."""
+        self.scheduler._step_index = 0
+        runner.begin_clip(latents[0].reshape(T, 4, hw), image_latents.reshape(2, 4, hw), tsteps, sig)
+        for i in range(len(tsteps)):
+            runner.step(i)
             self.scheduler._step_index = i + 1
-            if callback_on_step_end is None:
-                return False
-            cur = cur_lat.reshape(1, T, 4, h, w)
-            outs = callback_on_step_end(self, i, self.scheduler.timesteps[i], {"latents": cur}) or {}
-            new = outs.pop("latents", None)
-            if new is not None and new is not cur:
-                cur_lat.copy_(new.reshape(T, 4, hw))
-            return True             # an in-place edit of `cur` counts too (H/pipeline/pipeline.py loop end)
-
-        denoise_hybrid(ops, unet_net, face.net, drag.net, by_rows, lat, il, sig, tsteps, h, w, min_guidance_scale,
-                       max_guidance_scale, ctrl_scale_ldmk, ctrl_scale_traj, on_step)
+            if callback_on_step_end is not None:
+                cur = runner.lat_h.reshape(1, T, 4, h, w)
+                outs = callback_on_step_end(self, i, self.scheduler.timesteps[i], {"latents": cur}) or {}
+                new = outs.pop("latents", None)
+                if new is not None and new is not cur:
+                    runner.lat_h.copy_(new.reshape(T, 4, hw))
+                runner.rebuild_input(sig[i + 1])      # an in-place edit of `cur` counts too
+        lat = runner.lat_h.clone()
         latents = lat.reshape(1, T, 4, h, w)
         frames = self._decode_output(latents, num_frames, decode_chunk_size, output_type)
         if not return_dict:

@@ -119,18 +119,7 @@ class FlowControlNetPipeline(_TrajPipeline):
         shard = None
         if shard_windows and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             shard = (dist.get_world_size(), dist.get_rank())
-        states = []
-        for k, ((ts, te), mult) in enumerate(unique_views(window_views(num_frames, window_size, stride))):
-            if shard is not None and k % shard[0] != shard[1]:
-                states.append(None)            # another rank's window: no conditioning needed here
-                continue
-            # loop-invariant conditioning of every distinct view
-            fl = flow[:, (ts - 1):(te - 1)]
-            lm = torch.cat([ldmk[:, 0:1], ldmk[:, ts:te]], dim=1)
-            ad.prepare_condition(cond, torch.cat([fl] * 2), torch.cat([lm] * 2), force=True)
-            states.append(((ts, te), mult, (ad.net.warped, ad.net.ldmk)))
-        lat = latents[0].to(torch.float16).reshape(num_frames, 4, hw).contiguous()
-        il = image_latents.to(torch.float16).reshape(2, 4, hw).contiguous()
+        views = unique_views(window_views(num_frames, window_size, stride))
         sig, tsteps = self.scheduler._sigmas_host, self.scheduler._timesteps_host
         self._num_timesteps = len(tsteps)
 
@@ -143,8 +132,41 @@ class FlowControlNetPipeline(_TrajPipeline):
             new = outs.pop("latents", None)
             return cur_lat if new is None else new.reshape(num_frames, 4, hw).to(torch.float16).contiguous()
 
-        lat = denoise_windowed(ops, unet_net, ad.net, states, lat, il, sig, tsteps, h, w, T, min_guidance_scale,
-                               max_guidance_scale, controlnet_cond_scale, on_step, shard=shard)
+        if len(views) == 1 and shard is None:
+            # num_frames == window_size (configs[2]): the two windows of the reference are the same view (Q12), the
+            # value / count average of identical latents is the identity, and the loop is the Traj loop with the landmark
+            # adapter -- so it runs through the same captured-step runner (graph_step.StepRunner)
+            (ts, te), _ = views[0]
+            runner = self._step_runner(unet_net, ad.net, T, h, w, min_guidance_scale, max_guidance_scale,
+                                       controlnet_cond_scale)
+            unet_net.prepare_clip(image_embeddings, added_time_ids)
+            ad.net.prepare_clip(image_embeddings, added_time_ids)
+            ad.prepare_condition(cond, torch.cat([flow[:, (ts - 1):(te - 1)]] * 2),
+                                 torch.cat([torch.cat([ldmk[:, 0:1], ldmk[:, ts:te]], dim=1)] * 2), force=True)
+            runner.begin_clip(latents[0].reshape(num_frames, 4, hw), image_latents.reshape(2, 4, hw), tsteps, sig)
+            for i in range(len(tsteps)):
+                runner.step(i)
+                new = on_step(i, runner.lat_h)
+                if callback_on_step_end is not None:
+                    if new is not runner.lat_h:
+                        runner.lat_h.copy_(new)
+                    runner.rebuild_input(sig[i + 1])
+            lat = runner.lat_h.clone()
+        else:
+            states = []
+            for k, ((ts, te), mult) in enumerate(views):
+                if shard is not None and k % shard[0] != shard[1]:
+                    states.append(None)            # another rank's window: no conditioning needed here
+                    continue
+                # loop-invariant conditioning of every distinct view
+                fl = flow[:, (ts - 1):(te - 1)]
+                lm = torch.cat([ldmk[:, 0:1], ldmk[:, ts:te]], dim=1)
+                ad.prepare_condition(cond, torch.cat([fl] * 2), torch.cat([lm] * 2), force=True)
+                states.append(((ts, te), mult, (ad.net.warped, ad.net.ldmk)))
+            lat = latents[0].to(torch.float16).reshape(num_frames, 4, hw).contiguous()
+            il = image_latents.to(torch.float16).reshape(2, 4, hw).contiguous()
+            lat = denoise_windowed(ops, unet_net, ad.net, states, lat, il, sig, tsteps, h, w, T, min_guidance_scale,
+                                   max_guidance_scale, controlnet_cond_scale, on_step, shard=shard)
         latents = lat.reshape(1, num_frames, 4, h, w)
         frames = self._decode_output(latents, num_frames, decode_chunk_size, output_type)
         if not return_dict:
