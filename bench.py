@@ -354,10 +354,12 @@ def run_engine(args):
         g_n = sum(v["launches"] for v in gem.values())
         ach = g_fl / (g_ms * 1e-3) / 1e12 if g_ms else 0.0
         traffic = None
-        tf = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
-        if os.path.exists(tf):
-            with open(tf) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+        for name in ("r2_gemm_traffic.json", "r1_gemm_traffic.json"):   # ncu capture of this kernel family (newest first)
+            tf = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(tf):
+                with open(tf) as f:
+                    traffic = json.load(f).get("dram_bytes_per_launch")
+                break
         att = prof.get("attn_spatial", {"ms": 0.0, "work": 0.0, "launches": 0})
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (linear / conv3x3 / temporal3 implicit GEMM)",
                 "achieved": round(ach, 1), "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
