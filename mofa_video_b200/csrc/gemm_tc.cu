@@ -611,16 +611,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int g_loc = grp - gn_g_first;
                         const bool to_smem = gn_smem && g_loc < kGnGroups;           // else: straight to global memory
                         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                        // Lanes of one group are neighbours (cpg / 2 of them).  fp32 atomicAdd on shared memory is a
+                        // compare-and-swap loop (ATOMS.CAST.SPIN): ten lanes on one address = ten rounds, and it made the
+                        // temporal-conv GEMMs 2.2x slower (profiles/r2_step_detail_f/g).  So: inclusive prefix sums over the
+                        // lanes, each group's total = difference of two prefixes, and only the LAST lane of a group touches
+                        // memory (distinct addresses within the warp).
                         auto add_stat = [&](int st_seg) {   // st_seg: statistic index relative to st_first
-                            if (!col_ok) return;
-                            if (to_smem) {
-                                float* d = s_gn + ((static_cast<int>(iter % kGnBufs) * kGnSlots + st_seg) * kGnGroups + g_loc) * 2;
-                                atomicAdd(d, s0 + s1);
-                                atomicAdd(d + 1, q0 + q1);
-                            } else {
-                                float* d = p.gn_stats + ((st_first + st_seg) * p.gn_groups + grp) * 2;
-                                atomicAdd(d, s0 + s1);
-                                atomicAdd(d + 1, q0 + q1);
+                            const int gkey = col_ok ? grp : -1;
+                            float ps = col_ok ? s0 + s1 : 0.f, pq = col_ok ? q0 + q1 : 0.f;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const float ts = __shfl_up_sync(0xffffffffu, ps, o), tq = __shfl_up_sync(0xffffffffu, pq, o);
+                                if (lane >= o) {
+                                    ps += ts;
+                                    pq += tq;
+                                }
+                            }
+                            const int g_next = __shfl_down_sync(0xffffffffu, gkey, 1);
+                            const int g_prev = __shfl_up_sync(0xffffffffu, gkey, 1);
+                            const bool is_last = lane == 31 || g_next != gkey;
+                            const bool is_first = lane == 0 || g_prev != gkey;
+                            // prefix just before my group's first lane: broadcast from the group's first lane
+                            const uint32_t firsts = __ballot_sync(0xffffffffu, is_first);
+                            const int first_lane = 31 - __clz(firsts & (0xffffffffu >> (31 - lane)));
+                            const float bs = __shfl_sync(0xffffffffu, ps, (first_lane + 31) & 31);
+                            const float bq = __shfl_sync(0xffffffffu, pq, (first_lane + 31) & 31);
+                            if (is_last && gkey >= 0) {
+                                const float ts = first_lane > 0 ? ps - bs : ps, tq = first_lane > 0 ? pq - bq : pq;
+                                if (to_smem) {
+                                    const uint32_t d = smem_u32(s_gn) + static_cast<uint32_t>(
+                                        (((static_cast<int>(iter % kGnBufs) * kGnSlots + st_seg) * kGnGroups + g_loc) * 2) * 4);
+                                    asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(d), "f"(ts) : "memory");
+                                    asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(d + 4), "f"(tq) : "memory");
+                                } else {
+                                    float* d = p.gn_stats + ((st_first + st_seg) * p.gn_groups + grp) * 2;
+                                    atomicAdd(d, ts);
+                                    atomicAdd(d + 1, tq);
+                                }
                             }
                         };
                         const uint32_t lane_base = smem_u32(stg) + ((lane & 3) << 2);
@@ -706,7 +733,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         __threadfence_block();
                         float* sb = s_gn + buf * kGnSlots * kGnGroups * 2;
                         for (int i = lane; i < kGnSlots * kGnGroups; i += 32) {
-                            const float a = atomicExch(&sb[2 * i], 0.f), b = atomicExch(&sb[2 * i + 1], 0.f);
+                            const float a = sb[2 * i], b = sb[2 * i + 1];   // all eight warps are done with this buffer
+                            sb[2 * i] = 0.f;
+                            sb[2 * i + 1] = 0.f;
                             if (a != 0.f || b != 0.f) {
                                 const int g = gn_g_first + (i % kGnGroups);
                                 float* d = p.gn_stats + ((st_first + i / kGnGroups) * p.gn_groups + g) * 2;
