@@ -63,17 +63,36 @@ class PeerFrameGather:
         self.slot_bytes = (n + 255) // 256 * 256
         total = self.world * self.slot_bytes + self.FLAG_BYTES
         dev = torch.device("cuda", torch.cuda.current_device())
+        # Every rank executes the same collectives whatever fails locally (a rank that raised before a collective would
+        # leave the others hanging in it); errors are exchanged and raised by all ranks together.
+        err, box = None, [None]
         if self.rank == dst:
-            self.buf = torch.zeros(total, dtype=torch.uint8, device=dev)
-            torch.cuda.synchronize()
+            try:
+                self.buf = torch.zeros(total, dtype=torch.uint8, device=dev)
+                torch.cuda.synchronize()
+                if self.world > 1:
+                    from torch.multiprocessing.reductions import reduce_tensor
+                    box = [reduce_tensor(self.buf)]                          # CUDA IPC handle of the allocation
+            except Exception as exc:  # noqa: BLE001
+                err = f"rank {self.rank}: {type(exc).__name__}: {exc}"
         if self.world > 1:
-            from torch.multiprocessing.reductions import reduce_tensor
-            box = [reduce_tensor(self.buf) if self.rank == dst else None]   # CUDA IPC handle of the allocation
             dist.broadcast_object_list(box, src=dst)
             if self.rank != dst:
-                rebuild, args = box[0]
-                self.buf = rebuild(*args)                                    # dst's memory, mapped into this process
-                self.ops.peer_enable(self.buf.device.index)                  # kernels on OUR device may address it
+                try:
+                    if box[0] is None:
+                        raise RuntimeError("the destination rank could not export its buffer")
+                    rebuild, args = box[0]
+                    self.buf = rebuild(*args)                                # dst's memory, mapped into this process
+                    self.ops.peer_enable(self.buf.device.index)              # kernels on OUR device may address it
+                except Exception as exc:  # noqa: BLE001
+                    err = f"rank {self.rank}: {type(exc).__name__}: {exc}"
+            errs = [None] * self.world
+            dist.all_gather_object(errs, err)
+            errs = [e for e in errs if e]
+            if errs:
+                raise RuntimeError("PeerFrameGather unavailable: " + "; ".join(errs)[:300])
+        elif err:
+            raise RuntimeError(err)
         self.flags = self.buf[self.world * self.slot_bytes:].view(torch.int32)
         self.ready = self.flags[:self.world]
         self.consumed = self.flags[64:65]
