@@ -99,6 +99,12 @@ MOFA_DEVICE TileCoord tile_coord(const GemmKernelParams& p, int mt) {
     return c;
 }
 
+// fire-and-forget fp32 add to GLOBAL memory.  atomicAdd() on a pointer the compiler cannot prove global compiles to ATOM (value
+// returned: the warp waits a full round trip per call) behind an address-space test; the statistics flush issues 128 of them.
+MOFA_DEVICE void red_add_global(float* addr, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(__cvta_generic_to_global(addr)), "f"(v) : "memory");
+}
+
 union H8 {
     uint4 u;
     __half2 h2[4];
@@ -645,8 +651,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(d + 4), "f"(tq) : "memory");
                                 } else {
                                     float* d = p.gn_stats + ((st_first + st_seg) * p.gn_groups + grp) * 2;
-                                    atomicAdd(d, ts);
-                                    atomicAdd(d + 1, tq);
+                                    red_add_global(d, ts);
+                                    red_add_global(d + 1, tq);
                                 }
                             }
                         };
@@ -739,8 +745,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (a != 0.f || b != 0.f) {
                                 const int g = gn_g_first + (i % kGnGroups);
                                 float* d = p.gn_stats + ((st_first + i / kGnGroups) * p.gn_groups + g) * 2;
-                                atomicAdd(d, a);
-                                atomicAdd(d + 1, b);
+                                red_add_global(d, a);
+                                red_add_global(d + 1, b);
                             }
                         }
                         __syncwarp();
