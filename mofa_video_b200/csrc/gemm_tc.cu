@@ -37,6 +37,7 @@ constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kABytes = BM * BK * 2;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kStagingBytes = 4096;  // 32 rows x 128 B per epilogue warp
+constexpr bool kGegluCompact = true;      // rolled 8-column GEGLU epilogue (A/B switch; see the epilogue)
 constexpr int kGnSlots = 2;               // statistics (frames / batch items) one M tile may span in shared memory
 constexpr int kGnGroups = 32;             // groups one N tile may span in shared memory
 constexpr int kGnBufs = 3;                // tiles in flight: an epilogue warp is at most 2 tiles ahead of another (2 TMEM stages)
@@ -446,6 +447,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         // loop, so the common case issues only: residual loads, tcgen05.ld, bias add, convert, store.
                         // (ncu on the first version: predicated-off activation/residual code still cost issue slots,
                         //  ~15 instructions per output element.)
+                        if constexpr (kGeglu && kGegluCompact) {
+                            // GEGLU half-chunk as a ROLLED loop over four 8-column groups (x8 TMEM loads, the next group's
+                            // loads in flight while this group's GELUs run): ~200 instructions of loop body instead of a
+                            // 32-wide unrolled ~700 (the epilogue was fetch-limited: stall_no_instruction 0.45 per issue).
+                            // GEGLU launches carry no residual / row bias / alpha (mofa_gemm checks).
+                            uint32_t a8[8], g8[8];
+                            tmem_ld_32x8(taddr + col0, a8);
+                            tmem_ld_32x8(taddr + half_bn + col0, g8);
+#pragma unroll 1
+                            for (int g = 0; g < 4; ++g) {
+                                H8 bv, bg;
+                                bv.u = make_uint4(0, 0, 0, 0);
+                                bg.u = make_uint4(0, 0, 0, 0);
+                                if (p.bias) {
+                                    const int nb = nt * p.bn + col0 + g * 8;
+                                    bv.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nb));
+                                    bg.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nb + half_bn));
+                                }
+                                tmem_ld_wait();
+                                float va[8], ga[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    va[j] = __uint_as_float(a8[j]);
+                                    ga[j] = __uint_as_float(g8[j]);
+                                }
+                                if (g < 3) {
+                                    tmem_ld_32x8(taddr + col0 + (g + 1) * 8, a8);
+                                    tmem_ld_32x8(taddr + half_bn + col0 + (g + 1) * 8, g8);
+                                }
+                                H8 o;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float y0 = (va[2 * j] + __half2float(bv.h[2 * j])) *
+                                                     gelu_erf_relu_form(ga[2 * j] + __half2float(bg.h[2 * j]));
+                                    const float y1 = (va[2 * j + 1] + __half2float(bv.h[2 * j + 1])) *
+                                                     gelu_erf_relu_form(ga[2 * j + 1] + __half2float(bg.h[2 * j + 1]));
+                                    o.h2[j] = __floats2half2_rn(y0, y1);
+                                }
+                                const int ci = hlf * 4 + g;
+                                *reinterpret_cast<uint4*>(stg + lane * 128 + ((ci ^ (lane & 7)) << 4)) = o.u;
+                            }
+                            continue;
+                        }
                         uint4 r1[4], r2[4], rbv[4];
                         if (!kGeglu && p.rowbias) {  // row-group bias: requested with the residuals, not after the
 #pragma unroll                                       // accumulator wait (its L2 latency sat on the critical path)
@@ -873,8 +917,8 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
         set_last_error("mofa_gemm: GEGLU needs 16-byte aligned rows and bn %% 128 == 0");
         return MOFA_ERR_ARG;
     }
-    if (geglu && a->rowbias) {
-        set_last_error("mofa_gemm: GEGLU does not take a row-group bias");
+    if (geglu && (a->rowbias || a->res1 || a->res2 || a->alpha != 1.0f)) {
+        set_last_error("mofa_gemm: GEGLU takes a bias only (no row-group bias, residual or alpha)");
         return MOFA_ERR_ARG;
     }
 
