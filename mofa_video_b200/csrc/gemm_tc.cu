@@ -37,6 +37,7 @@ constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kABytes = BM * BK * 2;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kStagingBytes = 4096;  // 32 rows x 128 B per epilogue warp
+constexpr bool kGeglu16 = true;           // GEGLU (LINEAR mode) on the 16-epilogue-warp instantiation (A/B switch)
 constexpr bool kGegluCompact = true;      // rolled 8-column GEGLU epilogue (A/B switch; see the epilogue)
 constexpr int kGnSlots = 2;               // statistics (frames / batch items) one M tile may span in shared memory
 constexpr int kGnGroups = 32;             // groups one N tile may span in shared memory
@@ -187,10 +188,14 @@ __device__ __noinline__ void epilogue_direct8(const GemmKernelParams& p, const f
 //   1 GEGLU                                               -- FeedForward first projections
 //   2 generic activations (SiLU, ReLU, sigmoid, GELU, quick-GELU, ReLU-after-residual): conditioning convs, CMP, VAE, CLIP
 // kStats (plain only): GroupNorm statistics of the output accumulated from the staging tile (mofa_gemm_args.gn_stats).
-template <int kEpi, bool kStats>
+// kEW = epilogue warps: 8 everywhere; 16 for the GEGLU kernel (LINEAR mode only), whose epilogue is the bottleneck at
+// K = 320 / 640 and latency-limited with two warps per sub-partition (issue-active 59 %): four warps per sub-partition, each
+// owning one 32-column half-chunk, 32 x 64-byte SWIZZLE_64B staging tiles, one {32 cols, 32 rows} TMA store each.
 // 168 registers is the ceiling for a 320-thread CTA: the register file is split per sub-partition (16384 each) and ten warps
-// land 3 + 3 + 2 + 2, so 3 warps x 32 x R <= 16384 (a 176-register build fails to launch: "too many resources requested")
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// land 3 + 3 + 2 + 2, so 3 warps x 32 x R <= 16384 (a 176-register build fails to launch: "too many resources requested");
+// 18 warps (kEW = 16) land 5 + 5 + 4 + 4: 96 registers.
+template <int kEpi, bool kStats, int kEW>
+__global__ void __launch_bounds__(64 + 32 * kEW, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                const GemmKernelParams p) {
@@ -202,7 +207,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t b_bytes = static_cast<uint32_t>(p.bn) * (BK * 2);
     const uint32_t stage_bytes = kABytes + b_bytes;
     uint8_t* staging = smem + static_cast<size_t>(p.stages) * stage_bytes;  // kEpiWarps x 4 KB, 1024-aligned
-    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kEpiWarps * kStagingBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kEpiWarps * kStagingBytes);  // same 32 KB for kEW = 16 (2 KB tiles)
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + p.stages;
     uint64_t* tfull_bar = bars + 2 * p.stages;
@@ -232,7 +237,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], kEpiWarps);
+            mbar_init(&tempty_bar[i], kEW);
         }
         fence_barrier_init();
     }
@@ -343,7 +348,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;   // TMEM lane quarter this warp may touch
         const int half = e >> 2;  // which of the two warps sharing that quarter
         const int r = q * 32 + lane;
-        uint8_t* stg = staging + e * kStagingBytes;
+        uint8_t* stg = staging + e * (kEW == 16 ? kStagingBytes / 2 : kStagingBytes);
         const int half_bn = p.bn >> 1;
         uint32_t iter = 0;
         int mt, nt;
@@ -431,7 +436,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * acc_stride;
 
-            if (p.tma_out) {
+            if constexpr (kEW == 16) {
+                // GEGLU, LINEAR mode: warp (q, sub) drains the 32-column half-chunks sub, sub + 4, ... of its lane quarter
+                const int sub = e >> 2;
+                const int n_units = (out_cols + 31) >> 5;
+#pragma unroll 1
+                for (int u = sub; u < n_units; u += 4) {
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+                    const int col0 = u * 32;
+                    uint32_t a8[8], g8[8];
+                    tmem_ld_32x8(taddr + col0, a8);
+                    tmem_ld_32x8(taddr + half_bn + col0, g8);
+#pragma unroll 1
+                    for (int g = 0; g < 4; ++g) {
+                        H8 bv, bg;
+                        bv.u = make_uint4(0, 0, 0, 0);
+                        bg.u = make_uint4(0, 0, 0, 0);
+                        if (p.bias) {
+                            const int nb = nt * p.bn + col0 + g * 8;
+                            bv.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nb));
+                            bg.u = __ldg(reinterpret_cast<const uint4*>(p.bias + nb + half_bn));
+                        }
+                        tmem_ld_wait();
+                        float va[8], ga[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            va[j] = __uint_as_float(a8[j]);
+                            ga[j] = __uint_as_float(g8[j]);
+                        }
+                        if (g < 3) {
+                            tmem_ld_32x8(taddr + col0 + (g + 1) * 8, a8);
+                            tmem_ld_32x8(taddr + half_bn + col0 + (g + 1) * 8, g8);
+                        }
+                        H8 o;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float y0 = (va[2 * j] + __half2float(bv.h[2 * j])) *
+                                             gelu_erf_relu_form(ga[2 * j] + __half2float(bg.h[2 * j]));
+                            const float y1 = (va[2 * j + 1] + __half2float(bv.h[2 * j + 1])) *
+                                             gelu_erf_relu_form(ga[2 * j + 1] + __half2float(bg.h[2 * j + 1]));
+                            o.h2[j] = __floats2half2_rn(y0, y1);
+                        }
+                        // 64-byte rows, SWIZZLE_64B: 16-byte chunk g of row r lives at chunk g ^ ((r >> 1) & 3)
+                        *reinterpret_cast<uint4*>(stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = o.u;
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmOut, stg, nt * out_cols_tile + col0, static_cast<int>(tc.m0) + q * 32);
+                        tma_store_commit();
+                    }
+                }
+            } else if (p.tma_out) {
                 const int n_chunks = (out_cols + 63) >> 6;
 #pragma unroll 1
                 for (int c = half; c < n_chunks; c += 2) {
@@ -779,7 +836,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         done = atomicAdd(&s_gn_cnt[buf], 1);
                     }
                     done = __shfl_sync(0xffffffffu, done, 0);
-                    if (done == kEpiWarps - 1) {
+                    if (done == kEW - 1) {
                         __threadfence_block();
                         float* sb = s_gn + buf * kGnSlots * kGnGroups * 2;
                         for (int i = lane; i < kGnSlots * kGnGroups; i += 32) {
@@ -833,8 +890,16 @@ static PFN_tmapEncodeTiled get_encode_fn() {
 }
 
 // fp16 tensor map, SWIZZLE_128B, inner box = 64 elements (128 B); dims innermost first
+int make_tmap_f16_sw(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, CUtensorMapSwizzle swizzle);
+
 int make_tmap_f16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box) {
+    return make_tmap_f16_sw(m, ptr, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int make_tmap_f16_sw(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, CUtensorMapSwizzle swizzle) {
     PFN_tmapEncodeTiled fn = get_encode_fn();
     if (!fn) return MOFA_ERR_CUDA;
     cuuint64_t gdims[5];
@@ -859,7 +924,7 @@ int make_tmap_f16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dim
         }
     }
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(ptr), gdims,
-                    gstrides, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    gstrides, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu %llu %llu)", (int)r,
@@ -1004,8 +1069,13 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
         if (tma_out) {
             uint64_t od[2] = {static_cast<uint64_t>(n_out_cols), static_cast<uint64_t>(a->M)};
             uint64_t os[1] = {ldc_b};
-            uint32_t ob[2] = {64, 32};
-            if ((rc = make_tmap_f16(&tmOut, a->out, 2, od, os, ob)) != MOFA_OK) return rc;
+            if (geglu && kGeglu16) {   // 16 epilogue warps: {32 columns, 32 rows} stores out of 64-byte-row staging tiles
+                uint32_t ob[2] = {32, 32};
+                if ((rc = make_tmap_f16_sw(&tmOut, a->out, 2, od, os, ob, CU_TENSOR_MAP_SWIZZLE_64B)) != MOFA_OK) return rc;
+            } else {
+                uint32_t ob[2] = {64, 32};
+                if ((rc = make_tmap_f16(&tmOut, a->out, 2, od, os, ob)) != MOFA_OK) return rc;
+            }
         }
     } else if (a->mode == MOFA_A_CONV3X3) {
         if (a->n_img <= 0 || a->H <= 0 || a->W <= 0 || a->C <= 0 || (a->C % BK) != 0) {
@@ -1118,8 +1188,8 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
     if (total < grid) grid = static_cast<int>(total);
 
     using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmKernelParams);
-    static const Kern kernels[4] = {gemm_tc_kernel<0, false>, gemm_tc_kernel<0, true>, gemm_tc_kernel<1, false>,
-                                    gemm_tc_kernel<2, false>};
+    static const Kern kernels[5] = {gemm_tc_kernel<0, false, 8>, gemm_tc_kernel<0, true, 8>, gemm_tc_kernel<1, false, 8>,
+                                    gemm_tc_kernel<2, false, 8>, gemm_tc_kernel<1, false, 16>};
     static bool configured = false;
     if (!configured) {
         for (Kern k : kernels) {
@@ -1135,7 +1205,10 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
         set_last_error("mofa_gemm: gn_stats is implemented for the plain epilogue (act 0), got act %d", a->act);
         return MOFA_ERR_ARG;
     }
-    const Kern kern = geglu ? kernels[2] : (a->act != 0 ? kernels[3] : (p.gn_stats ? kernels[1] : kernels[0]));
-    kern<<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, tmOut, p);
+    const bool geglu16 = geglu && kGeglu16 && a->mode == MOFA_A_LINEAR;
+    const Kern kern = geglu16 ? kernels[4]
+                      : geglu ? kernels[2]
+                              : (a->act != 0 ? kernels[3] : (p.gn_stats ? kernels[1] : kernels[0]));
+    kern<<<grid, geglu16 ? 64 + 32 * 16 : kGemmThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, tmOut, p);
     return check_launch("mofa_gemm");
 }
