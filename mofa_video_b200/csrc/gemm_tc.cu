@@ -24,6 +24,7 @@
 // exposed residual-load latency dominating K=320 GEMMs (15 % tensor-pipe).  Hence the compact loops here.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/mofa_b200.h"
 #include "common.cuh"
@@ -38,7 +39,7 @@ constexpr uint32_t kABytes = BM * BK * 2;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kStagingBytes = 4096;  // 32 rows x 128 B per epilogue warp
 constexpr bool kGeglu16 = true;           // GEGLU (LINEAR mode) on the 16-epilogue-warp instantiation (A/B switch)
-constexpr bool kGegluCompact = true;      // rolled 8-column GEGLU epilogue (A/B switch; see the epilogue)
+constexpr bool kGegluCompact = false;     // rolled 8-column GEGLU body in the 8-warp kernel too (measured: K >= 640 slower)
 constexpr int kGnSlots = 2;               // statistics (frames / batch items) one M tile may span in shared memory
 constexpr int kGnGroups = 32;             // groups one N tile may span in shared memory
 constexpr int kGnBufs = 3;                // tiles in flight: an epilogue warp is at most 2 tiles ahead of another (2 TMEM stages)
@@ -72,6 +73,7 @@ struct GemmKernelParams {
     float* gn_stats;            // GroupNorm statistics of the output (see mofa_gemm_args.gn_stats) or nullptr
     long long gn_rows_per_stat;
     int gn_groups, gn_cpg, gn_c_off;
+    int gn_debug;               // MOFA_GN_DEBUG (profiling experiments): 1 = no shared-memory adds, 2 = no row loop either
 };
 
 struct TileCoord {
@@ -704,7 +706,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if constexpr (kStats) {
+                    if constexpr (kStats) if (p.gn_debug < 3) {
                         // GroupNorm statistics of what was just staged (the fp16-rounded outputs the consumer will read):
                         // lane l owns the column pair (2l, 2l+1) of this 64-column chunk and walks the warp's 32 rows of
                         // the swizzled staging tile (one 128-byte row per step: conflict-free), fp32 sums; a group never
@@ -743,7 +745,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const int first_lane = 31 - __clz(firsts & (0xffffffffu >> (31 - lane)));
                             const float bs = __shfl_sync(0xffffffffu, ps, (first_lane + 31) & 31);
                             const float bq = __shfl_sync(0xffffffffu, pq, (first_lane + 31) & 31);
-                            if (is_last && gkey >= 0) {
+                            if (is_last && gkey >= 0 && p.gn_debug < 1) {
                                 const float ts = first_lane > 0 ? ps - bs : ps, tq = first_lane > 0 ? pq - bq : pq;
                                 if (to_smem) {
                                     const uint32_t d = smem_u32(s_gn) + static_cast<uint32_t>(
@@ -761,7 +763,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint32_t chunk = lane >> 2;
                         int seg_row = -1;
 #pragma unroll 4
-                        for (int rr = 0; rr < 32; ++rr) {
+                        for (int rr = 0; rr < (p.gn_debug >= 2 ? 1 : 32); ++rr) {
                             if (!((vmask >> rr) & 1u)) continue;                      // warp-uniform
                             if (seg_row >= 0 && ((bmask >> rr) & 1u)) {               // statistic index changes here
                                 add_stat(__shfl_sync(0xffffffffu, gn_st, seg_row));
@@ -1020,6 +1022,14 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
             return MOFA_ERR_ARG;
         }
         p.gn_stats = a->gn_stats;
+        {
+            static int dbg = -1;
+            if (dbg < 0) {
+                const char* e = getenv("MOFA_GN_DEBUG");
+                dbg = e ? atoi(e) : 0;
+            }
+            p.gn_debug = dbg;
+        }
         p.gn_rows_per_stat = a->gn_rows_per_stat;
         p.gn_groups = a->gn_groups;
         p.gn_cpg = a->gn_cpg;
@@ -1069,7 +1079,7 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
         if (tma_out) {
             uint64_t od[2] = {static_cast<uint64_t>(n_out_cols), static_cast<uint64_t>(a->M)};
             uint64_t os[1] = {ldc_b};
-            if (geglu && kGeglu16) {   // 16 epilogue warps: {32 columns, 32 rows} stores out of 64-byte-row staging tiles
+            if (geglu && kGeglu16 && a->K <= 384) {   // 16 epilogue warps: {32 columns, 32 rows} stores out of 64-byte-row staging tiles
                 uint32_t ob[2] = {32, 32};
                 if ((rc = make_tmap_f16_sw(&tmOut, a->out, 2, od, os, ob, CU_TENSOR_MAP_SWIZZLE_64B)) != MOFA_OK) return rc;
             } else {
@@ -1205,7 +1215,9 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
         set_last_error("mofa_gemm: gn_stats is implemented for the plain epilogue (act 0), got act %d", a->act);
         return MOFA_ERR_ARG;
     }
-    const bool geglu16 = geglu && kGeglu16 && a->mode == MOFA_A_LINEAR;
+    // 16 epilogue warps where the epilogue is the bottleneck (5 k-blocks per tile at K = 320: 690 -> 916 TFLOP/s); with
+    // longer main loops the 8-warp unrolled body is faster (K = 640: 1180 vs 1092, K = 1280: 1410 vs 1333)
+    const bool geglu16 = geglu && kGeglu16 && a->mode == MOFA_A_LINEAR && a->K <= 384;
     const Kern kern = geglu16 ? kernels[4]
                       : geglu ? kernels[2]
                               : (a->act != 0 ? kernels[3] : (p.gn_stats ? kernels[1] : kernels[0]));

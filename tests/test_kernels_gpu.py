@@ -94,14 +94,21 @@ def test_gemm_geglu(bn):
     lib = L()
     M, K, N = 600, 320, 2560
     a, w, bias = rnd(M, K, scale=0.5), rnd(N, K, scale=0.05), rnd(N, scale=0.1)
-    res = rnd(M, N // 2)
     out = torch.zeros(M, N // 2, dtype=torch.half, device=DEV)
     ref = torch.zeros_like(out)
-    kw = dict(bias=bias, act=R.ACT_GEGLU, bn=bn, res1=res, beta1=1.0)
-    lib.linear(a, w, out, **kw)
+    kw = dict(bias=bias, act=R.ACT_GEGLU, bn=bn)
+    lib.linear(a, w, out, **kw)                    # K = 320: the 16-epilogue-warp instantiation
     R.linear(a, w, ref, **kw)
     torch.cuda.synchronize()
     close(out, ref, 2e-2, 1e-2, "geglu")
+    K2 = 640                                       # K = 640: the 8-warp instantiation
+    a2, w2 = rnd(M, K2, scale=0.4), rnd(N, K2, scale=0.04)
+    lib.linear(a2, w2, out, **kw)
+    R.linear(a2, w2, ref, **kw)
+    torch.cuda.synchronize()
+    close(out, ref, 2e-2, 1e-2, "geglu K=640")
+    with pytest.raises(RuntimeError):              # GEGLU carries a bias only
+        lib.linear(a, w, out, res1=rnd(M, N // 2), **kw)
 
 
 @pytest.mark.parametrize("n_img,H,W,C,N", [
