@@ -759,28 +759,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 }
                             }
                         };
-                        const uint32_t lane_base = smem_u32(stg) + ((lane & 3) << 2);
+                        const uint8_t* lane_ptr = stg + ((lane & 3) << 2);
                         const uint32_t chunk = lane >> 2;
-                        int seg_row = -1;
-#pragma unroll 4
-                        for (int rr = 0; rr < (p.gn_debug >= 2 ? 1 : 32); ++rr) {
-                            if (!((vmask >> rr) & 1u)) continue;                      // warp-uniform
-                            if (seg_row >= 0 && ((bmask >> rr) & 1u)) {               // statistic index changes here
-                                add_stat(__shfl_sync(0xffffffffu, gn_st, seg_row));
-                                s0 = s1 = q0 = q1 = 0.f;
-                                seg_row = rr;
+                        if (vmask == 0xffffffffu && bmask == 0u && p.gn_debug < 2) {
+                            // common case -- 32 valid rows of one statistic: straight-line, all 32 loads independent
+                            // (a rolled loop with one load per trip cost 0.21 ms per level-0 temporal-conv launch: its 170
+                            // clocks per trip were the load-to-use latency, serialised; profiles/r2_gnstats_experiments.txt)
+                            uint32_t hv[32];
+#pragma unroll
+                            for (int rr = 0; rr < 32; ++rr)
+                                hv[rr] = *reinterpret_cast<const uint32_t*>(lane_ptr + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+                            float t0 = 0.f, t1 = 0.f, u0 = 0.f, u1 = 0.f;   // second accumulator set: shorter add chains
+#pragma unroll
+                            for (int rr = 0; rr < 32; rr += 2) {
+                                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hv[rr]));
+                                const float2 g2 = __half22float2(*reinterpret_cast<const __half2*>(&hv[rr + 1]));
+                                s0 += f.x;
+                                s1 += f.y;
+                                q0 = fmaf(f.x, f.x, q0);
+                                q1 = fmaf(f.y, f.y, q1);
+                                t0 += g2.x;
+                                t1 += g2.y;
+                                u0 = fmaf(g2.x, g2.x, u0);
+                                u1 = fmaf(g2.y, g2.y, u1);
                             }
-                            if (seg_row < 0) seg_row = rr;
-                            uint32_t hv;
-                            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(hv)
-                                         : "r"(lane_base + rr * 128 + ((chunk ^ (rr & 7)) << 4)));
-                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hv));
-                            s0 += f.x;
-                            s1 += f.y;
-                            q0 = fmaf(f.x, f.x, q0);
-                            q1 = fmaf(f.y, f.y, q1);
+                            s0 += t0;
+                            s1 += t1;
+                            q0 += u0;
+                            q1 += u1;
+                            add_stat(__shfl_sync(0xffffffffu, gn_st, 0));
+                        } else {
+                            int seg_row = -1;
+#pragma unroll 1
+                            for (int rr = 0; rr < (p.gn_debug >= 2 ? 1 : 32); ++rr) {
+                                if (!((vmask >> rr) & 1u)) continue;                      // warp-uniform
+                                if (seg_row >= 0 && ((bmask >> rr) & 1u)) {               // statistic index changes here
+                                    add_stat(__shfl_sync(0xffffffffu, gn_st, seg_row));
+                                    s0 = s1 = q0 = q1 = 0.f;
+                                    seg_row = rr;
+                                }
+                                if (seg_row < 0) seg_row = rr;
+                                const uint32_t hv =
+                                    *reinterpret_cast<const uint32_t*>(lane_ptr + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+                                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hv));
+                                s0 += f.x;
+                                s1 += f.y;
+                                q0 = fmaf(f.x, f.x, q0);
+                                q1 = fmaf(f.y, f.y, q1);
+                            }
+                            if (seg_row >= 0) add_stat(__shfl_sync(0xffffffffu, gn_st, seg_row));
                         }
-                        if (seg_row >= 0) add_stat(__shfl_sync(0xffffffffu, gn_st, seg_row));
                     }
                     if (lane == 0) {
                         const int n0 = nt * out_cols_tile + c * 64;
