@@ -432,13 +432,68 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             };
             // (not in the statistics kernel: its extra state would spill; its GEMMs are main-loop bound convolutions)
             constexpr bool kPrefetchRes = !kStats;
-            if (kPrefetchRes && p.tma_out && has1 && half * 64 < out_cols) load_r1(half, 0);
+            if (kEW == 8 && kPrefetchRes && p.tma_out && has1 && half * 64 < out_cols) load_r1(half, 0);
 
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * acc_stride;
 
-            if constexpr (kEW == 16) {
+            if constexpr (kEW == 16 && kEpi == 0) {
+                // plain epilogue, LINEAR mode, short K (the q|k|v / out / in projections at K = 320 are epilogue- and
+                // latency-bound): warp (q, sub) drains the 32-column units sub, sub + 4, ... in two 16-column passes
+                const int sub = e >> 2;
+                const int n_units = (out_cols + 31) >> 5;
+#pragma unroll 1
+                for (int u = sub; u < n_units; u += 4) {
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+#pragma unroll 1
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int col0 = u * 32 + hh * 16;
+                        const int n0 = nt * p.bn + col0;       // global output column (= bias column: plain epilogue)
+                        uint4 r1v[2], r2v[2], rbv[2], bvv[2];
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            const bool in = n0 + g * 8 < p.N_out;
+                            r1v[g] = r2v[g] = rbv[g] = bvv[g] = make_uint4(0, 0, 0, 0);
+                            if (has1 && valid && in)
+                                r1v[g] = __ldg(reinterpret_cast<const uint4*>(p.res1 + row * p.ldr1 + n0) + g);
+                            if (has2 && valid && in)
+                                r2v[g] = __ldg(reinterpret_cast<const uint4*>(p.res2 + row * p.ldr2 + n0) + g);
+                            if (p.rowbias && in)
+                                rbv[g] = __ldg(reinterpret_cast<const uint4*>(p.rowbias + group * p.ld_rowbias + n0) + g);
+                            if (p.bias && in) bvv[g] = __ldg(reinterpret_cast<const uint4*>(p.bias + n0) + g);
+                        }
+                        uint32_t acc[16];
+                        tmem_ld_32x16(taddr + col0, acc);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            H8 b, rb, a1, a2, o;
+                            b.u = bvv[g];
+                            rb.u = rbv[g];
+                            a1.u = r1v[g];
+                            a2.u = r2v[g];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float x = __uint_as_float(acc[g * 8 + j]) + __half2float(b.h[j]) + __half2float(rb.h[j]);
+                                x *= p.alpha;
+                                x = fmaf(p.beta1, __half2float(a1.h[j]), x);
+                                x = fmaf(p.beta2, __half2float(a2.h[j]), x);
+                                o.h[j] = __float2half_rn(x);
+                            }
+                            const int ci = hh * 2 + g;   // 16-byte chunk of the 64-byte staging row (SWIZZLE_64B)
+                            *reinterpret_cast<uint4*>(stg + lane * 64 + ((ci ^ ((lane >> 1) & 3)) << 4)) = o.u;
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmOut, stg, nt * p.bn + u * 32, static_cast<int>(tc.m0) + q * 32);
+                        tma_store_commit();
+                    }
+                }
+            } else if constexpr (kEW == 16) {
                 // GEGLU, LINEAR mode: warp (q, sub) drains the 32-column half-chunks sub, sub + 4, ... of its lane quarter
                 const int sub = e >> 2;
                 const int n_units = (out_cols + 31) >> 5;
@@ -994,6 +1049,9 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
     }
     const bool geglu = a->act == 2;
     const int bn = a->bn;
+    // 16 epilogue warps (LINEAR mode, K <= 384: five or six k-blocks per tile, the epilogue is the bottleneck): GEGLU and the
+    // plain epilogue without GroupNorm statistics
+    const bool short_k = a->mode == MOFA_A_LINEAR && a->K <= 384 && !a->a2;
     if (bn < 16 || bn > 256 || (bn % 16) != 0 || (geglu && (bn % 128) != 0)) {
         set_last_error("mofa_gemm: unsupported bn=%d (act=%d)", bn, a->act);
         return MOFA_ERR_ARG;
@@ -1017,6 +1075,8 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
         return MOFA_ERR_ARG;
     }
 
+    const bool use_ew16 = kGeglu16 && short_k && tma_out && (geglu || (a->act == 0 && !a->gn_stats)) &&
+                          ((geglu ? bn / 2 : bn) % 32) == 0;
     GemmKernelParams p;
     memset(&p, 0, sizeof(p));
     p.mode = a->mode;
@@ -1107,7 +1167,7 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
         if (tma_out) {
             uint64_t od[2] = {static_cast<uint64_t>(n_out_cols), static_cast<uint64_t>(a->M)};
             uint64_t os[1] = {ldc_b};
-            if (geglu && kGeglu16 && a->K <= 384) {   // 16 epilogue warps: {32 columns, 32 rows} stores out of 64-byte-row staging tiles
+            if (use_ew16) {   // 16 epilogue warps: {32 columns, 32 rows} stores out of 64-byte-row staging tiles
                 uint32_t ob[2] = {32, 32};
                 if ((rc = make_tmap_f16_sw(&tmOut, a->out, 2, od, os, ob, CU_TENSOR_MAP_SWIZZLE_64B)) != MOFA_OK) return rc;
             } else {
@@ -1226,8 +1286,9 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
     if (total < grid) grid = static_cast<int>(total);
 
     using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmKernelParams);
-    static const Kern kernels[5] = {gemm_tc_kernel<0, false, 8>, gemm_tc_kernel<0, true, 8>, gemm_tc_kernel<1, false, 8>,
-                                    gemm_tc_kernel<2, false, 8>, gemm_tc_kernel<1, false, 16>};
+    static const Kern kernels[6] = {gemm_tc_kernel<0, false, 8>, gemm_tc_kernel<0, true, 8>, gemm_tc_kernel<1, false, 8>,
+                                    gemm_tc_kernel<2, false, 8>, gemm_tc_kernel<1, false, 16>,
+                                    gemm_tc_kernel<0, false, 16>};
     static bool configured = false;
     if (!configured) {
         for (Kern k : kernels) {
@@ -1243,12 +1304,12 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
         set_last_error("mofa_gemm: gn_stats is implemented for the plain epilogue (act 0), got act %d", a->act);
         return MOFA_ERR_ARG;
     }
-    // 16 epilogue warps where the epilogue is the bottleneck (5 k-blocks per tile at K = 320: 690 -> 916 TFLOP/s); with
-    // longer main loops the 8-warp unrolled body is faster (K = 640: 1180 vs 1092, K = 1280: 1410 vs 1333)
-    const bool geglu16 = geglu && kGeglu16 && a->mode == MOFA_A_LINEAR && a->K <= 384;
-    const Kern kern = geglu16 ? kernels[4]
-                      : geglu ? kernels[2]
-                              : (a->act != 0 ? kernels[3] : (p.gn_stats ? kernels[1] : kernels[0]));
+    // 16 epilogue warps where the epilogue is the bottleneck (5 k-blocks per tile at K = 320: GEGLU 690 -> 916 TFLOP/s); with
+    // longer main loops the 8-warp unrolled body is faster (GEGLU K = 640: 1180 vs 1092, K = 1280: 1410 vs 1333)
+    const bool geglu16 = use_ew16;
+    const Kern kern = use_ew16 ? (geglu ? kernels[4] : kernels[5])
+                      : geglu  ? kernels[2]
+                               : (a->act != 0 ? kernels[3] : (p.gn_stats ? kernels[1] : kernels[0]));
     kern<<<grid, geglu16 ? 64 + 32 * 16 : kGemmThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, tmOut, p);
     return check_launch("mofa_gemm");
 }

@@ -146,6 +146,24 @@ def test_gemm_temporal3(B, T, HW, C, N):
     close(out, ref, 3e-2, 1e-2, f"temporal3 {B}x{T}x{HW}x{C}->{N}")
 
 
+@pytest.mark.parametrize("M,K,N", [(700, 320, 960), (1000, 320, 320), (300, 72, 320), (513, 384, 96), (260, 128, 1280)])
+def test_gemm_linear_short_k_16_epilogue_warps(M, K, N):
+    """LINEAR, K <= 384, plain epilogue: the 16-epilogue-warp instantiation (32-column units, SWIZZLE_64B staging)."""
+    lib = L()
+    a, w = rnd(M, K, scale=0.5), rnd(N, K, scale=0.05)
+    bias, res1, res2 = rnd(N, scale=0.2), rnd(M, N), rnd(M, N)
+    out = torch.zeros(M, N, dtype=torch.half, device=DEV)
+    ref = torch.zeros_like(out)
+    for kw in (dict(bias=bias), dict(bias=bias, res1=res1, res2=res2, alpha=0.7, beta1=0.5, beta2=-1.25),
+               dict(bias=bias, res1=res1, rowbias=rnd(4, N), rows_per_group=(M + 3) // 4),
+               dict(res1=res1, rowbias=rnd(3, N), rowbias_mod=3, alpha=1.5), dict()):
+        out.zero_()
+        lib.linear(a, w, out, **kw)
+        R.linear(a, w, ref, **kw)
+        torch.cuda.synchronize()
+        close(out, ref, 2e-2, 1e-2, f"short-K linear {M}x{K}x{N} {sorted(kw)}")
+
+
 @pytest.mark.parametrize("n_img,H,W,C,N", [
     (50, 9, 16, 64, 128),    # level 3 of 576x1024: tiles of {16 px, 1 row, 8 images}; 50 images = 6 full groups + 2
     (6, 8, 8, 64, 64),       # level 3 of 512x512: two whole images per tile
