@@ -1075,7 +1075,10 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
         return MOFA_ERR_ARG;
     }
 
-    const bool use_ew16 = kGeglu16 && short_k && tma_out && (geglu || (a->act == 0 && !a->gn_stats)) &&
+    // (plain: only with a residual -- its per-row loads are what the extra warps hide: out-projection with row bias + residual
+    //  295 -> 360 TFLOP/s; the residual-free q|k|v projection is faster on 8 warps with 64-column stores: 786 vs 630)
+    const bool use_ew16 = kGeglu16 && short_k && tma_out &&
+                          (geglu || (a->act == 0 && !a->gn_stats && a->res1 != nullptr)) &&
                           ((geglu ? bn / 2 : bn) % 32) == 0;
     GemmKernelParams p;
     memset(&p, 0, sizeof(p));

@@ -154,7 +154,7 @@ def test_gemm_linear_short_k_16_epilogue_warps(M, K, N):
     bias, res1, res2 = rnd(N, scale=0.2), rnd(M, N), rnd(M, N)
     out = torch.zeros(M, N, dtype=torch.half, device=DEV)
     ref = torch.zeros_like(out)
-    for kw in (dict(bias=bias), dict(bias=bias, res1=res1, res2=res2, alpha=0.7, beta1=0.5, beta2=-1.25),
+    for kw in (dict(bias=bias, res1=res1), dict(bias=bias, res1=res1, res2=res2, alpha=0.7, beta1=0.5, beta2=-1.25),
                dict(bias=bias, res1=res1, rowbias=rnd(4, N), rows_per_group=(M + 3) // 4),
                dict(res1=res1, rowbias=rnd(3, N), rowbias_mod=3, alpha=1.5), dict()):
         out.zero_()
