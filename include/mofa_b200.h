@@ -247,6 +247,16 @@ int mofa_flow_post(const void* flow_in, const void* brush, const void* flow_out,
 int mofa_resize_antialias(const void* img, void* out, int32_t planes, int32_t H, int32_t W, int32_t Ho, int32_t Wo,
                           mofa_stream_t stream);
 
+/* Fused FeedForward of a transformer block (diffusers 0.24 FeedForward(activation_fn="geglu"): GEGLU projection, GELU gate,
+ * output Linear; blocks built at unet_spatio_temporal_condition_controlnet.py:169-233 / controlnet_sdv.py:270-309), for
+ * C <= 320 (SVD level 0):  out = alpha * (GEGLU(x W1^T + b1) W2^T + b2) + beta1 * res1 + beta2 * res2.
+ * x [M, C]; w1_packed [2*hidden, C] and b1_packed [2*hidden] in the GEGLU packing with bn = 128 (per 128 rows: 64 value rows,
+ * then their 64 gate rows); w2 [C, hidden]; b2 [C]; out, res1, res2 [M, C] (rows of ldr elements).  The hidden activation
+ * stays in tensor memory (second GEMM's A operand), so the [M, hidden] intermediate is never written. */
+int mofa_ff_geglu(const void* x, const void* w1_packed, const void* b1_packed, const void* w2, const void* b2, void* out,
+                  int64_t M, int32_t C, int32_t hidden, const void* res1, int64_t ldr1, const void* res2, int64_t ldr2,
+                  float alpha, float beta1, float beta2, mofa_stream_t stream);
+
 /* Multi-head self-attention for small sequences and head dims other than 64 (CLIP ViT-H/14 image encoder of
  * /root/reference/MOFA-Video-Traj/pipeline/pipeline.py:114-141: 16 heads x 80, 257 tokens): qkv fp16 [n_seq, L, 3*C]
  * (q | k | v per token, C = heads * head_dim), out fp16 [n_seq, L, C]; softmax(q k^T * scale) v in fp32. */

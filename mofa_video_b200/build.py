@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmofa_b200.so")
-SOURCES = ["runtime.cu", "gemm_tc.cu", "attn_spatial.cu", "attn_temporal.cu", "attn_small.cu", "elementwise.cu", "softsplat.cu", "cmp_ops.cu"]
+SOURCES = ["runtime.cu", "gemm_tc.cu", "ff_fused.cu", "attn_spatial.cu", "attn_temporal.cu", "attn_small.cu", "elementwise.cu", "softsplat.cu", "cmp_ops.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",

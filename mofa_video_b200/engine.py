@@ -279,11 +279,16 @@ class Net:
 
         t["s_n1"], t["s_qkv"], t["s_o"] = pk.norm(sb + ".norm1"), qkv(sb + ".attn1"), pk.lin(sb + ".attn1.to_out.0")
         t["s_x"] = xattn(sb + ".attn2")
-        t["s_n3"], t["s_ff1"], t["s_ff2"] = pk.norm(sb + ".norm3"), pk.geglu(sb + ".ff.net.0.proj", self.pk_bn), pk.lin(sb + ".ff.net.2")
-        t["t_nin"], t["t_ffi1"], t["t_ffi2"] = pk.norm(tb + ".norm_in"), pk.geglu(tb + ".ff_in.net.0.proj", self.pk_bn), pk.lin(tb + ".ff_in.net.2")
+        # FeedForward blocks of width C <= 320 run as ONE fused kernel (mofa_ff_geglu) whose first projection is packed with
+        # 128-row GEGLU groups; wider ones as two GEMMs with the widest tile that divides 8C
+        fused = C <= getattr(self.ops, "FF_FUSED_MAX_C", 0) and hasattr(self.ops, "ff_geglu")
+        t["ff_fused"] = fused
+        ff_bn = (lambda n, geglu=True: 128) if fused else self.pk_bn
+        t["s_n3"], t["s_ff1"], t["s_ff2"] = pk.norm(sb + ".norm3"), pk.geglu(sb + ".ff.net.0.proj", ff_bn), pk.lin(sb + ".ff.net.2")
+        t["t_nin"], t["t_ffi1"], t["t_ffi2"] = pk.norm(tb + ".norm_in"), pk.geglu(tb + ".ff_in.net.0.proj", ff_bn), pk.lin(tb + ".ff_in.net.2")
         t["t_n1"], t["t_qkv"], t["t_o"] = pk.norm(tb + ".norm1"), qkv(tb + ".attn1"), pk.lin(tb + ".attn1.to_out.0")
         t["t_x"] = xattn(tb + ".attn2")
-        t["t_n3"], t["t_ff1"], t["t_ff2"] = pk.norm(tb + ".norm3"), pk.geglu(tb + ".ff.net.0.proj", self.pk_bn), pk.lin(tb + ".ff.net.2")
+        t["t_n3"], t["t_ff1"], t["t_ff2"] = pk.norm(tb + ".norm3"), pk.geglu(tb + ".ff.net.0.proj", ff_bn), pk.lin(tb + ".ff.net.2")
         t["pos"] = pk.h(_frame_pos_embed(pk.sd, pre + ".time_pos_embed", C, self.T))
         t["alpha"] = torch.sigmoid(pk.get(pre + ".time_mixer.mix_factor").float()).item()
         return t
@@ -438,19 +443,27 @@ class Net:
         h2 = self.new(rows, C)
         lin(a, t["s_o"][0], h2, bias=t["s_o"][1], res1=h, rowbias=self.xvec[t["s_x"]], rows_per_group=T * hw)
         ops.layernorm(h2, t["s_n3"][0], t["s_n3"][1], hn, 1e-5)
+        fused = t["ff_fused"]
         w1, b1, bn = t["s_ff1"]
-        f = self.new(rows, 4 * C)
-        lin(hn, w1, f, bias=b1, act=ops.ACT_GEGLU, bn=bn)
         hsp = self.new(rows, C)
-        lin(f, t["s_ff2"][0], hsp, bias=t["s_ff2"][1], res1=h2)
+        if fused:   # GEGLU -> Linear in one kernel: the [rows, 4C] activation stays in tensor memory
+            f = None
+            ops.ff_geglu(hn, w1, b1, t["s_ff2"][0], t["s_ff2"][1], hsp, res1=h2)
+        else:
+            f = self.new(rows, 4 * C)
+            lin(hn, w1, f, bias=b1, act=ops.ACT_GEGLU, bn=bn)
+            lin(f, t["s_ff2"][0], hsp, bias=t["s_ff2"][1], res1=h2)
         # ---- temporal block on x_mix = h_spatial + frame position embedding (row order stays (b,t,p))
         hmix = self.new(rows, C)
         ops.layernorm(hsp, t["t_nin"][0], t["t_nin"][1], hn, 1e-5, add=t["pos"], rows_per_group=hw, add_period=T,
                       sum_out=hmix)
         w1, b1, bn = t["t_ffi1"]
-        lin(hn, w1, f, bias=b1, act=ops.ACT_GEGLU, bn=bn)
         g = self.new(rows, C)
-        lin(f, t["t_ffi2"][0], g, bias=t["t_ffi2"][1], res1=hmix)
+        if fused:
+            ops.ff_geglu(hn, w1, b1, t["t_ffi2"][0], t["t_ffi2"][1], g, res1=hmix)
+        else:
+            lin(hn, w1, f, bias=b1, act=ops.ACT_GEGLU, bn=bn)
+            lin(f, t["t_ffi2"][0], g, bias=t["t_ffi2"][1], res1=hmix)
         ops.layernorm(g, t["t_n1"][0], t["t_n1"][1], hn, 1e-5)
         lin(hn, t["t_qkv"], qkv)
         if d == 64 and T <= 32:
@@ -463,11 +476,16 @@ class Net:
         lin(a, t["t_o"][0], g2, bias=t["t_o"][1], res1=g, rowbias=self.xvec[t["t_x"]], rowbias_mod=B)
         ops.layernorm(g2, t["t_n3"][0], t["t_n3"][1], hn, 1e-5)
         w1, b1, bn = t["t_ff1"]
-        lin(hn, w1, f, bias=b1, act=ops.ACT_GEGLU, bn=bn)
         am = t["alpha"]
         mixed = self.new(rows, C)
         # AlphaBlender: am * h_spatial + (1-am) * (ff + g2)
-        lin(f, t["t_ff2"][0], mixed, bias=t["t_ff2"][1], alpha=1.0 - am, res1=g2, beta1=1.0 - am, res2=hsp, beta2=am)
+        if fused:
+            ops.ff_geglu(hn, w1, b1, t["t_ff2"][0], t["t_ff2"][1], mixed, res1=g2, res2=hsp, alpha=1.0 - am,
+                         beta1=1.0 - am, beta2=am)
+        else:
+            lin(hn, w1, f, bias=b1, act=ops.ACT_GEGLU, bn=bn)
+            lin(f, t["t_ff2"][0], mixed, bias=t["t_ff2"][1], alpha=1.0 - am, res1=g2, beta1=1.0 - am, res2=hsp,
+                beta2=am)
         out = self.new(rows, C)
         lin(mixed, t["proj_out"][0], out, bias=t["proj_out"][1], res1=x)
         return out

@@ -25,7 +25,7 @@ EXPORTS = [
     "mofa_vae_time_conv_out", "mofa_im2col", "mofa_pool2d", "mofa_resize_bilinear_ac", "mofa_cmp_fuser",
     "mofa_copy_cols", "mofa_flow_pyramid", "mofa_mask_blend", "mofa_downsample_nearest", "mofa_flow_post",
     "mofa_resize_antialias", "mofa_cfg_euler_step_dev", "mofa_sparse_hints", "mofa_peer_enable", "mofa_peer_signal", "mofa_peer_wait",
-    "mofa_attn_small", "mofa_attn_small_temporal",
+    "mofa_attn_small", "mofa_attn_small_temporal", "mofa_ff_geglu",
 ]
 
 
@@ -84,6 +84,7 @@ def load():
     lib.mofa_peer_enable.argtypes = [i32]
     lib.mofa_peer_signal.argtypes = [vp, ctypes.c_uint32, vp]
     lib.mofa_peer_wait.argtypes = [vp, i32, ctypes.c_uint32, ctypes.c_double, vp, vp]
+    lib.mofa_ff_geglu.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, i32, vp, i64, vp, i64, f32, f32, f32, vp]
     lib.mofa_attn_small.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp]
     lib.mofa_attn_small_temporal.argtypes = [vp, vp, i32, i32, i32, i32, i32, f32, vp]
     lib.mofa_softmax_rows.argtypes = [vp, i64, i32, i64, vp]
@@ -271,6 +272,24 @@ def attn_spatial(qkv, out, frames, L, heads, scale):
     _chk_h(qkv, out)
     with _Timed("attn_spatial", 4.0 * frames * heads * L * L * 64, f"L={L} heads={heads}"):
         _check(load().mofa_attn_spatial(_p(qkv), _p(out), frames, L, heads, scale, _stream()), "mofa_attn_spatial")
+    return out
+
+
+FF_FUSED_MAX_C = 320   # TMEM: the output accumulator (C columns) + 128 + 64 must fit 512
+
+
+def ff_geglu(x, w1_packed, b1_packed, w2, b2, out, res1=None, res2=None, alpha=1.0, beta1=1.0, beta2=1.0):
+    """Fused GEGLU FeedForward (mofa_ff_geglu): x [M, C] -> out [M, C]; w1_packed / b1_packed in the bn = 128 GEGLU packing."""
+    _chk_h(x, w1_packed, b1_packed, w2, b2, out, res1, res2)
+    M, C = x.shape
+    hidden = w2.shape[1]
+    assert w1_packed.shape == (2 * hidden, C) and w2.shape[0] == C and out.shape == (M, C)
+    work = 2.0 * M * C * hidden * 3
+    with _Timed("ff_geglu_fused", work, f"M={M} C={C} hidden={hidden} res={int(res1 is not None) + int(res2 is not None)}"):
+        _check(load().mofa_ff_geglu(_p(x), _p(w1_packed), _p(b1_packed), _p(w2), _p(b2), _p(out), M, C, hidden, _p(res1),
+                                    res1.shape[-1] if res1 is not None else 0, _p(res2),
+                                    res2.shape[-1] if res2 is not None else 0, alpha, beta1, beta2, _stream()),
+               "mofa_ff_geglu")
     return out
 
 

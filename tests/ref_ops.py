@@ -110,6 +110,25 @@ def attn_spatial(qkv, out, frames, L, heads, scale):
     return out
 
 
+FF_FUSED_MAX_C = 320
+
+
+def ff_geglu(x, w1_packed, b1_packed, w2, b2, out, res1=None, res2=None, alpha=1.0, beta1=1.0, beta2=1.0):
+    """mofa_ff_geglu: GEGLU projection (bn = 128 packing: per 128 rows 64 value then 64 gate) -> GELU gate -> Linear."""
+    hidden = w2.shape[1]
+    h = x.float() @ w1_packed.float().t() + (b1_packed.float() if b1_packed is not None else 0.0)
+    t = h.view(x.shape[0], hidden // 64, 2, 64)
+    hid = (t[:, :, 0] * F.gelu(t[:, :, 1])).reshape(x.shape[0], hidden).half().float()   # H is fp16 in tensor memory
+    v = hid @ w2.float().t() + (b2.float() if b2 is not None else 0.0)
+    v = alpha * v
+    if res1 is not None:
+        v = v + beta1 * res1.float()
+    if res2 is not None:
+        v = v + beta2 * res2.float()
+    out.copy_(v.half())
+    return out
+
+
 def attn_small(qkv, out, n_seq, L, heads, head_dim, scale):
     t = qkv.float().reshape(n_seq, L, 3, heads, head_dim).permute(2, 0, 3, 1, 4)
     q, k, v = t[0], t[1], t[2]

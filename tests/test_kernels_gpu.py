@@ -146,6 +146,34 @@ def test_gemm_temporal3(B, T, HW, C, N):
     close(out, ref, 3e-2, 1e-2, f"temporal3 {B}x{T}x{HW}x{C}->{N}")
 
 
+@pytest.mark.parametrize("M,C", [(1000, 320), (460, 64), (700, 256), (128, 192)])
+def test_ff_geglu_fused(M, C):
+    """mofa_ff_geglu (GEGLU projection -> GELU gate -> Linear, hidden activation kept in tensor memory) vs its statement,
+    and vs the two-GEMM path on the same packed weights."""
+    lib = L()
+    hidden = 4 * C
+    x = rnd(M, C, scale=0.7)
+    w1, b1 = rnd(2 * hidden, C, scale=0.08), rnd(2 * hidden, scale=0.2)
+    w2, b2 = rnd(C, hidden, scale=0.05), rnd(C, scale=0.2)
+    r1, r2 = rnd(M, C), rnd(M, C)
+    for kw in (dict(), dict(res1=r1), dict(res1=r1, res2=r2, alpha=0.6, beta1=0.6, beta2=0.4)):
+        out = torch.zeros(M, C, dtype=torch.half, device=DEV)
+        ref = torch.zeros_like(out)
+        lib.ff_geglu(x, w1, b1, w2, b2, out, **kw)
+        R.ff_geglu(x, w1, b1, w2, b2, ref, **kw)
+        torch.cuda.synchronize()
+        close(out, ref, 3e-2, 1e-2, f"fused FF M={M} C={C} {sorted(kw)}")
+    # the unfused path on the same weights (GEGLU GEMM with 128-row groups, then the output GEMM)
+    f = torch.empty(M, hidden, dtype=torch.half, device=DEV)
+    two = torch.empty(M, C, dtype=torch.half, device=DEV)
+    lib.linear(x, w1, f, bias=b1, act=lib.ACT_GEGLU, bn=128)
+    lib.linear(f, w2, two, bias=b2, res1=r1)
+    one = torch.empty_like(two)
+    lib.ff_geglu(x, w1, b1, w2, b2, one, res1=r1)
+    torch.cuda.synchronize()
+    close(one, two, 2e-2, 1e-2, "fused vs two GEMMs")
+
+
 @pytest.mark.parametrize("M,K,N", [(700, 320, 960), (1000, 320, 320), (300, 72, 320), (513, 384, 96), (260, 128, 1280)])
 def test_gemm_linear_short_k_16_epilogue_warps(M, K, N):
     """LINEAR, K <= 384, plain epilogue: the 16-epilogue-warp instantiation (32-column units, SWIZZLE_64B staging)."""

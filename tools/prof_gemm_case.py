@@ -59,6 +59,20 @@ elif case in ("temporal320", "temporal320_stats", "conv320_stats"):
         kw = dict(gn_stats=st, gn_rows_per_stat=HW) if case.endswith("_stats") else {}
         fn = lambda: lib.gemm(lib.A_TEMPORAL3, a, w, out, N=C, B=B, T=T, HW=HW, C=C, bias=b, res1=r, alpha=0.5, **kw)
         flops = 2.0 * rows * C * 3 * C
+elif case == "ff_fused":
+    x, w1, b1, w2, b2, r = h(M, 320), h(2560, 320), h(2560), h(320, 1280, scale=0.05), h(320), h(M, 320)
+    out = torch.empty(M, 320, dtype=torch.half, device=dev)
+    fn = lambda: lib.ff_geglu(x, w1, b1, w2, b2, out, res1=r)
+    flops = 2.0 * M * 320 * 1280 * 3
+elif case == "ff_unfused":
+    x, w1, b1, w2, b2, r = h(M, 320), h(2560, 320), h(2560), h(320, 1280, scale=0.05), h(320), h(M, 320)
+    f = torch.empty(M, 1280, dtype=torch.half, device=dev)
+    out = torch.empty(M, 320, dtype=torch.half, device=dev)
+
+    def fn():
+        lib.linear(x, w1, f, bias=b1, act=2, bn=256)
+        lib.linear(f, w2, out, bias=b2, res1=r)
+    flops = 2.0 * M * 320 * 1280 * 3
 for _ in range(2):
     fn()
 torch.cuda.synchronize()
