@@ -177,6 +177,71 @@ MOFA_DEVICE void umma_commit(uint64_t* bar) {
                  : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------
+// CTA pairs (cta_group::2): two CTAs of a cluster on the two SMs of a TPC issue ONE tcgen05.mma of M = 256.  Each CTA
+// stages its own 128 rows of A and HALF of the B rows, so the shared-memory traffic per SM and flop drops by a quarter to
+// a third; the accumulator rows 0..127 land in the even CTA's tensor memory, rows 128..255 in the odd CTA's.
+// Shared-memory addresses of the odd CTA carry bit 24 in the shared::cluster window; clearing it names the same offset
+// in the even (leader) CTA -- the convention the 2-SM TMA / commit forms rely on.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+MOFA_DEVICE uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+MOFA_DEVICE void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// loads into THIS CTA's shared memory, completion bytes counted on the LEADER CTA's mbarrier
+MOFA_DEVICE void tma_load_2d_2sm(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+MOFA_DEVICE void tma_load_4d_2sm(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+        "[%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// arrive on the mbarrier at this offset in the leader CTA (from either CTA of the pair)
+MOFA_DEVICE void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+// executed by one warp of EACH CTA of the pair (same warp index, same destination offset)
+MOFA_DEVICE void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+MOFA_DEVICE void tmem_dealloc_2sm(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[256 x N] (+)= A[256 x 16] * B[N x 16]^T: issued by ONE thread of the leader CTA; the descriptors name offsets that are
+// valid in both CTAs (A: that CTA's 128 rows, B: that CTA's N/2 rows)
+MOFA_DEVICE void umma_f16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the mbarrier at this offset in BOTH CTAs once the pair's previously issued MMAs have completed
+MOFA_DEVICE void umma_commit_2sm(uint64_t* bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(static_cast<uint16_t>(3))
+        : "memory");
+}
+
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread t holds row lane_base+t)
 MOFA_DEVICE void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -249,7 +314,14 @@ MOFA_DEVICE uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t lbo_by
     d |= 2ull << 61;
     return d;
 }
-// instruction descriptor: fp16 x fp16 -> fp32, M = 128
+// instruction descriptor: fp16 x fp16 -> fp32, M = 128 (or 256 for a CTA pair)
+MOFA_DEVICE uint32_t umma_idesc_f16_m(uint32_t n, uint32_t m) {
+    uint32_t d = 0;
+    d |= 1u << 4;           // D format: F32
+    d |= (n >> 3) << 17;    // N / 8
+    d |= (m >> 4) << 24;    // M / 16
+    return d;
+}
 MOFA_DEVICE uint32_t umma_idesc_f16(uint32_t n, bool b_mn_major) {
     uint32_t d = 0;
     d |= 1u << 4;                     // D format: F32

@@ -22,6 +22,7 @@
 //   warps 3..18 : epilogue; warp (quarter q, sub s) owns hidden columns [16 s, 16 s + 16) of every chunk and, at the end of a
 //                 tile, the 32-column output units s, s + 4, ... (bias, alpha, two residuals, SWIZZLE_64B staging, TMA store)
 #include "../../include/mofa_b200.h"
+#include <cstdlib>
 #include "common.cuh"
 
 namespace mofa {
@@ -34,7 +35,8 @@ int num_sms();
 
 namespace ff {
 
-constexpr int kW1Stages = 4;
+constexpr int kW1Stages = 5;      // one full chunk of W1 k-blocks (C = 320): the next chunk prefetches while this one computes
+constexpr int kStgBytes = 1024;   // output staging per epilogue warp: 32 rows x 16 columns
 constexpr int kEW = 16;
 constexpr int kThreads = 96 + 32 * kEW;
 constexpr uint32_t kTile16K = 128 * 64 * 2;
@@ -49,7 +51,23 @@ struct Params {
     const __half* res2;
     long long ldr2;
     float alpha, beta1, beta2;
+    int w1_stages;      // W1 ring depth actually used (<= kW1Stages)
+    int debug;          // experiment mask (env MOFA_FF_DEBUG): 1 skip S MMAs, 2 skip OUT MMAs, 4 skip the GEGLU math, 8 / 16 skip the W1 / W2 loads
 };
+
+__device__ long long ff_dbg[64 * 16];
+#define FF_STAMP(slot, gidx)                                                            \
+    if ((p.debug & 2048) && blockIdx.x == 0 && (gidx) < 64u) ff_dbg[(gidx) * 16 + (slot)] = clock64();
+
+// experiment helper: suspend-hinted try_wait (default) or a pure test_wait spin
+MOFA_DEVICE void mma_wait(bool spin, uint64_t* bar, uint32_t parity) {
+    if (spin) {
+        while (!mbar_test(bar, parity)) {
+        }
+    } else {
+        mbar_wait(bar, parity);
+    }
+}
 
 union H8 {
     uint4 u;
@@ -68,7 +86,7 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     uint8_t* sW1 = sX + static_cast<size_t>(KB) * kTile16K;
     uint8_t* sW2 = sW1 + kW1Stages * kTile16K;
     uint8_t* staging = sW2 + static_cast<size_t>(p.C) * 128;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kEW * 2048);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kEW * kStgBytes);
     uint64_t* x_full = bars;
     uint64_t* x_empty = bars + 1;
     uint64_t* w1_full = bars + 2;
@@ -127,9 +145,13 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             for (int j = 0; j < nch; ++j) {
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(&w1_empty[st], ph ^ 1u);
-                    mbar_arrive_expect_tx(&w1_full[st], kTile16K);
-                    tma_load_2d(&tmW1, &w1_full[st], sW1 + st * kTile16K, kb * 64, j * 128);
-                    if (++st == kW1Stages) {
+                    if (p.debug & 8) {
+                        mbar_arrive(&w1_full[st]);
+                    } else {
+                        mbar_arrive_expect_tx(&w1_full[st], kTile16K);
+                        tma_load_2d(&tmW1, &w1_full[st], sW1 + st * kTile16K, kb * 64, j * 128);
+                    }
+                    if (++st == p.w1_stages) {
                         st = 0;
                         ph ^= 1u;
                     }
@@ -142,67 +164,98 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
             for (int j = 0; j < nch; ++j, ++g) {
                 mbar_wait(w2_empty, (g & 1u) ^ 1u);   // OUT += H_{g-1} W2_{g-1}^T has completed
+                if (p.debug & 16) {
+                    mbar_arrive(w2_full);
+                    continue;
+                }
                 mbar_arrive_expect_tx(w2_full, static_cast<uint32_t>(p.C) * 128u);
                 for (int pc = 0; pc < KB; ++pc) tma_load_2d(&tmW2, w2_full, sW2 + pc * 8192, j * 64, pc * 64);
             }
         }
-    } else if (threadIdx.x == 32) {
+    } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        // The whole warp walks the (warp-uniform) schedule and one elected lane issues: descriptors, barrier addresses
+        // and loop state then live in uniform registers.  With the loop inside a single-thread branch the compiler
+        // re-elects a lane and broadcasts every operand before each tcgen05 instruction (~16 instructions per MMA,
+        // ~4.2k issue cycles per 64-wide chunk against 1.9k cycles of tensor work: profiles/r2_ff_fused_notes.txt).
+        const bool leader = elect_one();
+        const bool spin_m = (p.debug & 32) != 0;
         const uint32_t idesc_s = umma_idesc_f16(128, false);
         const uint32_t idesc_o1 = umma_idesc_f16(static_cast<uint32_t>(p.n1), false);
         const uint32_t idesc_o2 = umma_idesc_f16(static_cast<uint32_t>(p.n2 > 0 ? p.n2 : 16), false);
+        const uint64_t dX0 = umma_desc_sw128_kmajor(smem_u32(sX));
+        const uint64_t dW10 = umma_desc_sw128_kmajor(smem_u32(sW1));
+        const uint64_t dw = umma_desc_sw128_kmajor(smem_u32(sW2));
+        const uint64_t dw2 = umma_desc_sw128_kmajor(smem_u32(sW2 + p.n1 * 128));
+        const bool two = p.n2 > 0;
+        const bool skip1 = (p.debug & 1) != 0, skip2 = (p.debug & 2) != 0;
         int st = 0;
         uint32_t ph = 0, t = 0;
         for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++t) {
-            mbar_wait(x_full, t & 1u);
+            mma_wait(spin_m, x_full, t & 1u);
             tc_fence_after();
             for (int j = 0; j <= nch; ++j) {
                 if (j < nch) {
                     const uint32_t g = t * static_cast<uint32_t>(nch) + static_cast<uint32_t>(j);
                     if (g > 0) {   // the epilogue warps hold S_{g-1} in registers
-                        mbar_wait(s_free, (g - 1u) & 1u);
+                        mma_wait(spin_m, s_free, (g - 1u) & 1u);
                         tc_fence_after();
                     }
+                    if (leader) { FF_STAMP(0, g) }
                     for (int kb = 0; kb < KB; ++kb) {
-                        mbar_wait(&w1_full[st], ph);
+                        mma_wait(spin_m, &w1_full[st], ph);
                         tc_fence_after();
-                        const uint64_t da = umma_desc_sw128_kmajor(smem_u32(sX + kb * kTile16K));
-                        const uint64_t db = umma_desc_sw128_kmajor(smem_u32(sW1 + st * kTile16K));
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_f16_ss(tmem_S, da + 2 * k, db + 2 * k, idesc_s, (kb | k) != 0 ? 1u : 0u);
-                        umma_commit(&w1_empty[st]);
-                        if (++st == kW1Stages) {
+                        if (leader) {
+                            const uint64_t da = dX0 + static_cast<uint64_t>(kb) * (kTile16K >> 4);
+                            const uint64_t db = dW10 + static_cast<uint64_t>(st) * (kTile16K >> 4);
+                            if (!skip1) {
+                                umma_f16_ss(tmem_S, da, db, idesc_s, kb != 0 ? 1u : 0u);
+                                umma_f16_ss(tmem_S, da + 2, db + 2, idesc_s, 1u);
+                                umma_f16_ss(tmem_S, da + 4, db + 4, idesc_s, 1u);
+                                umma_f16_ss(tmem_S, da + 6, db + 6, idesc_s, 1u);
+                            }
+                            if (p.debug & 128) mbar_arrive(&w1_empty[st]); else umma_commit(&w1_empty[st]);
+                        }
+                        if (++st == p.w1_stages) {
                             st = 0;
                             ph ^= 1u;
                         }
                     }
-                    umma_commit(s_full);
-                    if (j == nch - 1) umma_commit(x_empty);
+                    if (leader) {
+                        umma_commit(s_full);
+                        if (j == nch - 1) umma_commit(x_empty);
+                        FF_STAMP(1, g)
+                    }
                 }
                 if (j > 0) {
                     const int jj = j - 1;
                     const uint32_t gg = t * static_cast<uint32_t>(nch) + static_cast<uint32_t>(jj);
                     const uint32_t buf = gg & 1u;
-                    mbar_wait(&h_full[buf], (gg >> 1) & 1u);
-                    mbar_wait(w2_full, gg & 1u);
-                    if (jj == 0 && t > 0) mbar_wait(out_free, (t - 1u) & 1u);   // the previous tile's output was drained
+                    mma_wait(spin_m, &h_full[buf], (gg >> 1) & 1u);
+                    mma_wait(spin_m, w2_full, gg & 1u);
+                    if (jj == 0 && t > 0) mma_wait(spin_m, out_free, (t - 1u) & 1u);   // the previous tile's output was drained
                     tc_fence_after();
-                    const uint64_t dw = umma_desc_sw128_kmajor(smem_u32(sW2));
-                    const uint64_t dw2 = umma_desc_sw128_kmajor(smem_u32(sW2 + p.n1 * 128));
+                    if (leader) {
+                        FF_STAMP(2, gg)
+                        const uint32_t ha = tmem_H + buf * 32;
+                        if (!skip2) {
+                            umma_f16_ts(tmem_OUT, ha, dw, idesc_o1, jj > 0 ? 1u : 0u);
+                            if (two) umma_f16_ts(tmem_OUT + p.n1, ha, dw2, idesc_o2, jj > 0 ? 1u : 0u);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint32_t acc = (jj > 0 || kk > 0) ? 1u : 0u;
-                        umma_f16_ts(tmem_OUT, tmem_H + buf * 32 + kk * 8, dw + 2 * kk, idesc_o1, acc);
-                        if (p.n2 > 0)
-                            umma_f16_ts(tmem_OUT + p.n1, tmem_H + buf * 32 + kk * 8, dw2 + 2 * kk, idesc_o2, acc);
+                            for (int kk = 1; kk < 4; ++kk) {
+                                umma_f16_ts(tmem_OUT, ha + kk * 8, dw + 2 * kk, idesc_o1, 1u);
+                                if (two) umma_f16_ts(tmem_OUT + p.n1, ha + kk * 8, dw2 + 2 * kk, idesc_o2, 1u);
+                            }
+                        }
+                        umma_commit(w2_empty);
+                        umma_commit(&h_free[buf]);
+                        FF_STAMP(3, gg)
+                        if (jj == nch - 1) umma_commit(out_full);
                     }
-                    umma_commit(w2_empty);
-                    umma_commit(&h_free[buf]);
-                    if (jj == nch - 1) umma_commit(out_full);
                 }
             }
         }
+        __syncwarp();
     } else if (warp >= 3) {
         // ===================== epilogue =====================
         const int e = warp - 3;
@@ -210,7 +263,7 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const int sub = e >> 2;        // which 16 hidden columns of a chunk / which output units
         const int r = q * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-        uint8_t* stg = staging + e * 2048;
+        uint8_t* stg = staging + e * kStgBytes;
         uint32_t t = 0;
         for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++t) {
             const long long row = static_cast<long long>(tile) * 128 + r;
@@ -224,21 +277,36 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 for (int i = 0; i < 2; ++i) {
                     bvv[i] = make_uint4(0, 0, 0, 0);
                     bgv[i] = make_uint4(0, 0, 0, 0);
-                    if (p.b1) {
+                    if (p.b1 && !(p.debug & 1024)) {
                         bvv[i] = __ldg(reinterpret_cast<const uint4*>(p.b1 + j * 128 + sub * 16) + i);
                         bgv[i] = __ldg(reinterpret_cast<const uint4*>(p.b1 + j * 128 + 64 + sub * 16) + i);
                     }
                 }
-                mbar_wait(s_full, g & 1u);
+                mma_wait((p.debug & 64) != 0, s_full, g & 1u);
                 tc_fence_after();
+                if (threadIdx.x == 96) { FF_STAMP(4, g) }
+                if (threadIdx.x == 576) { FF_STAMP(9, g) }
                 uint32_t va[16], ga[16];
-                tmem_ld_32x16(tmem_S + lane_addr + sub * 16, va);
-                tmem_ld_32x16(tmem_S + lane_addr + 64 + sub * 16, ga);
-                tmem_ld_wait();
+                if (p.debug & 512) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) va[i] = ga[i] = static_cast<uint32_t>(i + lane);
+                } else {
+                    tmem_ld_32x16(tmem_S + lane_addr + sub * 16, va);
+                    tmem_ld_32x16(tmem_S + lane_addr + 64 + sub * 16, ga);
+                    tmem_ld_wait();
+                }
                 tc_fence_before();
                 __syncwarp();
+                if (threadIdx.x == 96) { FF_STAMP(5, g) }
+                if (threadIdx.x == 576) { FF_STAMP(10, g) }
                 if (lane == 0) mbar_arrive(s_free);        // S_{g+1} may overwrite the buffer
+                if ((p.debug & 4096) && q == 1) __nanosleep(200);   // experiment: leave the MMA warp's scheduler alone
+                if (p.debug & 8192) __nanosleep(100);
                 uint32_t packed[8];
+                if (p.debug & 4) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) packed[i] = va[i] ^ ga[i];
+                } else
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     H8 bv, bg;
@@ -255,60 +323,75 @@ ff_geglu_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                         packed[i * 4 + c] = *reinterpret_cast<const uint32_t*>(&hh);
                     }
                 }
+                if (threadIdx.x == 96) { FF_STAMP(6, g) }
                 if (g >= 2) {   // OUT += H_{g-2} W2^T has finished reading this H buffer
                     mbar_wait(&h_free[buf], ((g >> 1) - 1u) & 1u);
                     tc_fence_after();
                 }
-                tmem_st_32x8(tmem_H + lane_addr + buf * 32 + sub * 8, packed);
-                tmem_st_wait();
+                if (!(p.debug & 256)) {
+                    tmem_st_32x8(tmem_H + lane_addr + buf * 32 + sub * 8, packed);
+                    tmem_st_wait();
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&h_full[buf]);
+                if (threadIdx.x == 96) { FF_STAMP(7, g) }
+                if (threadIdx.x == 576) { FF_STAMP(11, g) }
             }
             // ---- output of the tile: bias, alpha, residuals, fp16, TMA store
             mbar_wait(out_full, t & 1u);
             tc_fence_after();
-            const int n_units = p.C >> 5;
+            const int n_units = p.C >> 4;      // 16-column units: 1 KB of staging per warp (the W1 ring needs the rest)
             const bool has1 = p.res1 != nullptr, has2 = p.res2 != nullptr;
+            uint4 r1n[2], r2n[2];              // residuals of the NEXT unit: their latency hides behind this unit's work
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                r1n[i] = r2n[i] = make_uint4(0, 0, 0, 0);
+                if (has1 && valid && sub < n_units)
+                    r1n[i] = __ldg(reinterpret_cast<const uint4*>(p.res1 + row * p.ldr1 + sub * 16) + i);
+                if (has2 && valid && sub < n_units)
+                    r2n[i] = __ldg(reinterpret_cast<const uint4*>(p.res2 + row * p.ldr2 + sub * 16) + i);
+            }
 #pragma unroll 1
             for (int u = sub; u < n_units; u += 4) {
-                if (lane == 0) tma_store_wait_read<0>();
+                const int n0 = u * 16;
+                uint4 r1v[2], r2v[2], bvv[2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    r1v[i] = r1n[i];
+                    r2v[i] = r2n[i];
+                    bvv[i] = make_uint4(0, 0, 0, 0);
+                    if (p.b2) bvv[i] = __ldg(reinterpret_cast<const uint4*>(p.b2 + n0) + i);
+                    if (u + 4 < n_units) {
+                        if (has1 && valid) r1n[i] = __ldg(reinterpret_cast<const uint4*>(p.res1 + row * p.ldr1 + n0 + 64) + i);
+                        if (has2 && valid) r2n[i] = __ldg(reinterpret_cast<const uint4*>(p.res2 + row * p.ldr2 + n0 + 64) + i);
+                    }
+                }
+                uint32_t acc[16];
+                tmem_ld_32x16(tmem_OUT + lane_addr + n0, acc);
+                tmem_ld_wait();
+                if (lane == 0) tma_store_wait_read<0>();   // the previous unit's store has read the staging rows
                 __syncwarp();
-#pragma unroll 1
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int n0 = u * 32 + hh * 16;
-                    uint4 r1v[2], r2v[2], bvv[2];
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        r1v[i] = r2v[i] = bvv[i] = make_uint4(0, 0, 0, 0);
-                        if (has1 && valid) r1v[i] = __ldg(reinterpret_cast<const uint4*>(p.res1 + row * p.ldr1 + n0) + i);
-                        if (has2 && valid) r2v[i] = __ldg(reinterpret_cast<const uint4*>(p.res2 + row * p.ldr2 + n0) + i);
-                        if (p.b2) bvv[i] = __ldg(reinterpret_cast<const uint4*>(p.b2 + n0) + i);
+                for (int i = 0; i < 2; ++i) {
+                    H8 b, a1, a2, o;
+                    b.u = bvv[i];
+                    a1.u = r1v[i];
+                    a2.u = r2v[i];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        float x = (__uint_as_float(acc[i * 8 + c]) + __half2float(b.h[c])) * p.alpha;
+                        x = fmaf(p.beta1, __half2float(a1.h[c]), x);
+                        x = fmaf(p.beta2, __half2float(a2.h[c]), x);
+                        o.h[c] = __float2half_rn(x);
                     }
-                    uint32_t acc[16];
-                    tmem_ld_32x16(tmem_OUT + lane_addr + n0, acc);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        H8 b, a1, a2, o;
-                        b.u = bvv[i];
-                        a1.u = r1v[i];
-                        a2.u = r2v[i];
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            float x = (__uint_as_float(acc[i * 8 + c]) + __half2float(b.h[c])) * p.alpha;
-                            x = fmaf(p.beta1, __half2float(a1.h[c]), x);
-                            x = fmaf(p.beta2, __half2float(a2.h[c]), x);
-                            o.h[c] = __float2half_rn(x);
-                        }
-                        const int ci = hh * 2 + i;   // 16-byte chunk of the 64-byte staging row (SWIZZLE_64B)
-                        *reinterpret_cast<uint4*>(stg + lane * 64 + ((ci ^ ((lane >> 1) & 3)) << 4)) = o.u;
-                    }
+                    // 16-byte chunk i of the 32-byte staging row (SWIZZLE_32B: address bit 4 ^= bit 7)
+                    *reinterpret_cast<uint4*>(stg + lane * 32 + ((i ^ ((lane >> 2) & 1)) << 4)) = o.u;
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_2d(&tmOut, stg, u * 32, tile * 128 + q * 32);
+                    tma_store_2d(&tmOut, stg, n0, tile * 128 + q * 32);
                     tma_store_commit();
                 }
             }
@@ -358,6 +441,13 @@ extern "C" int mofa_ff_geglu(const void* x, const void* w1_packed, const void* b
     p.res2 = static_cast<const __half*>(res2);
     p.ldr2 = ldr2;
     p.alpha = alpha;
+    {
+        const char* dbg = getenv("MOFA_FF_DEBUG");
+        p.debug = dbg ? atoi(dbg) : 0;
+        const char* stg = getenv("MOFA_FF_STAGES");
+        p.w1_stages = stg ? atoi(stg) : ff::kW1Stages;
+        if (p.w1_stages < 2 || p.w1_stages > ff::kW1Stages) p.w1_stages = ff::kW1Stages;
+    }
     p.beta1 = beta1;
     p.beta2 = beta2;
 
@@ -368,8 +458,8 @@ extern "C" int mofa_ff_geglu(const void* x, const void* w1_packed, const void* b
         uint64_t s[1] = {static_cast<uint64_t>(C) * 2};
         uint32_t b[2] = {64, 128};
         if ((rc = make_tmap_f16(&tmX, x, 2, d, s, b)) != MOFA_OK) return rc;
-        uint32_t ob[2] = {32, 32};
-        if ((rc = make_tmap_f16_sw(&tmOut, out, 2, d, s, ob, CU_TENSOR_MAP_SWIZZLE_64B)) != MOFA_OK) return rc;
+        uint32_t ob[2] = {16, 32};
+        if ((rc = make_tmap_f16_sw(&tmOut, out, 2, d, s, ob, CU_TENSOR_MAP_SWIZZLE_32B)) != MOFA_OK) return rc;
     }
     {
         uint64_t d[2] = {static_cast<uint64_t>(C), static_cast<uint64_t>(2) * hidden};
@@ -384,7 +474,7 @@ extern "C" int mofa_ff_geglu(const void* x, const void* w1_packed, const void* b
         if ((rc = make_tmap_f16(&tmW2, w2, 2, d, s, b)) != MOFA_OK) return rc;
     }
     const size_t smem_bytes = static_cast<size_t>(C / 64) * ff::kTile16K + ff::kW1Stages * ff::kTile16K +
-                              static_cast<size_t>(C) * 128 + ff::kEW * 2048 + 32 * 8 + 16 + 1024;
+                              static_cast<size_t>(C) * 128 + ff::kEW * ff::kStgBytes + 32 * 8 + 16 + 1024;
     static size_t configured = 0;
     if (smem_bytes > configured) {
         cudaError_t e = cudaFuncSetAttribute(ff::ff_geglu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -399,4 +489,9 @@ extern "C" int mofa_ff_geglu(const void* x, const void* w1_packed, const void* b
     if (p.m_tiles < grid) grid = p.m_tiles;
     ff::ff_geglu_kernel<<<grid, ff::kThreads, smem_bytes, stream>>>(tmX, tmW1, tmW2, tmOut, p);
     return check_launch("mofa_ff_geglu");
+}
+
+// experiment support (not part of the ABI header): copy the stage timestamps of block 0 (MOFA_FF_DEBUG bit 2048)
+extern "C" int mofa_ff_debug_dump(long long* host_out) {
+    return cudaMemcpyFromSymbol(host_out, mofa::ff::ff_dbg, sizeof(long long) * 64 * 16) == cudaSuccess ? 0 : 1;
 }

@@ -196,7 +196,10 @@ __device__ __noinline__ void epilogue_direct8(const GemmKernelParams& p, const f
 // 168 registers is the ceiling for a 320-thread CTA: the register file is split per sub-partition (16384 each) and ten warps
 // land 3 + 3 + 2 + 2, so 3 warps x 32 x R <= 16384 (a 176-register build fails to launch: "too many resources requested");
 // 18 warps (kEW = 16) land 5 + 5 + 4 + 4: 96 registers.
-template <int kEpi, bool kStats, int kEW>
+// k2: CTA pairs (cluster of 2, cta_group::2 MMAs of M = 256): CTA `rank` of pair `i` owns M tile 2 i + rank and stages the
+// B rows [rank * n/2, (rank + 1) * n/2) of the pair's N tile; the leader (rank 0) issues every MMA.  Everything after
+// the accumulator (the epilogues) is per CTA and unchanged.
+template <int kEpi, bool kStats, int kEW, bool k2>
 __global__ void __launch_bounds__(64 + 32 * kEW, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
@@ -206,7 +209,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // SWIZZLE_128B tiles need 1024 B alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-    const uint32_t b_bytes = static_cast<uint32_t>(p.bn) * (BK * 2);
+    const uint32_t rank = k2 ? cluster_ctarank() : 0u;
+    const uint32_t b_bytes = static_cast<uint32_t>(k2 ? (p.bn >> 1) : p.bn) * (BK * 2);   // B rows staged by THIS CTA
     const uint32_t stage_bytes = kABytes + b_bytes;
     uint8_t* staging = smem + static_cast<size_t>(p.stages) * stage_bytes;  // kEpiWarps x 4 KB, 1024-aligned
     uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kEpiWarps * kStagingBytes);  // same 32 KB for kEW = 16 (2 KB tiles)
@@ -239,13 +243,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], kEW);
+            mbar_init(&tempty_bar[i], k2 ? 2 * kEW : kEW);   // pair: both CTAs' epilogue warps arrive at the leader
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_ptr_smem, kTmemCols);
+    if (warp == 1) {
+        if constexpr (k2) tmem_alloc_2sm(tmem_ptr_smem, kTmemCols);
+        else tmem_alloc(tmem_ptr_smem, kTmemCols);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (k2) cluster_sync_all();   // the peer's barriers must exist before any remote arrive / multicast commit
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
     const uint32_t acc_stride = (static_cast<uint32_t>(p.bn) + 31u) & ~31u;
@@ -255,21 +263,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // (K = 320: 80 KB) is re-read from L2 right after its first use instead of racing a neighbour CTA to DRAM
     // (ncu: 838 MB read for 590 MB of algorithmic input on the 320x320 projection; +19 % on that GEMM).  The M tiles
     // that do not fill a whole round of CTAs (m_tiles mod grid) are dealt out N-fastest again to keep the tail short.
-    const int grid_i = static_cast<int>(gridDim.x), cta_i = static_cast<int>(blockIdx.x);
-    const int full_groups = (p.n_tiles > 1 && p.m_tiles / grid_i >= 2) ? p.m_tiles / grid_i : 0;
+    // (pairs: the same walk over PAIRS of M tiles; both CTAs of a pair see the same sequence, each takes its own half)
+    const int grid_i = static_cast<int>(gridDim.x) >> (k2 ? 1 : 0), cta_i = static_cast<int>(blockIdx.x) >> (k2 ? 1 : 0);
+    const int m_sched = p.m_tiles >> (k2 ? 1 : 0);
+    const int full_groups = (p.n_tiles > 1 && m_sched / grid_i >= 2) ? m_sched / grid_i : 0;
     const int grouped_tiles = full_groups * p.n_tiles;           // per CTA
-    const int tail_tiles = (p.m_tiles - full_groups * grid_i) * p.n_tiles;  // whole grid
+    const int tail_tiles = (m_sched - full_groups * grid_i) * p.n_tiles;  // whole grid
     auto tile_at = [&](int i, int& mt, int& nt) {  // i-th tile of this CTA; false past the end
+        bool ok = true;
         if (i < grouped_tiles) {
             const int g = i / p.n_tiles;
             mt = cta_i + g * grid_i;
             nt = i - g * p.n_tiles;
-            return true;
+        } else {
+            const int j = cta_i + (i - grouped_tiles) * grid_i;
+            mt = full_groups * grid_i + j / p.n_tiles;
+            nt = j % p.n_tiles;
+            ok = j < tail_tiles;
         }
-        const int j = cta_i + (i - grouped_tiles) * grid_i;
-        mt = full_groups * grid_i + j / p.n_tiles;
-        nt = j % p.n_tiles;
-        return j < tail_tiles;
+        if constexpr (k2) mt = 2 * mt + static_cast<int>(rank);
+        return ok;
     };
 
     if (threadIdx.x == 0) {
@@ -279,71 +292,105 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int mt, nt;
         for (int ti = 0; tile_at(ti, mt, nt); ++ti) {
             const TileCoord tc = tile_coord(p, mt);
+            int b_row0 = nt * p.bn;
+            if constexpr (k2) {   // this CTA's half of the (possibly narrower, last) N tile
+                int n_this = p.N - nt * p.bn;
+                n_this = n_this >= p.bn ? p.bn : ((n_this + 31) & ~31);
+                b_row0 += static_cast<int>(rank) * (n_this >> 1);
+            }
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
                 uint8_t* sb = sa + kABytes;
-                mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+                // pair: the leader's barrier counts the bytes of BOTH CTAs' loads (one arrival, the leader's)
+                if (!k2 || rank == 0) mbar_arrive_expect_tx(&full_bar[stage], k2 ? 2 * stage_bytes : stage_bytes);
+                auto load2 = [&](const CUtensorMap* m, void* dst, int c0, int c1) {
+                    if constexpr (k2) tma_load_2d_2sm(m, &full_bar[stage], dst, c0, c1);
+                    else tma_load_2d(m, &full_bar[stage], dst, c0, c1);
+                };
+                auto load4 = [&](const CUtensorMap* m, void* dst, int c0, int c1, int c2, int c3) {
+                    if constexpr (k2) tma_load_4d_2sm(m, &full_bar[stage], dst, c0, c1, c2, c3);
+                    else tma_load_4d(m, &full_bar[stage], dst, c0, c1, c2, c3);
+                };
                 if (p.mode == MOFA_A_LINEAR) {
                     if (kb < p.kb_split)
-                        tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, static_cast<int>(tc.m0));
+                        load2(&tmA, sa, kb * BK, static_cast<int>(tc.m0));
                     else
-                        tma_load_2d(&tmA2, &full_bar[stage], sa, (kb - p.kb_split) * BK, static_cast<int>(tc.m0));
+                        load2(&tmA2, sa, (kb - p.kb_split) * BK, static_cast<int>(tc.m0));
                 } else if (p.mode == MOFA_A_CONV3X3) {
                     const int tap = kb / p.kb_per_tap;
                     const int c0 = (kb - tap * p.kb_per_tap) * BK;
                     const int ky = tap / p.ks, kx = tap - ky * p.ks;
                     const int half_k = p.ks >> 1;  // "same" padding: taps centred on the output pixel
-                    tma_load_4d(&tmA, &full_bar[stage], sa, c0, tc.x0 + (kx - half_k) * p.dil,
-                                tc.y0 + (ky - half_k) * p.dil, tc.n_img);
+                    load4(&tmA, sa, c0, tc.x0 + (kx - half_k) * p.dil, tc.y0 + (ky - half_k) * p.dil, tc.n_img);
                 } else {
                     const int tap = kb / p.kb_per_tap;
                     const int c0 = (kb - tap * p.kb_per_tap) * BK;
                     const int b = tc.frame / p.T;
                     const int t = tc.frame - b * p.T;
-                    tma_load_4d(&tmA, &full_bar[stage], sa, c0, tc.p0, t + tap - 1, b);
+                    load4(&tmA, sa, c0, tc.p0, t + tap - 1, b);
                 }
-                tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, nt * p.bn);
+                load2(&tmB, sb, kb * BK, b_row0);
                 if (++stage == p.stages) {
                     stage = 0;
                     phase ^= 1;
                 }
             }
         }
-    } else if (threadIdx.x == 32) {
+    } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        int stage = 0;
-        uint32_t phase = 0;
-        uint32_t iter = 0;
-        int mt, nt;
-        for (; tile_at(static_cast<int>(iter), mt, nt); ++iter) {
-            int n_this = p.N - nt * p.bn;             // the last N tile of a row may be narrower
-            n_this = n_this >= p.bn ? p.bn : ((n_this + 15) & ~15);
-            const uint32_t idesc = umma_idesc_f16(static_cast<uint32_t>(n_this), false);
-            const uint32_t as = iter & 1u;
-            const uint32_t aphase = (iter >> 1) & 1u;
-            mbar_wait(&tempty_bar[as], aphase ^ 1);
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + as * acc_stride;
-            for (int kb = 0; kb < p.num_kb; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
+        // The whole warp walks the (warp-uniform) schedule and one elected lane issues, so descriptors, barrier addresses
+        // and loop state live in uniform registers (inside a single-thread branch the compiler re-elects a lane and
+        // broadcasts every operand before each tcgen05 instruction).  Pair: only the leader CTA issues.
+        const bool leader = elect_one();
+        if (!k2 || rank == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t iter = 0;
+            int mt, nt;
+            for (; tile_at(static_cast<int>(iter), mt, nt); ++iter) {
+                int n_this = p.N - nt * p.bn;             // the last N tile of a row may be narrower
+                n_this = n_this >= p.bn ? p.bn : ((n_this + (k2 ? 31 : 15)) & ~(k2 ? 31 : 15));
+                const uint32_t idesc = umma_idesc_f16_m(static_cast<uint32_t>(n_this), k2 ? 256u : 128u);
+                const uint32_t as = iter & 1u;
+                const uint32_t aphase = (iter >> 1) & 1u;
+                mbar_wait(&tempty_bar[as], aphase ^ 1);
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
-                const uint64_t da = umma_desc_sw128_kmajor(sa);
-                const uint64_t db = umma_desc_sw128_kmajor(sa + kABytes);
-#pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    // +32 B per K=16 step inside the 128 B swizzle atom: +2 in 16 B address units
-                    umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                const uint32_t tmem_d = tmem_base + as * acc_stride;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (leader) {
+                        const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+                        const uint64_t da = umma_desc_sw128_kmajor(sa);
+                        const uint64_t db = umma_desc_sw128_kmajor(sa + kABytes);
+                        // +32 B per K=16 step inside the 128 B swizzle atom: +2 in 16 B address units
+                        if constexpr (k2) {
+                            umma_f16_ss_2sm(tmem_d, da, db, idesc, kb != 0 ? 1u : 0u);
+                            umma_f16_ss_2sm(tmem_d, da + 2, db + 2, idesc, 1u);
+                            umma_f16_ss_2sm(tmem_d, da + 4, db + 4, idesc, 1u);
+                            umma_f16_ss_2sm(tmem_d, da + 6, db + 6, idesc, 1u);
+                            umma_commit_2sm(&empty_bar[stage]);
+                        } else {
+                            umma_f16_ss(tmem_d, da, db, idesc, kb != 0 ? 1u : 0u);
+                            umma_f16_ss(tmem_d, da + 2, db + 2, idesc, 1u);
+                            umma_f16_ss(tmem_d, da + 4, db + 4, idesc, 1u);
+                            umma_f16_ss(tmem_d, da + 6, db + 6, idesc, 1u);
+                            umma_commit(&empty_bar[stage]);
+                        }
+                    }
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
-                umma_commit(&empty_bar[stage]);
-                if (++stage == p.stages) {
-                    stage = 0;
-                    phase ^= 1;
+                if (leader) {
+                    if constexpr (k2) umma_commit_2sm(&tfull_bar[as]);
+                    else umma_commit(&tfull_bar[as]);
                 }
             }
-            umma_commit(&tfull_bar[as]);
         }
+        __syncwarp();
     } else if (warp >= 2) {
         // ===================== epilogue =====================
         const int e = warp - 2;
@@ -905,7 +952,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (lane == 0) {
+                if constexpr (k2) mbar_arrive_leader(&tempty_bar[as]);
+                else mbar_arrive(&tempty_bar[as]);
+            }
             if constexpr (kStats) {
                 if (gn_smem) {
                     // No barrier: every warp counts itself done with this tile's buffer and the LAST one moves the partial
@@ -945,10 +995,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (k2) cluster_sync_all();   // the peer may still be reading this CTA's shared / tensor memory
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if constexpr (k2) tmem_dealloc_2sm(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -1260,14 +1312,23 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
         return MOFA_ERR_ARG;
     }
     if (!tma_out) tmOut = tmA;
+    // CTA pairs (cta_group::2, see the kernel): an even number of M tiles so both CTAs of a pair always have a tile, every
+    // N tile a multiple of 32 wide so each half is a legal MMA N.  MOFA_GEMM_2CTA=0 switches them off (A/B measurements).
+    static int pair_mode = -1;
+    if (pair_mode < 0) {
+        const char* e = getenv("MOFA_GEMM_2CTA");
+        pair_mode = e ? atoi(e) : 1;
+    }
+    const bool k2 = pair_mode != 0 && !use_ew16 && (p.m_tiles % 2) == 0 && (bn % 32) == 0 && (a->N % 32) == 0 &&
+                    num_sms() >= 2 && (a->max_ctas <= 0 || a->max_ctas >= 2);
     {
         uint64_t dims[2] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(a->N)};
         uint64_t strides[1] = {static_cast<uint64_t>(Ktot) * 2};
-        uint32_t box[2] = {BK, static_cast<uint32_t>(bn)};
+        uint32_t box[2] = {BK, static_cast<uint32_t>(k2 ? bn / 2 : bn)};
         if ((rc = make_tmap_f16(&tmB, a->w, 2, dims, strides, box)) != MOFA_OK) return rc;
     }
 
-    const uint32_t stage_bytes = kABytes + static_cast<uint32_t>(bn) * BK * 2;
+    const uint32_t stage_bytes = kABytes + static_cast<uint32_t>(k2 ? bn / 2 : bn) * BK * 2;
     const size_t fixed = kEpiWarps * kStagingBytes + 1024 + 256;
     int stages = static_cast<int>((227u * 1024u - fixed) / stage_bytes);
     if (stages > 8) stages = 8;
@@ -1287,11 +1348,14 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
     int grid = num_sms();
     if (a->max_ctas > 0 && a->max_ctas < grid) grid = a->max_ctas;
     if (total < grid) grid = static_cast<int>(total);
+    if (k2) grid &= ~1;   // whole pairs (total is even: m_tiles is)
 
     using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmKernelParams);
-    static const Kern kernels[6] = {gemm_tc_kernel<0, false, 8>, gemm_tc_kernel<0, true, 8>, gemm_tc_kernel<1, false, 8>,
-                                    gemm_tc_kernel<2, false, 8>, gemm_tc_kernel<1, false, 16>,
-                                    gemm_tc_kernel<0, false, 16>};
+    static const Kern kernels[10] = {gemm_tc_kernel<0, false, 8, false>, gemm_tc_kernel<0, true, 8, false>,
+                                     gemm_tc_kernel<1, false, 8, false>, gemm_tc_kernel<2, false, 8, false>,
+                                     gemm_tc_kernel<1, false, 16, false>, gemm_tc_kernel<0, false, 16, false>,
+                                     gemm_tc_kernel<0, false, 8, true>, gemm_tc_kernel<0, true, 8, true>,
+                                     gemm_tc_kernel<1, false, 8, true>, gemm_tc_kernel<2, false, 8, true>};
     static bool configured = false;
     if (!configured) {
         for (Kern k : kernels) {
@@ -1310,9 +1374,29 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
     // 16 epilogue warps where the epilogue is the bottleneck (5 k-blocks per tile at K = 320: GEGLU 690 -> 916 TFLOP/s); with
     // longer main loops the 8-warp unrolled body is faster (GEGLU K = 640: 1180 vs 1092, K = 1280: 1410 vs 1333)
     const bool geglu16 = use_ew16;
-    const Kern kern = use_ew16 ? (geglu ? kernels[4] : kernels[5])
-                      : geglu  ? kernels[2]
-                               : (a->act != 0 ? kernels[3] : (p.gn_stats ? kernels[1] : kernels[0]));
-    kern<<<grid, geglu16 ? 64 + 32 * 16 : kGemmThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, tmOut, p);
+    const int base = geglu ? 2 : (a->act != 0 ? 3 : (p.gn_stats ? 1 : 0));
+    const Kern kern = use_ew16 ? (geglu ? kernels[4] : kernels[5]) : kernels[base + (k2 ? 6 : 0)];
+    if (k2) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmB, tmOut, p);
+        if (e != cudaSuccess) {
+            set_last_error("mofa_gemm: cluster launch: %s", cudaGetErrorString(e));
+            return MOFA_ERR_CUDA;
+        }
+    } else {
+        kern<<<grid, geglu16 ? 64 + 32 * 16 : kGemmThreads, smem_bytes, stream>>>(tmA, tmA2, tmB, tmOut, p);
+    }
     return check_launch("mofa_gemm");
 }
