@@ -131,22 +131,29 @@ attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
                 phase ^= 1;
             }
         }
-    } else if (threadIdx.x == 32) {
+    } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        // The whole warp walks the schedule (every decision is a warp vote, so it stays warp-uniform) and one elected
+        // lane issues: descriptors and loop state live in uniform registers.  Inside a single-thread branch the compiler
+        // re-elects a lane and broadcasts every operand before each tcgen05 instruction -- ~16 instructions per MMA on a
+        // scheduler shared with softmax warps, more than the 32..64 cycles one of these MMAs occupies the tensor pipe.
+        const bool leader = elect_one();
         const uint32_t idesc_s = umma_idesc_f16(128, false);
         const uint32_t idesc_o = umma_idesc_f16(64, true);
-        uint64_t dq[2];
-        dq[0] = umma_desc_sw128_kmajor(smem_u32(sQ));
-        dq[1] = umma_desc_sw128_kmajor(smem_u32(sQ + kTile));
+        const uint64_t dq0 = umma_desc_sw128_kmajor(smem_u32(sQ));
+        const uint64_t dq1 = umma_desc_sw128_kmajor(smem_u32(sQ + kTile));
+        const uint64_t dk0 = umma_desc_sw128_kmajor(smem_u32(sKV));
+        const uint64_t dv0 = umma_desc_sw128_mnmajor(smem_u32(sKV + kTile), kTile);
+        constexpr uint64_t kStageStep = (2 * kTile) >> 4;   // descriptor address units per K/V ring stage
         mbar_wait(q_full, 0);
         mbar_wait(&kv_full[0], 0);
         tc_fence_after();
-        {
-            const uint64_t dk = umma_desc_sw128_kmajor(smem_u32(sKV));
+        if (leader) {
 #pragma unroll
             for (int w = 0; w < 2; ++w) {
+                const uint64_t dq = w ? dq1 : dq0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_S + w * 128, dq[w] + 2 * k, dk + 2 * k, idesc_s, k != 0);
+                for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_S + w * 128, dq + 2 * k, dk0 + 2 * k, idesc_s, k != 0);
                 umma_commit(&s_full[w]);
             }
         }
@@ -159,14 +166,18 @@ attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
             bool progress = false;
 #pragma unroll
             for (int w = 0; w < 2; ++w) {
-                if (js[w] < n_kv && mbar_test(&s_free[w], (js[w] - 1) & 1) &&
-                    mbar_test(&kv_full[js_stage[w]], js_phase[w])) {
+                const uint64_t dq = w ? dq1 : dq0;
+                if (js[w] < n_kv && __all_sync(0xffffffffu, mbar_test(&s_free[w], (js[w] - 1) & 1) &&
+                                                                mbar_test(&kv_full[js_stage[w]], js_phase[w]))) {
                     tc_fence_after();
-                    const uint64_t dk = umma_desc_sw128_kmajor(smem_u32(sKV + js_stage[w] * 2 * kTile));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_f16_ss(tmem_S + w * 128, dq[w] + 2 * k, dk + 2 * k, idesc_s, k != 0);
-                    umma_commit(&s_full[w]);
+                    if (leader) {
+                        const uint64_t dk = dk0 + static_cast<uint64_t>(js_stage[w]) * kStageStep;
+                        umma_f16_ss(tmem_S + w * 128, dq, dk, idesc_s, 0u);
+                        umma_f16_ss(tmem_S + w * 128, dq + 2, dk + 2, idesc_s, 1u);
+                        umma_f16_ss(tmem_S + w * 128, dq + 4, dk + 4, idesc_s, 1u);
+                        umma_f16_ss(tmem_S + w * 128, dq + 6, dk + 6, idesc_s, 1u);
+                        umma_commit(&s_full[w]);
+                    }
                     ++js[w];
                     if (++js_stage[w] == kKVStages) {
                         js_stage[w] = 0;
@@ -174,21 +185,23 @@ attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
                     }
                     progress = true;
                 }
-                if (jp[w] < n_kv && mbar_test(&p_full[w], jp[w] & 1)) {
+                if (jp[w] < n_kv && __all_sync(0xffffffffu, mbar_test(&p_full[w], jp[w] & 1))) {
                     tc_fence_after();
-                    const uint32_t va = smem_u32(sKV + jp_stage[w] * 2 * kTile + kTile);
-                    const uint64_t dv = umma_desc_sw128_mnmajor(va, kTile);
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk)  // 16 keys per step = 8 TMEM columns of packed P
-                        umma_f16_ts(tmem_O + w * 64, tmem_P + w * 64 + kk * 8, dv + 128 * kk, idesc_o,
-                                    (jp[w] > 0) || (kk != 0));
-                    umma_commit(&o_full[w]);
                     ++jp[w];
-                    if (++jp_stage[w] == kKVStages) jp_stage[w] = 0;
-                    // a K/V stage is free once both query tiles have issued its PV (the commit covers every earlier MMA)
                     const int done = jp[0] < jp[1] ? jp[0] : jp[1];
+                    if (leader) {
+                        const uint64_t dv = dv0 + static_cast<uint64_t>(jp_stage[w]) * kStageStep;
+                        const uint32_t acc0 = jp[w] > 1 ? 1u : 0u;
+                        umma_f16_ts(tmem_O + w * 64, tmem_P + w * 64, dv, idesc_o, acc0);
+#pragma unroll
+                        for (int kk = 1; kk < 8; ++kk)  // 16 keys per step = 8 TMEM columns of packed P
+                            umma_f16_ts(tmem_O + w * 64, tmem_P + w * 64 + kk * 8, dv + 128 * kk, idesc_o, 1u);
+                        umma_commit(&o_full[w]);
+                        // a K/V stage is free once both query tiles have issued its PV (the commit covers every earlier MMA)
+                        if (done > released) umma_commit(&kv_empty[rel_stage]);
+                    }
+                    if (++jp_stage[w] == kKVStages) jp_stage[w] = 0;
                     if (done > released) {
-                        umma_commit(&kv_empty[rel_stage]);
                         ++released;
                         if (++rel_stage == kKVStages) rel_stage = 0;
                     }
@@ -197,6 +210,7 @@ attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
             }
             if (!progress && p.idle_ns > 0) __nanosleep(p.idle_ns);
         }
+        __syncwarp();
     } else if (warp >= 2) {
         // ===================== softmax warps =====================
         const int sw = warp - 2;

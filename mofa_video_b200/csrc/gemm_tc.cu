@@ -285,10 +285,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         return ok;
     };
 
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
         // ===================== TMA producer =====================
+        // Warp-uniform like the MMA issuer (one elected lane issues), and the k-block -> (tap, channel block) walk is
+        // kept in counters: as a single-thread branch with a division per k-block this loop took ~225 instructions
+        // (~1000 cycles) per stage against 400..600 cycles of MMA work per stage -- the 3x3 convolutions were
+        // producer-bound (ncu, profiles/r2_ncu_conv320_producer_bound.txt: MMA warp 45 % of its time waiting for data
+        // with the memory system at half load).
+        const bool leader = elect_one();
         int stage = 0;
         uint32_t phase = 0;
+        uint32_t s_off = 0;   // stage * stage_bytes
         int mt, nt;
         for (int ti = 0; tile_at(ti, mt, nt); ++ti) {
             const TileCoord tc = tile_coord(p, mt);
@@ -298,45 +305,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 n_this = n_this >= p.bn ? p.bn : ((n_this + 31) & ~31);
                 b_row0 += static_cast<int>(rank) * (n_this >> 1);
             }
+            const int half_k = p.ks >> 1;  // conv "same" padding: taps centred on the output pixel
+            int tb = 0, tt = 0;            // temporal: batch item and frame of this tile
+            if (p.mode == MOFA_A_TEMPORAL3) {
+                tb = tc.frame / p.T;
+                tt = tc.frame - tb * p.T;
+            }
+            int tap = 0, kbt = 0, ky = 0, kx = 0;   // k-block = (tap, channel block kbt); conv tap = (ky, kx)
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
-                uint8_t* sb = sa + kABytes;
-                // pair: the leader's barrier counts the bytes of BOTH CTAs' loads (one arrival, the leader's)
-                if (!k2 || rank == 0) mbar_arrive_expect_tx(&full_bar[stage], k2 ? 2 * stage_bytes : stage_bytes);
-                auto load2 = [&](const CUtensorMap* m, void* dst, int c0, int c1) {
-                    if constexpr (k2) tma_load_2d_2sm(m, &full_bar[stage], dst, c0, c1);
-                    else tma_load_2d(m, &full_bar[stage], dst, c0, c1);
-                };
-                auto load4 = [&](const CUtensorMap* m, void* dst, int c0, int c1, int c2, int c3) {
-                    if constexpr (k2) tma_load_4d_2sm(m, &full_bar[stage], dst, c0, c1, c2, c3);
-                    else tma_load_4d(m, &full_bar[stage], dst, c0, c1, c2, c3);
-                };
-                if (p.mode == MOFA_A_LINEAR) {
-                    if (kb < p.kb_split)
-                        load2(&tmA, sa, kb * BK, static_cast<int>(tc.m0));
-                    else
-                        load2(&tmA2, sa, (kb - p.kb_split) * BK, static_cast<int>(tc.m0));
-                } else if (p.mode == MOFA_A_CONV3X3) {
-                    const int tap = kb / p.kb_per_tap;
-                    const int c0 = (kb - tap * p.kb_per_tap) * BK;
-                    const int ky = tap / p.ks, kx = tap - ky * p.ks;
-                    const int half_k = p.ks >> 1;  // "same" padding: taps centred on the output pixel
-                    load4(&tmA, sa, c0, tc.x0 + (kx - half_k) * p.dil, tc.y0 + (ky - half_k) * p.dil, tc.n_img);
-                } else {
-                    const int tap = kb / p.kb_per_tap;
-                    const int c0 = (kb - tap * p.kb_per_tap) * BK;
-                    const int b = tc.frame / p.T;
-                    const int t = tc.frame - b * p.T;
-                    load4(&tmA, sa, c0, tc.p0, t + tap - 1, b);
+                if (leader) {
+                    uint8_t* sa = smem + s_off;
+                    uint8_t* sb = sa + kABytes;
+                    // pair: the leader's barrier counts the bytes of BOTH CTAs' loads (one arrival, the leader's)
+                    if (!k2 || rank == 0) mbar_arrive_expect_tx(&full_bar[stage], k2 ? 2 * stage_bytes : stage_bytes);
+                    auto load2 = [&](const CUtensorMap* m, void* dst, int c0, int c1) {
+                        if constexpr (k2) tma_load_2d_2sm(m, &full_bar[stage], dst, c0, c1);
+                        else tma_load_2d(m, &full_bar[stage], dst, c0, c1);
+                    };
+                    auto load4 = [&](const CUtensorMap* m, void* dst, int c0, int c1, int c2, int c3) {
+                        if constexpr (k2) tma_load_4d_2sm(m, &full_bar[stage], dst, c0, c1, c2, c3);
+                        else tma_load_4d(m, &full_bar[stage], dst, c0, c1, c2, c3);
+                    };
+                    if (p.mode == MOFA_A_LINEAR) {
+                        if (kb < p.kb_split)
+                            load2(&tmA, sa, kb * BK, static_cast<int>(tc.m0));
+                        else
+                            load2(&tmA2, sa, (kb - p.kb_split) * BK, static_cast<int>(tc.m0));
+                    } else if (p.mode == MOFA_A_CONV3X3) {
+                        load4(&tmA, sa, kbt * BK, tc.x0 + (kx - half_k) * p.dil, tc.y0 + (ky - half_k) * p.dil, tc.n_img);
+                    } else {
+                        load4(&tmA, sa, kbt * BK, tc.p0, tt + tap - 1, tb);
+                    }
+                    load2(&tmB, sb, kb * BK, b_row0);
                 }
-                load2(&tmB, sb, kb * BK, b_row0);
+                if (++kbt == p.kb_per_tap) {
+                    kbt = 0;
+                    ++tap;
+                    if (++kx == p.ks) {
+                        kx = 0;
+                        ++ky;
+                    }
+                }
+                s_off += stage_bytes;
                 if (++stage == p.stages) {
                     stage = 0;
+                    s_off = 0;
                     phase ^= 1;
                 }
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         // The whole warp walks the (warp-uniform) schedule and one elected lane issues, so descriptors, barrier addresses
@@ -1319,8 +1338,12 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
         const char* e = getenv("MOFA_GEMM_2CTA");
         pair_mode = e ? atoi(e) : 1;
     }
+    // (measured, level-0 shapes: 3x3 conv 1150 -> 1244 TFLOP/s, temporal conv 841 -> 884, K = 1280 projection 839 -> 904,
+    //  q|k|v 848 -> 886; with the GroupNorm-statistics epilogue on a short main loop the lock step of the two CTAs'
+    //  epilogues costs more than the pair saves: temporal conv 761 -> 731, so those stay single)
     const bool k2 = pair_mode != 0 && !use_ew16 && (p.m_tiles % 2) == 0 && (bn % 32) == 0 && (a->N % 32) == 0 &&
-                    num_sms() >= 2 && (a->max_ctas <= 0 || a->max_ctas >= 2);
+                    num_sms() >= 2 && (a->max_ctas <= 0 || a->max_ctas >= 2) &&
+                    !(p.gn_stats && a->mode != MOFA_A_CONV3X3);
     {
         uint64_t dims[2] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(a->N)};
         uint64_t strides[1] = {static_cast<uint64_t>(Ktot) * 2};

@@ -275,7 +275,11 @@ def attn_spatial(qkv, out, frames, L, heads, scale):
     return out
 
 
-FF_FUSED_MAX_C = 320   # TMEM: the output accumulator (C columns) + 128 + 64 must fit 512
+# Widest FeedForward the engine routes through the fused kernel.  The kernel handles C <= 320 (tensor memory: the output
+# accumulator's C columns + 128 + 64 must fit 512) and is correct, but with its N = 128 first MMA and single S buffer it
+# is no faster in the step than the two pipelined GEMMs, so it is opt-in: MOFA_FF_FUSED=1.
+FF_FUSED_LIMIT_C = 320
+FF_FUSED_MAX_C = FF_FUSED_LIMIT_C if os.environ.get("MOFA_FF_FUSED", "0") == "1" else 0
 
 
 def ff_geglu(x, w1_packed, b1_packed, w2, b2, out, res1=None, res2=None, alpha=1.0, beta1=1.0, beta2=1.0):

@@ -29,7 +29,7 @@ DEFAULT_CONFIG = dict(
 # (no GPU in the builder container) switch both through `default_backend(...)` so that UNMODIFIED reference code --
 # e.g. T/run_gradio.py:init_models, which never passes ops= / device= -- can be executed against these classes.
 _BACKEND = {"ops": None, "device": "cuda"}
-PACK_FORMAT = "mofa-b200-pack-v3"   # bump when engine.Net's packed layout changes (invalidates pack caches)
+PACK_FORMAT = "mofa-b200-pack-v4"   # bump when engine.Net's packed layout changes (invalidates pack caches)
 
 
 class default_backend:

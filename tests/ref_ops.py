@@ -110,7 +110,8 @@ def attn_spatial(qkv, out, frames, L, heads, scale):
     return out
 
 
-FF_FUSED_MAX_C = 320
+FF_FUSED_MAX_C = 0      # product default (lib.FF_FUSED_MAX_C): the fused FeedForward is opt-in
+FF_FUSED_LIMIT_C = 320
 
 
 def ff_geglu(x, w1_packed, b1_packed, w2, b2, out, res1=None, res2=None, alpha=1.0, beta1=1.0, beta2=1.0):

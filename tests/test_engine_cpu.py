@@ -69,6 +69,16 @@ def test_engine_rectangular_and_more_frames():
     assert e < 5e-3, f"unet output rel err {e}"
 
 
+def test_engine_fused_feedforward_branch(monkeypatch):
+    """Host logic of the opt-in fused GEGLU FeedForward (128-row GEGLU packing, one call per FeedForward)."""
+    monkeypatch.setattr(ref_ops, "FF_FUSED_MAX_C", ref_ops.FF_FUSED_LIMIT_C)
+    cfg = dict(fixtures.TINY_CONFIG)
+    cfg["num_frames"] = 3
+    r = run_pair(16, 16, cfg)
+    e = rel_err(r["out"], r["ref"])
+    assert e < 5e-3, f"unet output rel err {e}"
+
+
 def test_engine_full_frame_count():
     """T = 25 frames (the SVD-XT clip length: frame-position embedding table, temporal attention / conv over 25 tokens,
     CFG batch of 50 frames) at the tiny channel widths."""

@@ -73,6 +73,15 @@ def test_step_full_width_channels():
     one_step(cfg, 16, 16, 1e-2)
 
 
+def test_step_full_width_channels_fused_feedforward(monkeypatch):
+    """The opt-in fused GEGLU FeedForward (mofa_ff_geglu) on the C = 320 level of the same step."""
+    from mofa_video_b200 import lib
+    monkeypatch.setattr(lib, "FF_FUSED_MAX_C", lib.FF_FUSED_LIMIT_C)
+    n0 = lib.launch_count()
+    one_step(dict(num_frames=2), 16, 16, 1e-2)
+    assert lib.launch_count() > n0
+
+
 def test_step_head_dim_128_generic_attention():
     """Reference class-default head geometry (d = 128 on one level): mofa_attn_small / mofa_attn_small_temporal."""
     cfg = dict(fixtures.TINY_CONFIG)

@@ -43,16 +43,16 @@ elif case == "ff2":
     out = torch.empty(M, 320, dtype=torch.half, device=dev)
     fn = lambda: lib.linear(a, w, out, bias=b, res1=r)
     flops = 2.0 * M * 320 * 1280
-elif case in ("temporal320", "temporal320_stats", "conv320_stats"):
+elif case in ("temporal320", "temporal320_stats", "conv320_stats", "conv320"):
     B, T, HW, C = 2, 25, 9216, 320
     rows = B * T * HW
     a, r = h(rows, C), h(rows, C)
     st = torch.zeros(B * T * 64, device=dev)
     out = torch.empty(rows, C, dtype=torch.half, device=dev)
-    if case == "conv320_stats":
+    if case.startswith("conv320"):
         w, b = h(C, 9 * C, scale=0.03), h(C)
-        fn = lambda: lib.gemm(lib.A_CONV3X3, a, w, out, N=C, n_img=B * T, H=72, W=128, C=C, bias=b, res1=r, gn_stats=st,
-                              gn_rows_per_stat=HW)
+        kw = dict(gn_stats=st, gn_rows_per_stat=HW) if case.endswith("_stats") else {}
+        fn = lambda: lib.gemm(lib.A_CONV3X3, a, w, out, N=C, n_img=B * T, H=72, W=128, C=C, bias=b, res1=r, **kw)
         flops = 2.0 * rows * C * 9 * C
     else:
         w, b = h(C, 3 * C, scale=0.05), h(C)
