@@ -82,8 +82,16 @@ class PeerFrameGather:
                     if box[0] is None:
                         raise RuntimeError("the destination rank could not export its buffer")
                     rebuild, args = box[0]
-                    self.buf = rebuild(*args)                                # dst's memory, mapped into this process
-                    self.ops.peer_enable(self.buf.device.index)              # kernels on OUR device may address it
+                    # Open the handle with OUR device current (argument 6 of rebuild_cuda_tensor is the device the storage
+                    # is opened on): cudaIpcOpenMemHandle(..., cudaIpcMemLazyEnablePeerAccess) then maps dst's memory for
+                    # this GPU.  Opened on dst's device index (what the exporter recorded) the mapping belongs to that
+                    # device's context in this process and a kernel on our GPU faults on it (seen on 2 x B200).
+                    args = list(args)
+                    if not (len(args) >= 8 and isinstance(args[6], int)):
+                        raise RuntimeError("unexpected CUDA IPC descriptor layout from torch.multiprocessing.reductions")
+                    self.ops.peer_enable(args[6])
+                    args[6] = dev.index
+                    self.buf = rebuild(*args)                                # dst's memory, addressable from this GPU
                 except Exception as exc:  # noqa: BLE001
                     err = f"rank {self.rank}: {type(exc).__name__}: {exc}"
             errs = [None] * self.world
