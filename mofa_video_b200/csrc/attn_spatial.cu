@@ -294,15 +294,32 @@ attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
                 asm volatile("bar.sync %0, 64;" ::"r"(bar_mine) : "memory");
                 asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(m_x) : "r"(fence_slot) : "memory");
             }
+            // kPolyEvery: -1 packed-half row sums, no polynomial; 0 / 2 / 4 fp32 sums (and 1/2, 1/4 of the exponentials on
+            // the FMA pipe); 12 / 13 / 14 packed-half sums AND every 2nd / 3rd / 4th PAIR of exponentials on the packed
+            // fp32 FMA pipe (poly_exp2x2).  The score scaling is one FFMA2 per pair in every variant.
+            constexpr bool kHalfSum = kPolyEvery < 0 || kPolyEvery >= 10;
+            constexpr int kPE = kPolyEvery >= 10 ? kPolyEvery - 10 : (kPolyEvery > 0 ? kPolyEvery : 0);
+            const float2 sl2v = make_float2(sl2, sl2), nmv = make_float2(-m_x, -m_x);
 #pragma unroll
             for (int i = 0; i < kCols / 2; ++i) {
-                const float x0 = fmaf(__uint_as_float(s[2 * i]), sl2, -m_x);
-                const float x1 = fmaf(__uint_as_float(s[2 * i + 1]), sl2, -m_x);
-                const bool poly = kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == 0;
-                const float p0 = poly ? poly_exp2(x0) : fast_exp2(x0);
-                const float p1 = poly ? poly_exp2(x1) : fast_exp2(x1);
+                const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), sl2v, nmv);
+                const bool poly = kPE > 0 && (i % (kPE > 0 ? kPE : 1)) == 0;
+                float p0, p1;
+                if (poly) {
+                    if (kPolyEvery >= 10) {
+                        const float2 pp = poly_exp2x2(x);
+                        p0 = pp.x;
+                        p1 = pp.y;
+                    } else {
+                        p0 = poly_exp2(x.x);
+                        p1 = poly_exp2(x.y);
+                    }
+                } else {
+                    p0 = fast_exp2(x.x);
+                    p1 = fast_exp2(x.y);
+                }
                 const __half2 h = __floats2half2_rn(p0, p1);
-                if (kPolyEvery < 0) {
+                if (kHalfSum) {
                     hs[i & 3] = __hadd2(hs[i & 3], h);
                 } else if (i & 1) {
                     sum2 += p0;
@@ -313,7 +330,7 @@ attn_spatial2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Params p) 
                 }
                 packed[i] = *reinterpret_cast<const uint32_t*>(&h);
             }
-            if (kPolyEvery < 0) {
+            if (kHalfSum) {
                 const float2 a = __half22float2(hs[0]), b = __half22float2(hs[1]);
                 const float2 c = __half22float2(hs[2]), d = __half22float2(hs[3]);
                 sum0 = a.x + a.y;
@@ -428,8 +445,9 @@ extern "C" int mofa_attn_spatial(const void* qkv, void* out, int32_t frames, int
     const size_t smem_bytes = 2 * v2::kTile + v2::kKVStages * 2 * v2::kTile + 16 * 8 + 16 +
                               (64 + 256 * 2) * 4 + 2 * 2 * 2 * 128 * 4 + 1024;
     // variants (environment, read once): MOFA_ATTN_SPLIT = 1 | 2 threads per query row, MOFA_ATTN_HANDOFF = 0 | 1
-    // (kSplit 1 only), MOFA_ATTN_POLY = -1 | 0 | 2 | 4 (-1: packed-half row sums; 0: fp32 row sums; 2 / 4: fp32 sums and
-    // 1/2 / 1/4 of the exponentials on the FMA pipe).
+    // (kSplit 1 only), MOFA_ATTN_POLY = -1 | 0 | 2 | 4 | 12 | 13 | 14 (-1: packed-half row sums; 0: fp32 row sums; 2 / 4: fp32
+    // sums and 1/2 / 1/4 of the exponentials on the FMA pipe; 12 / 13 / 14: packed-half sums and every 2nd / 3rd / 4th pair
+    // of exponentials as a packed-fp32 polynomial).
     // Defaults are the measured best on B200 (profiles/).
     using Kern = void (*)(const CUtensorMap, const v2::Params);
     static Kern kern = nullptr;
@@ -438,9 +456,12 @@ extern "C" int mofa_attn_spatial(const void* qkv, void* out, int32_t frames, int
         const char* ep = getenv("MOFA_ATTN_POLY");
         const char* eh = getenv("MOFA_ATTN_HANDOFF");
         const char* es = getenv("MOFA_ATTN_SPLIT");
-        const int poly = ep ? atoi(ep) : -1;  // -1: packed-half row sums (+3.8 % over fp32 sums, same-box A/B)
+        const int poly = ep ? atoi(ep) : 14;  // packed-half row sums, every 3rd pair of exponentials on the packed FMA pipe
+                                               // (same-box A/B at L = 9216: -1 734, 12 746, 13 770, 14 760 TFLOP/s)
         const int split = es ? atoi(es) : 1;
-        const bool handoff = eh ? (eh[0] == '1') : true;
+        // (the MUFU hand-off paid while every exponential was a MUFU op: 734 vs ~700; with a third of them on the FMA pipe
+        //  the pipe is no longer saturated and the barrier only serialises: 771 with, 813 without)
+        const bool handoff = eh ? (eh[0] == '1') : false;
         Kern k;
         if (split == 2) {
             k = poly == 2   ? v2::attn_spatial2_kernel<2, false, 2>
@@ -450,11 +471,20 @@ extern "C" int mofa_attn_spatial(const void* qkv, void* out, int32_t frames, int
             k = poly == 2    ? v2::attn_spatial2_kernel<2, true, 1>
                 : poly == 4  ? v2::attn_spatial2_kernel<4, true, 1>
                 : poly == -1 ? v2::attn_spatial2_kernel<-1, true, 1>
+                : poly == 12 ? v2::attn_spatial2_kernel<12, true, 1>
+                : poly == 13 ? v2::attn_spatial2_kernel<13, true, 1>
+                : poly == 14 ? v2::attn_spatial2_kernel<14, true, 1>
                              : v2::attn_spatial2_kernel<0, true, 1>;
         } else {
-            k = poly == 2   ? v2::attn_spatial2_kernel<2, false, 1>
-                : poly == 4 ? v2::attn_spatial2_kernel<4, false, 1>
-                            : v2::attn_spatial2_kernel<0, false, 1>;
+            k = poly == 2    ? v2::attn_spatial2_kernel<2, false, 1>
+                : poly == 4  ? v2::attn_spatial2_kernel<4, false, 1>
+                : poly == 12 ? v2::attn_spatial2_kernel<12, false, 1>
+                : poly == 13 ? v2::attn_spatial2_kernel<13, false, 1>
+                : poly == 14 ? v2::attn_spatial2_kernel<14, false, 1>
+                : poly == 15 ? v2::attn_spatial2_kernel<15, false, 1>
+                : poly == 16 ? v2::attn_spatial2_kernel<16, false, 1>
+                : poly == -1 ? v2::attn_spatial2_kernel<-1, false, 1>
+                             : v2::attn_spatial2_kernel<0, false, 1>;
         }
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem_bytes));

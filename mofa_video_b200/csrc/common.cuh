@@ -350,6 +350,21 @@ MOFA_DEVICE float poly_exp2(float x) {
     q = fmaf(q, f, 0.99992828f);
     return __int_as_float(__float_as_int(q) + (__float_as_int(r) << 23));
 }
+// two at a time on the packed-fp32 FMA pipe (FFMA2 / FADD2, sm_100): 5 instructions per element instead of 8
+MOFA_DEVICE float2 poly_exp2x2(float2 x) {
+    x.x = fmaxf(x.x, -126.0f);
+    x.y = fmaxf(x.y, -126.0f);
+    const float2 r = __fadd2_rn(x, make_float2(12582912.0f, 12582912.0f));
+    const float2 t = __fadd2_rn(r, make_float2(-12582912.0f, -12582912.0f));
+    const float2 f = __ffma2_rn(t, make_float2(-1.0f, -1.0f), x);
+    float2 q = __ffma2_rn(make_float2(0.05517027f, 0.05517027f), f, make_float2(0.24260795f, 0.24260795f));
+    q = __ffma2_rn(q, f, make_float2(0.69326093f, 0.69326093f));
+    q = __ffma2_rn(q, f, make_float2(0.99992828f, 0.99992828f));
+    float2 o;
+    o.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(r.x) << 23));
+    o.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(r.y) << 23));
+    return o;
+}
 MOFA_DEVICE float fast_rcp(float x) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
