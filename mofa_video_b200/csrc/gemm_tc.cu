@@ -265,7 +265,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // that do not fill a whole round of CTAs (m_tiles mod grid) are dealt out N-fastest again to keep the tail short.
     // (pairs: the same walk over PAIRS of M tiles; both CTAs of a pair see the same sequence, each takes its own half)
     const int grid_i = static_cast<int>(gridDim.x) >> (k2 ? 1 : 0), cta_i = static_cast<int>(blockIdx.x) >> (k2 ? 1 : 0);
-    const int m_sched = p.m_tiles >> (k2 ? 1 : 0);
+    const int m_sched = k2 ? (p.m_tiles + 1) >> 1 : p.m_tiles;   // odd count: the last pair's second CTA runs an empty tile
     const int full_groups = (p.n_tiles > 1 && m_sched / grid_i >= 2) ? m_sched / grid_i : 0;
     const int grouped_tiles = full_groups * p.n_tiles;           // per CTA
     const int tail_tiles = (m_sched - full_groups * grid_i) * p.n_tiles;  // whole grid
@@ -440,7 +440,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 row = (static_cast<long long>(ni) * p.H + y) * p.W + x;
             } else {
                 const int pp = tc.p0 + r;
-                valid = pp < p.HW;
+                valid = pp < p.HW && tc.frame < p.n_img;   // (n_img = B * T here; beyond it only for a pair's empty tile)
                 row = static_cast<long long>(tc.frame) * p.HW + pp;
             }
             const long long group =
@@ -1310,6 +1310,7 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
         Ktot = 3LL * a->C;
         p.T = a->T;
         p.HW = a->HW;
+        p.n_img = a->B * a->T;
         p.tiles_p = (a->HW + BM - 1) / BM;
         p.m_tiles = a->B * a->T * p.tiles_p;
         p.kb_per_tap = a->C / BK;
@@ -1341,8 +1342,13 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
     // (measured, level-0 shapes: 3x3 conv 1150 -> 1244 TFLOP/s, temporal conv 841 -> 884, K = 1280 projection 839 -> 904,
     //  q|k|v 848 -> 886; with the GroupNorm-statistics epilogue on a short main loop the lock step of the two CTAs'
     //  epilogues costs more than the pair saves: temporal conv 761 -> 731, so those stay single)
-    const bool k2 = pair_mode != 0 && !use_ew16 && (p.m_tiles % 2) == 0 && (bn % 32) == 0 && (a->N % 32) == 0 &&
-                    num_sms() >= 2 && (a->max_ctas <= 0 || a->max_ctas >= 2) &&
+    // An odd number of M tiles leaves the last pair's second CTA an empty tile (all loads out of bounds = zeros, every
+    // store clipped / predicated off).
+    // 16-epilogue-warp kernels: GEGLU gains as pairs (K = 320: 963 -> 1005 TFLOP/s), the memory-bound plain projections
+    // lose 5 % (pair_mode 2 forces them on for measurements).  Level-2 shapes with 225 M tiles: GEGLU K = 1280
+    // 1343 -> 1478, K = 5120 projection 1301 -> 1354 (profiles/r2_gemm_pairs_ab.txt).
+    const bool k2 = pair_mode != 0 && (!use_ew16 || geglu || pair_mode == 2) && p.m_tiles >= 2 && (bn % 32) == 0 &&
+                    (a->N % 32) == 0 && num_sms() >= 2 && (a->max_ctas <= 0 || a->max_ctas >= 2) &&
                     !(p.gn_stats && a->mode != MOFA_A_CONV3X3);
     {
         uint64_t dims[2] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(a->N)};
@@ -1367,18 +1373,19 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
         const long long n_stat = (rows_total + p.gn_rows_per_stat - 1) / p.gn_rows_per_stat;
         cudaMemsetAsync(p.gn_stats, 0, sizeof(float) * 2 * p.gn_groups * n_stat, stream);
     }
-    const long long total = static_cast<long long>(p.m_tiles) * p.n_tiles;
+    const long long total = static_cast<long long>(k2 ? ((p.m_tiles + 1) & ~1) : p.m_tiles) * p.n_tiles;
     int grid = num_sms();
     if (a->max_ctas > 0 && a->max_ctas < grid) grid = a->max_ctas;
     if (total < grid) grid = static_cast<int>(total);
     if (k2) grid &= ~1;   // whole pairs (total is even: m_tiles is)
 
     using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmKernelParams);
-    static const Kern kernels[10] = {gemm_tc_kernel<0, false, 8, false>, gemm_tc_kernel<0, true, 8, false>,
+    static const Kern kernels[12] = {gemm_tc_kernel<0, false, 8, false>, gemm_tc_kernel<0, true, 8, false>,
                                      gemm_tc_kernel<1, false, 8, false>, gemm_tc_kernel<2, false, 8, false>,
                                      gemm_tc_kernel<1, false, 16, false>, gemm_tc_kernel<0, false, 16, false>,
                                      gemm_tc_kernel<0, false, 8, true>, gemm_tc_kernel<0, true, 8, true>,
-                                     gemm_tc_kernel<1, false, 8, true>, gemm_tc_kernel<2, false, 8, true>};
+                                     gemm_tc_kernel<1, false, 8, true>, gemm_tc_kernel<2, false, 8, true>,
+                                     gemm_tc_kernel<1, false, 16, true>, gemm_tc_kernel<0, false, 16, true>};
     static bool configured = false;
     if (!configured) {
         for (Kern k : kernels) {
@@ -1398,12 +1405,12 @@ extern "C" int mofa_gemm(const mofa_gemm_args* a, mofa_stream_t stream_) {
     // longer main loops the 8-warp unrolled body is faster (GEGLU K = 640: 1180 vs 1092, K = 1280: 1410 vs 1333)
     const bool geglu16 = use_ew16;
     const int base = geglu ? 2 : (a->act != 0 ? 3 : (p.gn_stats ? 1 : 0));
-    const Kern kern = use_ew16 ? (geglu ? kernels[4] : kernels[5]) : kernels[base + (k2 ? 6 : 0)];
+    const Kern kern = use_ew16 ? (geglu ? kernels[k2 ? 10 : 4] : kernels[k2 ? 11 : 5]) : kernels[base + (k2 ? 6 : 0)];
     if (k2) {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(kGemmThreads);
+        cfg.blockDim = dim3(geglu16 ? 64 + 32 * 16 : kGemmThreads);
         cfg.dynamicSmemBytes = smem_bytes;
         cfg.stream = stream;
         cudaLaunchAttribute attr[1];

@@ -38,6 +38,18 @@ elif case == "proj320rb":  # attention out-projection + collapsed cross-attentio
     out = torch.empty(M, 320, dtype=torch.half, device=dev)
     fn = lambda: lib.linear(a, w, out, bias=b, res1=r, rowbias=rb, rows_per_group=M // 2)
     flops = 2.0 * M * 320 * 320
+elif case == "geglu1280":   # level 2: 225 M tiles (odd)
+    M = 28800
+    a, w, b = h(M, 1280), h(10240, 1280, scale=0.03), h(10240)
+    out = torch.empty(M, 5120, dtype=torch.half, device=dev)
+    fn = lambda: lib.linear(a, w, out, bias=b, act=2, bn=256)
+    flops = 2.0 * M * 10240 * 1280
+elif case == "lin5120":     # level 2 FeedForward output projection
+    M = 28800
+    a, w, b, r = h(M, 5120), h(1280, 5120, scale=0.02), h(1280), h(M, 1280)
+    out = torch.empty(M, 1280, dtype=torch.half, device=dev)
+    fn = lambda: lib.linear(a, w, out, bias=b, res1=r)
+    flops = 2.0 * M * 1280 * 5120
 elif case == "ff2":
     a, w, b, r = h(M, 1280), h(320, 1280), h(320), h(M, 320)
     out = torch.empty(M, 320, dtype=torch.half, device=dev)
