@@ -61,7 +61,9 @@ KEEP = re.compile(r"dram__bytes_(read|write)\.sum$|gpu__time_duration\.sum|sm__p
                   r"sm__inst_executed_pipe_(xu|fma|alu).*pct|smsp__issue_active.*pct|sm__warps_active.*pct|"
                   r"launch__registers_per_thread|launch__shared_mem_per_block_dynamic|lts__t_sector_hit_rate.pct|"
                   r"smsp__average_warps_issue_stalled_.*_per_issue_active|sm__throughput.*pct|smsp__inst_executed.sum$|"
-                  r"l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum$|gpu__dram_throughput.*pct|sm__cycles_active.avg$")
+                  r"l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum$|gpu__dram_throughput.*pct|sm__cycles_active.avg$|"
+                  r"l1tex__m_xbar2l1tex_read_bytes.sum$|l1tex__m_xbar2l1tex_read_bytes.sum.pct_of_peak_sustained_elapsed|"
+                  r"lts__throughput.avg.pct_of_peak_sustained_elapsed|launch__cluster_size|sm__cycles_elapsed.max$")
 
 
 def full(path):
@@ -74,7 +76,7 @@ def full(path):
     r = data[0]
     for k in ("Kernel Name", "Block Size", "Grid Size"):
         if k in r:
-            print(f"{k},,\\"{r[k]}\\"")
+            print(f'{k},,"{r[k]}"')
     for k in sorted(hdr):
         if KEEP.search(k):
             print(f"{k},{units.get(k, '')},{r[k]}")
