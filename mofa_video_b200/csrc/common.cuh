@@ -413,6 +413,28 @@ MOFA_DEVICE float gelu_erf_relu_form(float x) {
     const float q = (poly * t) * e;
     return fmaf(-ax, q, fmaxf(x, 0.0f));
 }
+// GEGLU of two adjacent columns on the packed-fp32 pipe (FFMA2 / FMUL2 / FADD2): (v + bv) * gelu(g + bg), the same
+// arithmetic as gelu_erf_relu_form per element, ~13 issue slots per element instead of ~19 (the GEGLU epilogues are
+// issue-bound: 16 epilogue warps at K = 320)
+MOFA_DEVICE float2 geglu2(float2 v, float2 g, __half2 bv, __half2 bg) {
+    const float2 x = __fadd2_rn(g, __half22float2(bg));
+    const float2 val = __fadd2_rn(v, __half22float2(bv));
+    const float2 nax = make_float2(-fabsf(x.x), -fabsf(x.y));
+    const float kk = 0.3275911f * 0.70710678118654752440f;
+    const float2 d = __ffma2_rn(make_float2(-kk, -kk), nax, make_float2(1.0f, 1.0f));
+    const float2 t = make_float2(fast_rcp(d.x), fast_rcp(d.y));
+    float2 poly = __ffma2_rn(make_float2(0.5f * 1.061405429f, 0.5f * 1.061405429f), t,
+                             make_float2(0.5f * -1.453152027f, 0.5f * -1.453152027f));
+    poly = __ffma2_rn(poly, t, make_float2(0.5f * 1.421413741f, 0.5f * 1.421413741f));
+    poly = __ffma2_rn(poly, t, make_float2(0.5f * -0.284496736f, 0.5f * -0.284496736f));
+    poly = __ffma2_rn(poly, t, make_float2(0.5f * 0.254829592f, 0.5f * 0.254829592f));
+    const float ce = -0.5f * 1.4426950408889634f;
+    const float2 ea = __fmul2_rn(__fmul2_rn(x, x), make_float2(ce, ce));
+    const float2 e = make_float2(fast_exp2(ea.x), fast_exp2(ea.y));
+    const float2 q = __fmul2_rn(__fmul2_rn(poly, t), e);
+    const float2 gelu = __ffma2_rn(nax, q, make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f)));
+    return __fmul2_rn(val, gelu);
+}
 MOFA_DEVICE float erf_fast(float x) { return 2.0f * gelu_phi(x * 1.41421356237309504880f) - 1.0f; }
 
 }  // namespace mofa

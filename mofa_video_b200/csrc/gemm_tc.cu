@@ -595,11 +595,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         H8 o;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const float y0 = (va[2 * j] + __half2float(bv.h[2 * j])) *
-                                             gelu_erf_relu_form(ga[2 * j] + __half2float(bg.h[2 * j]));
-                            const float y1 = (va[2 * j + 1] + __half2float(bv.h[2 * j + 1])) *
-                                             gelu_erf_relu_form(ga[2 * j + 1] + __half2float(bg.h[2 * j + 1]));
-                            o.h2[j] = __floats2half2_rn(y0, y1);
+                            const float2 y = geglu2(make_float2(va[2 * j], va[2 * j + 1]),
+                                                    make_float2(ga[2 * j], ga[2 * j + 1]), bv.h2[j], bg.h2[j]);
+                            o.h2[j] = __floats2half2_rn(y.x, y.y);
                         }
                         // 64-byte rows, SWIZZLE_64B: 16-byte chunk g of row r lives at chunk g ^ ((r >> 1) & 3)
                         *reinterpret_cast<uint4*>(stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = o.u;
@@ -659,11 +657,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 H8 o;
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
-                                    const float y0 = (va[2 * j] + __half2float(bv.h[2 * j])) *
-                                                     gelu_erf_relu_form(ga[2 * j] + __half2float(bg.h[2 * j]));
-                                    const float y1 = (va[2 * j + 1] + __half2float(bv.h[2 * j + 1])) *
-                                                     gelu_erf_relu_form(ga[2 * j + 1] + __half2float(bg.h[2 * j + 1]));
-                                    o.h2[j] = __floats2half2_rn(y0, y1);
+                                    const float2 y = geglu2(make_float2(va[2 * j], va[2 * j + 1]),
+                                                            make_float2(ga[2 * j], ga[2 * j + 1]), bv.h2[j], bg.h2[j]);
+                                    o.h2[j] = __floats2half2_rn(y.x, y.y);
                                 }
                                 const int ci = hlf * 4 + g;
                                 *reinterpret_cast<uint4*>(stg + lane * 128 + ((ci ^ (lane & 7)) << 4)) = o.u;
@@ -728,10 +724,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     bv.u = bvv[g];
                                     bg.u = bgv[g];
 #pragma unroll
-                                    for (int j = 0; j < 8; ++j) {
-                                        const float val = __uint_as_float(acc[g * 8 + j]) + __half2float(bv.h[j]);
-                                        const float gate = __uint_as_float(ag[g * 8 + j]) + __half2float(bg.h[j]);
-                                        v[g * 8 + j] = val * gelu_erf_relu_form(gate);
+                                    for (int j = 0; j < 4; ++j) {
+                                        const float2 y = geglu2(
+                                            make_float2(__uint_as_float(acc[g * 8 + 2 * j]), __uint_as_float(acc[g * 8 + 2 * j + 1])),
+                                            make_float2(__uint_as_float(ag[g * 8 + 2 * j]), __uint_as_float(ag[g * 8 + 2 * j + 1])),
+                                            bv.h2[j], bg.h2[j]);
+                                        v[g * 8 + 2 * j] = y.x;
+                                        v[g * 8 + 2 * j + 1] = y.y;
                                     }
                                 }
                             } else {
