@@ -464,9 +464,12 @@ extern "C" int mofa_attn_spatial(const void* qkv, void* out, int32_t frames, int
         const bool handoff = eh ? (eh[0] == '1') : false;
         Kern k;
         if (split == 2) {
-            k = poly == 2   ? v2::attn_spatial2_kernel<2, false, 2>
-                : poly == 4 ? v2::attn_spatial2_kernel<4, false, 2>
-                            : v2::attn_spatial2_kernel<0, false, 2>;
+            k = poly == 2    ? v2::attn_spatial2_kernel<2, false, 2>
+                : poly == 4  ? v2::attn_spatial2_kernel<4, false, 2>
+                : poly == 13 ? v2::attn_spatial2_kernel<13, false, 2>
+                : poly == 14 ? v2::attn_spatial2_kernel<14, false, 2>
+                : poly == -1 ? v2::attn_spatial2_kernel<-1, false, 2>
+                             : v2::attn_spatial2_kernel<0, false, 2>;
         } else if (handoff) {
             k = poly == 2    ? v2::attn_spatial2_kernel<2, true, 1>
                 : poly == 4  ? v2::attn_spatial2_kernel<4, true, 1>
