@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for pv in 14 15 16 14; do
-  echo -n "HANDOFF=0 POLY=$pv "
-  MOFA_ATTN_POLY=$pv timeout 100 python tools/prof_attn_case.py 2>&1 | tail -1
-done | tee gpurun_out/r2_attn_variants4.txt
+for sp in 1 2; do for pv in 14 13 -1; do
+  echo -n "SPLIT=$sp POLY=$pv "
+  MOFA_ATTN_SPLIT=$sp MOFA_ATTN_POLY=$pv timeout 100 python tools/prof_attn_case.py 2>&1 | tail -1
+done; done | tee gpurun_out/r2_attn_variants5.txt
