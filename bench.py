@@ -399,6 +399,11 @@ def run_engine(args):
                "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(out), flush=True)
     if world > 1:
+        if gather is not None:
+            try:
+                gather.close()
+            except Exception:  # noqa: BLE001  (shutdown only: the line is already printed)
+                pass
         dist.destroy_process_group()
 
 

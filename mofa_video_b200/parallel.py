@@ -143,6 +143,18 @@ class PeerFrameGather:
         assert self.rank == self.dst
         self.ops.peer_signal(self.consumed, self.epoch)
 
+    def close(self):
+        """Collective: importers drop their mapping of dst's buffer before dst frees it (otherwise the exporting process
+        warns that it terminated with shared CUDA tensors outstanding)."""
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        if self.rank != self.dst:
+            self.flags = self.ready = self.consumed = None
+            self.buf = None
+        if self.world > 1:
+            dist.barrier()
+
     def check(self):
         """After a synchronize: raise if a wait gave up (a peer died or never published)."""
         v = int(self.timed_out.item())
