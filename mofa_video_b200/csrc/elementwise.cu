@@ -4,6 +4,7 @@
 #include "../../include/mofa_b200.h"
 #include <stdlib.h>
 
+#include <cstdlib>
 #include "common.cuh"
 
 namespace mofa {
@@ -119,7 +120,7 @@ groupnorm_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __re
     }
 }
 
-template <int kU, int kMinBlocks>
+template <int kU, int kMinBlocks, bool kPrefetch>
 __global__ void __launch_bounds__(256, kMinBlocks)
 groupnorm_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2,
                        const __half* __restrict__ gamma, const __half* __restrict__ beta, __half* __restrict__ out,
@@ -164,12 +165,17 @@ groupnorm_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __re
                 sc[j] = rstd * __half2float(gm.h[j]);
                 sh[j] = __half2float(bt.h[j]) - mean * sc[j];
             }
+            // Two batches of kU rows in flight: the next batch is requested before the current one is normalised, so the
+            // DRAM round trip overlaps the math and the stores instead of being exposed once per batch.
             long long r = r_begin + ty;
-            for (; r + static_cast<long long>(kU - 1) * VY < r_end; r += static_cast<long long>(kU) * VY) {
-                V8 v[kU];
+            const long long step = static_cast<long long>(kU) * VY;
+            auto full = [&](long long rr) { return rr + static_cast<long long>(kU - 1) * VY < r_end; };
+            auto load = [&](V8 (&v)[kU], long long rr) {
 #pragma unroll
                 for (int u = 0; u < kU; ++u)
-                    v[u].u = __ldg(reinterpret_cast<const uint4*>(base + (r + static_cast<long long>(u) * VY) * ld));
+                    v[u].u = __ldg(reinterpret_cast<const uint4*>(base + (rr + static_cast<long long>(u) * VY) * ld));
+            };
+            auto process = [&](const V8 (&v)[kU], long long rr) {
 #pragma unroll
                 for (int u = 0; u < kU; ++u) {
                     V8 o;
@@ -184,8 +190,31 @@ groupnorm_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __re
                         }
                         o.h2[j] = __floats2half2_rn(y0, y1);
                     }
-                    *reinterpret_cast<uint4*>(obase + (r + static_cast<long long>(u) * VY) * C) = o.u;
+                    *reinterpret_cast<uint4*>(obase + (rr + static_cast<long long>(u) * VY) * C) = o.u;
                 }
+            };
+            if constexpr (!kPrefetch) {   // one batch at a time (round-1 loop; kept for same-box A/Bs: MOFA_GN_APPLY=2)
+                for (; full(r); r += step) {
+                    V8 v[kU];
+                    load(v, r);
+                    process(v, r);
+                }
+            }
+            V8 va[kU], vb[kU];
+            bool ha = kPrefetch && full(r);
+            if (ha) load(va, r);
+            while (ha) {
+                const long long r2 = r + step;
+                const bool hb = full(r2);
+                if (hb) load(vb, r2);
+                process(va, r);
+                r = r2;
+                if (!hb) break;
+                const long long r3 = r2 + step;
+                ha = full(r3);
+                if (ha) load(va, r3);
+                process(vb, r2);
+                r = r3;
             }
             for (; r < r_end; r += VY) {
                 V8 v, o;
@@ -569,11 +598,25 @@ extern "C" int mofa_groupnorm(const void* x1, int32_t C1, const void* x2, int32_
     // apply pass: 4 loads of 16 bytes in flight per thread, 3 blocks per SM.  Round-2 microbenchmark of (2 loads, 4 blocks),
     // (2, 6), (1, 8) register / occupancy trade-offs: equal or slower (4.17 TB/s at level 0 for the first two, 3.8 / 3.5 for
     // the spilling ones; profiles/r2_groupnorm_variants.txt)
-    plan(8, 3, rpb, sps, n_slabs, grid);
-    groupnorm_apply_kernel<4, 3><<<grid, block, 0, stream>>>(
-        static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2, static_cast<const __half*>(gamma),
-        static_cast<const __half*>(beta), static_cast<__half*>(out), rows_per_stat, rpb, sps, n_slabs, groups, eps, silu,
-        stats);
+    // (24 rows per thread where that still leaves two waves of slabs: amortises the per-slab scale / shift set-up and gives
+    //  the prefetch something to run ahead on)
+    static int variant = -1;
+    if (variant < 0) {
+        const char* e = getenv("MOFA_GN_APPLY");
+        variant = e ? atoi(e) : 0;
+    }
+    const int bps = variant == 0 ? 2 : 3;
+    plan(variant == 2 ? 8 : 24, bps, rpb, sps, n_slabs, grid);
+    if (n_slabs < 2 * 148LL * bps) plan(8, bps, rpb, sps, n_slabs, grid);
+#define GN_APPLY(KU, MB, PF)                                                                                            \
+    groupnorm_apply_kernel<KU, MB, PF><<<grid, block, 0, stream>>>(                                                     \
+        static_cast<const __half*>(x1), C1, static_cast<const __half*>(x2), C2, static_cast<const __half*>(gamma),      \
+        static_cast<const __half*>(beta), static_cast<__half*>(out), rows_per_stat, rpb, sps, n_slabs, groups, eps, silu, \
+        stats)
+    if (variant == 0) GN_APPLY(4, 2, true);
+    else if (variant == 1) GN_APPLY(3, 3, true);
+    else GN_APPLY(4, 3, false);
+#undef GN_APPLY
     return check_launch("mofa_groupnorm(apply)");
 }
 
