@@ -256,6 +256,9 @@ int mofa_resize_antialias(const void* img, void* out, int32_t planes, int32_t H,
 int mofa_ff_geglu(const void* x, const void* w1_packed, const void* b1_packed, const void* w2, const void* b2, void* out,
                   int64_t M, int32_t C, int32_t hidden, const void* res1, int64_t ldr1, const void* res2, int64_t ldr2,
                   float alpha, float beta1, float beta2, mofa_stream_t stream);
+/* Profiling support for the kernel above (no reference counterpart): with MOFA_FF_DEBUG including 2048, block 0 records a
+ * clock64() stamp per pipeline stage for its first 64 hidden chunks; this copies the 64 x 16 stamps to host_out. */
+int mofa_ff_debug_dump(long long* host_out);
 
 /* Multi-head self-attention for small sequences and head dims other than 64 (CLIP ViT-H/14 image encoder of
  * /root/reference/MOFA-Video-Traj/pipeline/pipeline.py:114-141: 16 heads x 80, 257 tokens): qkv fp16 [n_seq, L, 3*C]

@@ -25,7 +25,7 @@ EXPORTS = [
     "mofa_vae_time_conv_out", "mofa_im2col", "mofa_pool2d", "mofa_resize_bilinear_ac", "mofa_cmp_fuser",
     "mofa_copy_cols", "mofa_flow_pyramid", "mofa_mask_blend", "mofa_downsample_nearest", "mofa_flow_post",
     "mofa_resize_antialias", "mofa_cfg_euler_step_dev", "mofa_sparse_hints", "mofa_peer_enable", "mofa_peer_signal", "mofa_peer_wait",
-    "mofa_attn_small", "mofa_attn_small_temporal", "mofa_ff_geglu",
+    "mofa_attn_small", "mofa_attn_small_temporal", "mofa_ff_geglu", "mofa_ff_debug_dump",
 ]
 
 

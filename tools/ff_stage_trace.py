@@ -26,8 +26,7 @@ for _ in range(2):
     lib.ff_geglu(x, w1, b1, w2, b2, out, res1=r)
 torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 1024)()
-so = ctypes.CDLL(os.path.join(os.path.dirname(lib.__file__), "libmofa_b200.so"))
-assert so.mofa_ff_debug_dump(buf) == 0
+assert lib.load().mofa_ff_debug_dump(buf) == 0
 v = [[buf[g * 16 + s] for s in range(14)] for g in range(64)]
 t0 = v[2][0]
 names = ["m_sfree", "m_s_iss", "m_hfull", "m_o_iss", "e_sfull", "e_ld", "e_math", "e_hfull", "m_top", "l_sfull", "l_ld",
